@@ -1,0 +1,147 @@
+/* cpfem.h - C ABI of the B200-native JAX-CPFEM hot path (libcpfem_b200.so).
+ *
+ * Drop-in boundary: every entry point takes plain DEVICE pointers, sizes and a CUDA stream (as an opaque
+ * void*), is enqueue-only (no device synchronisation, no allocation on the hot path) and returns an int
+ * status (0 = OK, <0 = hard error, text via cpfem_last_error).  These are the functions an XLA-FFI /
+ * ctypes / cffi binding of the reference's hot path would bind (INTEGRATION.md shows the stubs).
+ *
+ * Reference interfaces replaced (paths relative to the JAX-CPFEM tree; jax_fem = deepmodeling/jax-fem,
+ * imported by the reference at singlecrystal_copper/models_copper.py:9 but not vendored):
+ *
+ *   cpfem_plan_create / cpfem_plan_csr   jax_fem Problem.__post_init__ I/J construction (consumed at
+ *                                        crystal_plasticity_OR_design/solver.py:281) + the scipy COO->CSR
+ *                                        canonicalisation of get_A (solver.py:279-288)
+ *   cpfem_update_state                   CrystalPlasticity.update_int_vars_gp   (models_copper.py:273-282)
+ *   cpfem_residual                       Problem.compute_residual               (solver.py:244,715,807)
+ *   cpfem_newton_update                  Problem.newton_update -> res, V        (solver.py:392,281)
+ *                                        + get_A's CSR data                     (solver.py:281)
+ *   cpfem_avg_stress                     CrystalPlasticity.compute_avg_stress   (models_copper.py:297-319)
+ *   cpfem_point_stress_tangent           get_tensor_map()'s tensor_map under vmap, and its jacfwd
+ *                                        (models_copper.py:135-137,155-162,251-265)
+ *   cpfem_apply_dirichlet                apply_bc_vec + zeroRows                (solver.py:119-133,290-293)
+ */
+#ifndef CPFEM_H
+#define CPFEM_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPFEM_MAX_SLIP 24
+
+/* Uniform material constants (field meaning: models_copper.py:54-56,94-96,141-149,212,231). */
+typedef struct cpfem_material {
+    double C11, C12, C44;
+    double h, t_sat, gss_a, ao, xm, r;
+    double tol;          /* local Newton tolerance (1e-8)                     */
+    int32_t max_sub_step; /* 5 (Cu, Ta, DP) or 8 (304 steel)                  */
+    int32_t max_iter;     /* safety cap on local Newton iterations (e.g. 200) */
+} cpfem_material;
+
+/* State layout of the (point, component) arrays. */
+enum { CPFEM_LAYOUT_AOS = 0,   /* reference layout: (nc, 8, comps) C-contiguous        */
+       CPFEM_LAYOUT_SOA = 1 }; /* native layout:    (comps, nc*8)   C-contiguous        */
+
+/* Quadrature-point state, same order as the reference's internal_vars list
+ * (models_copper.py:133; models_DPsteel_inhomo.py:229).  The six trailing pointers are the per-point
+ * material arrays of the DP-steel / calibration variants; pass NULL to use cpfem_material instead.
+ * C, when given, is the (nc,8,3,3,3,3) elastic tensor array; it must be cubic in the crystal frame
+ * (only C[0,0,0,0], C[0,0,1,1], C[1,2,1,2] are read), which is what the reference builds. */
+typedef struct cpfem_state {
+    const double* Fp_inv;   /* (np, 9)  */
+    const double* g;        /* (np, ns) slip resistance */
+    const double* slip;     /* (np, ns) accumulated slip */
+    const double* rot;      /* (np, 9)  */
+    const double* gss_a;    /* (np) or NULL */
+    const double* h;        /* (np) or NULL */
+    const double* t_sat;    /* (np) or NULL */
+    const double* xm;       /* (np) or NULL */
+    const double* r;        /* (np) or NULL */
+    const double* C;        /* (np, 81) or NULL */
+    int32_t layout;         /* CPFEM_LAYOUT_* for Fp_inv, g, slip, rot */
+} cpfem_state;
+
+typedef struct cpfem_state_out {
+    double* Fp_inv;         /* (np, 9)  */
+    double* g;              /* (np, ns) */
+    double* slip;           /* (np, ns) */
+    int32_t layout;
+} cpfem_state_out;
+
+/* status words written by the kernels (device memory, 4 x int64, accumulated with atomics; zero it first):
+ *   [0] points that hit max_iter   [1] points with a non-finite residual
+ *   [2] max local Newton iterations seen   [3] sum of local Newton iterations */
+#define CPFEM_STATUS_WORDS 4
+
+typedef struct cpfem_plan cpfem_plan;
+
+/* Build the per-mesh plan on the current device: keeps device copies of the connectivity and node
+ * coordinates, the CSR pattern (bit-identical to scipy.sparse.csr_array((V,(I,J))) with the jax_fem I/J
+ * rule: columns sorted, duplicates merged, explicit zeros kept) and the per-cell slot map.
+ *   cells   device int32 (nc, 8), hex8 in meshio/Gmsh node order
+ *   points  device double (nnodes, 3)
+ *   slip    HOST double (ns, 6): rows "normal(3) direction(3)" as in data/csv/input_slip_sys*.txt
+ *           (normalised internally, models_copper.py:62-66) */
+int cpfem_plan_create(const int32_t* cells, int64_t nc, const double* points, int64_t nnodes,
+                      const double* slip, int32_t ns, void* stream, cpfem_plan** out);
+int cpfem_plan_destroy(cpfem_plan* plan);
+
+/* CSR pattern owned by the plan (device pointers). indptr has 3*nnodes+1 entries. */
+int cpfem_plan_csr(const cpfem_plan* plan, const int64_t** indptr, const int32_t** indices, int64_t* nnz);
+/* Sizes: nc, nnodes, ns, nnz, max node valence. out[5]. */
+int cpfem_plan_info(const cpfem_plan* plan, int64_t* out);
+
+/* update_int_vars_gp: sol (nnodes,3) + old state -> new state.  in/out may alias array-wise. */
+int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* in,
+                       const cpfem_state_out* out, double dt, int64_t* status, void* stream);
+
+/* compute_residual: res (nnodes,3) is OVERWRITTEN (zeroed inside, then accumulated). */
+int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* st,
+                   double dt, double* res, int64_t* status, void* stream);
+
+/* newton_update: res (nnodes,3) and csr_data (nnz) are overwritten with the residual and the assembled
+ * tangent on the plan's pattern.  coo_V, if not NULL, receives the reference's problem.V layout
+ * (nc, 24, 24): V[c, 3a+i, 3b+k].  Either of csr_data / coo_V may be NULL. */
+int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* st,
+                        double dt, double* res, double* csr_data, double* coo_V, int64_t* status, void* stream);
+
+/* compute_avg_stress: sigma_cell (nc, 9) = JxW-weighted mean Cauchy stress per cell. */
+int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* st,
+                     double dt, double* sigma_cell, int64_t* status, void* stream);
+
+/* tensor_map under vmap: u_grads (np, 9) given explicitly -> P (np, 9) and, if tangent != NULL,
+ * dP_ij/dH_kl (np, 81).  np need not be a multiple of 8; the plan only supplies the slip table. */
+int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads,
+                               int64_t np, const cpfem_state* st, double dt, double* P, double* tangent,
+                               int64_t* status, void* stream);
+
+/* Row-elimination Dirichlet conditions on device: res[row] = sol[row] - val  (apply_bc_vec) and, if
+ * csr_data != NULL, row := unit row (zeroRows with diag 1).  rows: device int64 (nbc) dof indices. */
+int cpfem_apply_dirichlet(const cpfem_plan* plan, const int64_t* rows, const double* vals, int64_t nbc,
+                          const double* sol, double* res, double* csr_data, void* stream);
+
+/* Interface exchange helper for element-partitioned runs: dst[map[i]] += src[i]. */
+int cpfem_scatter_add(const double* src, const int64_t* map, int64_t n, double* dst, void* stream);
+/* Pack helper: dst[i] = src[map[i]]. */
+int cpfem_gather(const double* src, const int64_t* map, int64_t n, double* dst, void* stream);
+/* sum of squares of a device vector into out[0] (device double, accumulated atomically; zero it first). */
+int cpfem_sumsq(const double* x, int64_t n, double* out, void* stream);
+
+/* Layout conversion (np, comps) <-> (comps, np). */
+int cpfem_aos_to_soa(const double* aos, int64_t np, int32_t comps, double* soa, void* stream);
+int cpfem_soa_to_aos(const double* soa, int64_t np, int32_t comps, double* aos, void* stream);
+
+/* FP64 FMA throughput microbenchmark used for the roofline denominator: runs `iters` dependent-chain
+ * DFMA rounds on every SM and returns the flop count in *flops (time it with CUDA events). */
+int cpfem_dfma_peak_kernel(int64_t iters, double* sink, double* flops, void* stream);
+
+const char* cpfem_last_error(void);
+int cpfem_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPFEM_H */

@@ -1,0 +1,491 @@
+// Per-quadrature-point Kalidindi crystal-plasticity update, hand-derived, fp64.
+//
+// Replaces (reference JAX-CPFEM, paths relative to its tree):
+//   helper             singlecrystal_copper/models_copper.py:172-192
+//   implicit_residual  singlecrystal_copper/models_copper.py:195-201
+//   newton_solver      singlecrystal_copper/models_copper.py:204-249   (literal control flow)
+//   f_jvp              singlecrystal_copper/models_copper.py:251-259   (implicit-function tangent)
+//   first_PK_stress    singlecrystal_copper/models_copper.py:155-162
+//   update_int_vars    singlecrystal_copper/models_copper.py:164-169
+// and the per-point-parameter form polycrystal_DPsteel/models_DPsteel_inhomo.py:240-361.
+//
+// Formulation (see DESIGN.md "Per-point algebra"): everything is done in the CRYSTAL frame, where the
+// Schmid tensors are the constant d (x) n of the slip table and the elastic tensor is cubic
+// (C11, C12, C44).  With  Fc = R^T F R,  Ac = R^T Fp_inv_old R,  G = Fc Ac  the reference's residual
+// r(S) = S - rot4(R,C) : 1/2 (Fe^T Fe - I) becomes  r_c(S_c) = S_c - C : 1/2 (Fe_c^T Fe_c - I)  with
+// Fe_c = G (I - sum_a dgamma_a d_a n_a^T); its Frobenius norm, the Newton iterates and the line-search
+// decisions are those of the reference up to rounding.  All iterates are symmetric (r and the Newton
+// increment are), so the unknown is the 6-vector s = (S00,S11,S22,S12,S02,S01) and the 9x9 solve of the
+// reference collapses to a 6x6 one.  The Newton matrix J = I + sum_a w_a (C:e_a) p_a^T is solved in the
+// scaled form  N z = -C^-1 r,  N = C^-1 D^-1 + sum_a w_a e_a etilde_a^T,  inc = D^-1 z  (D = diag(1,1,1,2,2,2)),
+// which is symmetric positive definite up to O(strain) terms, so the LU needs no pivoting.
+//
+// The functions are __host__ __device__ so that tests can compile this header with g++ and compare the
+// algebra with the oracle on a machine without a GPU (tests/hostcheck).  The product only ever calls
+// them from the CUDA kernels in cpfem_kernels.cu.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define CP_HD __host__ __device__ __forceinline__
+#else
+#define CP_HD inline
+#endif
+
+#define CP_MAX_NS 24
+
+// Uniform material description.  Per-point overrides (DP steel) come through CpPointParams.
+struct CpMaterial {
+    double C11, C12, C44;   // cubic elastic constants (models_copper.py:94-96)
+    double h;               // hardening modulus            (:141)
+    double t_sat;           // saturation slip resistance   (:143)
+    double gss_a;           // hardening exponent           (:145)
+    double ao;              // reference slip rate          (:147)
+    double xm;              // rate sensitivity; exponent is 1/xm (:149,174)
+    double r;               // latent hardening ratio       (:54)
+    double tol;             // local Newton tolerance       (:212)
+    int max_sub_step;       // line-search halvings         (:231)
+    int max_iter;           // safety cap (reference has none; hitting it is reported in the status word)
+};
+
+// Normalised slip normals / directions of the crystal (models_copper.py:62-66), passed by value as a
+// kernel parameter so that every access is a uniform constant-bank read.
+struct CpSlip {
+    double d[CP_MAX_NS * 3];
+    double n[CP_MAX_NS * 3];
+};
+
+struct CpPointParams {   // per-point values actually used at one quadrature point
+    double C11, C12, C44, h, t_sat, gss_a, n_exp /* = 1/xm */, r;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// small 3x3 helpers (row-major double[9])
+// ---------------------------------------------------------------------------------------------------
+CP_HD void m3_mul(const double* A, const double* B, double* C) {          // C = A B
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+CP_HD void m3_mul_tn(const double* A, const double* B, double* C) {       // C = A^T B
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+}
+CP_HD void m3_mul_nt(const double* A, const double* B, double* C) {       // C = A B^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
+}
+CP_HD double m3_det(const double* M) {
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+CP_HD void m3_inv(const double* M, double* Mi, double* det_out) {
+    double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
+    double id = 1.0 / det;
+    Mi[0] = c00 * id; Mi[1] = (M[2] * M[7] - M[1] * M[8]) * id; Mi[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    Mi[3] = c01 * id; Mi[4] = (M[0] * M[8] - M[2] * M[6]) * id; Mi[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    Mi[6] = c02 * id; Mi[7] = (M[1] * M[6] - M[0] * M[7]) * id; Mi[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+    *det_out = det;
+}
+// Voigt map used throughout: 0:(0,0) 1:(1,1) 2:(2,2) 3:(1,2) 4:(0,2) 5:(0,1)
+CP_HD void sym6_to_m3(const double* s, double* S) {
+    S[0] = s[0]; S[4] = s[1]; S[8] = s[2];
+    S[5] = S[7] = s[3]; S[2] = S[6] = s[4]; S[1] = S[3] = s[5];
+}
+
+// |x|^e for x >= 0.  Exactly-integer exponents (9, 19, 119 for the Cu/DP/304 parameter sets) take the
+// square-and-multiply path; everything else (tantalum: 44.2726) goes through pow().
+CP_HD double cp_pow_pos(double x, double e) {
+    if (e == floor(e) && e >= 0.0 && e < 2048.0) {
+        int k = (int)e;
+        double r = 1.0;
+        while (k) {
+            if (k & 1) r *= x;
+            x *= x;
+            k >>= 1;
+        }
+        return r;
+    }
+    return pow(x, e);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One residual evaluation at s (crystal frame).  Also returns what the next Jacobian needs.
+//   tau_a  = d_a . S n_a                          (models_copper.py:173)
+//   dg_a   = ao dt |tau/g|^(1/xm) sign(tau)       (:174)
+//   w_a    = d dg_a / d tau_a = ao dt n |tau/g|^(n-1) / g
+//   Fe     = G (I - sum_a dg_a d_a n_a^T)         (:188-191)
+//   r      = s - C : 1/2 (Fe^T Fe - I)            (:199)
+// returns ||r||_F over the 9 entries (:212, np.linalg.norm of the 9-vector)
+// ---------------------------------------------------------------------------------------------------
+template <int NS>
+CP_HD double cp_residual(const CpSlip& sl, const CpPointParams& pm, double cdt, const double* G, const double* ginv,
+                         const double* s, double* r, double* w, double* Fe, double* Lp) {
+    const double n1 = pm.n_exp - 1.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Lp[i] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+        const double d0 = sl.d[3 * a], d1 = sl.d[3 * a + 1], d2 = sl.d[3 * a + 2];
+        const double n0 = sl.n[3 * a], nn1 = sl.n[3 * a + 1], n2 = sl.n[3 * a + 2];
+        const double v0 = s[0] * n0 + s[5] * nn1 + s[4] * n2;
+        const double v1 = s[5] * n0 + s[1] * nn1 + s[3] * n2;
+        const double v2 = s[4] * n0 + s[3] * nn1 + s[2] * n2;
+        const double tau = d0 * v0 + d1 * v1 + d2 * v2;
+        const double x = tau * ginv[a];
+        const double pn1 = cp_pow_pos(fabs(x), n1);
+        const double cp = cdt * pn1;
+        const double dg = cp * x;
+        w[a] = cp * pm.n_exp * ginv[a];
+        const double e0 = dg * d0, e1 = dg * d1, e2 = dg * d2;
+        Lp[0] += e0 * n0; Lp[1] += e0 * nn1; Lp[2] += e0 * n2;
+        Lp[3] += e1 * n0; Lp[4] += e1 * nn1; Lp[5] += e1 * n2;
+        Lp[6] += e2 * n0; Lp[7] += e2 * nn1; Lp[8] += e2 * n2;
+    }
+    // Fe = G - G Lp
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            Fe[3 * i + j] = G[3 * i + j] - (G[3 * i] * Lp[j] + G[3 * i + 1] * Lp[3 + j] + G[3 * i + 2] * Lp[6 + j]);
+    // E = 1/2 (Fe^T Fe - I)
+    const double E0 = 0.5 * (Fe[0] * Fe[0] + Fe[3] * Fe[3] + Fe[6] * Fe[6] - 1.0);
+    const double E1 = 0.5 * (Fe[1] * Fe[1] + Fe[4] * Fe[4] + Fe[7] * Fe[7] - 1.0);
+    const double E2 = 0.5 * (Fe[2] * Fe[2] + Fe[5] * Fe[5] + Fe[8] * Fe[8] - 1.0);
+    const double E3 = 0.5 * (Fe[1] * Fe[2] + Fe[4] * Fe[5] + Fe[7] * Fe[8]);
+    const double E4 = 0.5 * (Fe[0] * Fe[2] + Fe[3] * Fe[5] + Fe[6] * Fe[8]);
+    const double E5 = 0.5 * (Fe[0] * Fe[1] + Fe[3] * Fe[4] + Fe[6] * Fe[7]);
+    r[0] = s[0] - (pm.C11 * E0 + pm.C12 * (E1 + E2));
+    r[1] = s[1] - (pm.C11 * E1 + pm.C12 * (E0 + E2));
+    r[2] = s[2] - (pm.C11 * E2 + pm.C12 * (E0 + E1));
+    r[3] = s[3] - 2.0 * pm.C44 * E3;
+    r[4] = s[4] - 2.0 * pm.C44 * E4;
+    r[5] = s[5] - 2.0 * pm.C44 * E5;
+    return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + 2.0 * (r[3] * r[3] + r[4] * r[4] + r[5] * r[5]));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Newton matrix in scaled form, LU-factorised in place (no pivoting, see header comment).
+//   N = C^-1 D^-1 + sum_a w_a e_a etilde_a^T,  e_a = voigt(sym(K d_a n_a^T)), K = Fe^T G,
+//   etilde_a = voigt(sym(d_a n_a^T))   (strain-like: shear entries carry the 1/2)
+// After the call N holds L (unit lower) and U; piv[i] = 1/U_ii.
+// ---------------------------------------------------------------------------------------------------
+template <int NS>
+CP_HD void cp_newton_matrix(const CpSlip& sl, const CpPointParams& pm, const double* G, const double* Fe,
+                            const double* w, double* N /*36*/, double* piv /*6*/) {
+    double K[9];
+    m3_mul_tn(Fe, G, K);
+    const double den = (pm.C11 - pm.C12) * (pm.C11 + 2.0 * pm.C12);
+    const double S11 = (pm.C11 + pm.C12) / den, S12 = -pm.C12 / den, S44q = 0.25 / pm.C44;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) N[i] = 0.0;
+    N[0] = N[7] = N[14] = S11;
+    N[1] = N[2] = N[6] = N[8] = N[12] = N[13] = S12;
+    N[21] = N[28] = N[35] = S44q;
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+        const double d0 = sl.d[3 * a], d1 = sl.d[3 * a + 1], d2 = sl.d[3 * a + 2];
+        const double n0 = sl.n[3 * a], n1 = sl.n[3 * a + 1], n2 = sl.n[3 * a + 2];
+        const double k0 = K[0] * d0 + K[1] * d1 + K[2] * d2;
+        const double k1 = K[3] * d0 + K[4] * d1 + K[5] * d2;
+        const double k2 = K[6] * d0 + K[7] * d1 + K[8] * d2;
+        double e[6], t[6];
+        const double wa = w[a];
+        e[0] = wa * (k0 * n0); e[1] = wa * (k1 * n1); e[2] = wa * (k2 * n2);
+        e[3] = wa * 0.5 * (k1 * n2 + k2 * n1); e[4] = wa * 0.5 * (k0 * n2 + k2 * n0); e[5] = wa * 0.5 * (k0 * n1 + k1 * n0);
+        t[0] = d0 * n0; t[1] = d1 * n1; t[2] = d2 * n2;
+        t[3] = 0.5 * (d1 * n2 + d2 * n1); t[4] = 0.5 * (d0 * n2 + d2 * n0); t[5] = 0.5 * (d0 * n1 + d1 * n0);
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) N[6 * i + j] += e[i] * t[j];
+    }
+    // in-place LU (Doolittle), no pivoting
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double ip = 1.0 / N[6 * k + k];
+        piv[k] = ip;
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const double l = N[6 * i + k] * ip;
+            N[6 * i + k] = l;
+#pragma unroll
+            for (int j = k + 1; j < 6; ++j) N[6 * i + j] -= l * N[6 * k + j];
+        }
+    }
+}
+
+CP_HD void cp_lu_solve(const double* N, const double* piv, double* b /*6, in: rhs, out: z*/) {
+#pragma unroll
+    for (int i = 1; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) b[i] -= N[6 * i + j] * b[j];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) b[i] -= N[6 * i + j] * b[j];
+        b[i] *= piv[i];
+    }
+}
+
+// b = -C^-1 r (strain-like vector)
+CP_HD void cp_compliance_neg(const CpPointParams& pm, const double* r, double* b) {
+    const double den = (pm.C11 - pm.C12) * (pm.C11 + 2.0 * pm.C12);
+    const double S11 = (pm.C11 + pm.C12) / den, S12 = -pm.C12 / den, S44h = 0.5 / pm.C44;
+    b[0] = -(S11 * r[0] + S12 * (r[1] + r[2]));
+    b[1] = -(S11 * r[1] + S12 * (r[0] + r[2]));
+    b[2] = -(S11 * r[2] + S12 * (r[0] + r[1]));
+    b[3] = -S44h * r[3]; b[4] = -S44h * r[4]; b[5] = -S44h * r[5];
+}
+
+struct CpSolveInfo {
+    int iters;      // outer Newton iterations taken
+    int evals;      // residual evaluations
+    int status;     // bit0: hit max_iter ; bit1: non-finite residual
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Local Newton solve, literal control flow of models_copper.py:204-249:
+//   y = 0 ; r = res(y)
+//   while ||r|| > tol:  inc = solve(J(y), -r); relax = 1; crt = r; sub = 0
+//        while ||crt|| >= ||r|| and sub < max_sub_step:  crt = res(y + relax inc); relax /= 2; sub++
+//        y += 2 relax inc ; r = crt
+// On return s, w, Fe, Lp are consistent with the last residual evaluation, which is the one at the
+// returned s (bitwise: y + relax*inc and y + 2*(relax/2)*inc are the same number).
+// ---------------------------------------------------------------------------------------------------
+template <int NS>
+CP_HD void cp_newton(const CpSlip& sl, const CpPointParams& pm, double cdt, double tol, int max_sub, int max_iter,
+                     const double* G, const double* ginv, double* s, double* w, double* Fe, double* Lp,
+                     CpSolveInfo& info) {
+    double r[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i] = 0.0;
+    double rn = cp_residual<NS>(sl, pm, cdt, G, ginv, s, r, w, Fe, Lp);
+    info.iters = 0; info.evals = 1; info.status = 0;
+    while (rn > tol) {
+        if (info.iters >= max_iter) { info.status |= 1; break; }
+        double N[36], piv[6], inc[6];
+        cp_newton_matrix<NS>(sl, pm, G, Fe, w, N, piv);
+        cp_compliance_neg(pm, r, inc);
+        cp_lu_solve(N, piv, inc);
+        inc[3] *= 0.5; inc[4] *= 0.5; inc[5] *= 0.5;          // inc = D^-1 z
+        double relax = 1.0, crtn = rn;
+        int sub = 0;
+        double st[6];
+        while (crtn >= rn && sub < max_sub) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) st[i] = s[i] + relax * inc[i];
+            crtn = cp_residual<NS>(sl, pm, cdt, G, ginv, st, r, w, Fe, Lp);
+            relax *= 0.5;
+            ++sub;
+            ++info.evals;
+        }
+        if (sub == 0) {
+            // only reachable when rn is NaN (comparison false): mimic the reference, which would leave y as is
+            info.status |= 2;
+            break;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = s[i] + 2.0 * relax * inc[i];
+        rn = crtn;
+        ++info.iters;
+    }
+    if (!(rn == rn)) info.status |= 2;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Frame change helpers
+// ---------------------------------------------------------------------------------------------------
+CP_HD void cp_to_crystal(const double* R, const double* M, double* Mc) {     // Mc = R^T M R
+    double T[9];
+    m3_mul_tn(R, M, T);
+    m3_mul(T, R, Mc);
+}
+CP_HD void cp_to_lab(const double* R, const double* Mc, double* M) {         // M = R Mc R^T
+    double T[9];
+    m3_mul(R, Mc, T);
+    m3_mul_nt(T, R, M);
+}
+
+template <int NS>
+struct CpPointState {       // everything the output stages need, crystal frame
+    double G[9], Ac[9], Fc[9];
+    double s[6], w[NS], Fe[9], Lp[9];
+    double ginv[NS];
+    double cdt;
+    CpSolveInfo info;
+};
+
+// Set-up + solve for one point.  H = u_grad (lab), A = Fp_inv_old (lab), g = slip resistances, R = rot_mat.
+template <int NS>
+CP_HD void cp_point_solve(const CpSlip& sl, const CpMaterial& mat, const CpPointParams& pm, double dt,
+                          const double* H, const double* A, const double* g, const double* R, CpPointState<NS>& ps) {
+    double F[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = H[i];
+    F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
+    cp_to_crystal(R, F, ps.Fc);
+    cp_to_crystal(R, A, ps.Ac);
+    m3_mul(ps.Fc, ps.Ac, ps.G);
+#pragma unroll
+    for (int a = 0; a < NS; ++a) ps.ginv[a] = 1.0 / g[a];
+    ps.cdt = mat.ao * dt;
+    cp_newton<NS>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.s, ps.w, ps.Fe, ps.Lp, ps.info);
+}
+
+// New state (models_copper.py:164-169 via helper :172-192): Fp_inv_new (lab), g_new, slip_new.
+template <int NS>
+CP_HD void cp_point_state_update(const CpSlip& sl, const CpPointParams& pm, const CpPointState<NS>& ps,
+                                 const double* g, const double* slip_old, const double* R,
+                                 double* A_new_lab, double* g_new, double* slip_new) {
+    double ImL[9], Anc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ImL[i] = -ps.Lp[i];
+    ImL[0] += 1.0; ImL[4] += 1.0; ImL[8] += 1.0;
+    m3_mul(ps.Ac, ImL, Anc);
+    cp_to_lab(R, Anc, A_new_lab);
+    double S[9];
+    sym6_to_m3(ps.s, S);
+    double tsum = 0.0;
+    double t[NS];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+        // dgamma_a recomputed from w_a: dg = w tau / n
+        const double d0 = sl.d[3 * a], d1 = sl.d[3 * a + 1], d2 = sl.d[3 * a + 2];
+        const double n0 = sl.n[3 * a], n1 = sl.n[3 * a + 1], n2 = sl.n[3 * a + 2];
+        const double tau = d0 * (S[0] * n0 + S[1] * n1 + S[2] * n2) + d1 * (S[3] * n0 + S[4] * n1 + S[5] * n2) +
+                           d2 * (S[6] * n0 + S[7] * n1 + S[8] * n2);
+        const double dg = ps.w[a] * tau / pm.n_exp;
+        slip_new[a] = slip_old[a] + dg;
+        const double y = 1.0 - g[a] / pm.t_sat;
+        const double sg = (y > 0.0) ? 1.0 : ((y < 0.0) ? -1.0 : 0.0);
+        t[a] = pm.h * fabs(dg) * pow(fabs(y), pm.gss_a) * sg;       // :178
+        tsum += t[a];
+    }
+    // g_inc = q t with q = r everywhere, 1 on the triples {3k,3k+1,3k+2}  (:71-76,179)
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+        const int b0 = (a / 3) * 3;
+        const double trip = t[b0] + t[b0 + 1] + t[b0 + 2];
+        g_new[a] = g[a] + (pm.r * (tsum - trip) + trip);
+    }
+}
+
+// First Piola-Kirchhoff stress (lab): P = Fe S A_new^T / det A_new  (== det F sigma F^-T, :160-161).
+// Also returns the crystal-frame pieces the tangent needs.
+template <int NS>
+struct CpStressAux {
+    double Anc[9];     // A_new crystal
+    double idet;       // 1/det(A_new)
+    double Pc[9];      // P crystal
+    double S[9];
+};
+
+template <int NS>
+CP_HD void cp_point_stress(const CpPointState<NS>& ps, const double* R, double* P_lab, CpStressAux<NS>& ax) {
+    double ImL[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ImL[i] = -ps.Lp[i];
+    ImL[0] += 1.0; ImL[4] += 1.0; ImL[8] += 1.0;
+    m3_mul(ps.Ac, ImL, ax.Anc);
+    ax.idet = 1.0 / m3_det(ax.Anc);
+    sym6_to_m3(ps.s, ax.S);
+    double T[9], T2[9];
+    m3_mul(ps.Fe, ax.S, T);
+    m3_mul_nt(T, ax.Anc, T2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ax.Pc[i] = T2[i] * ax.idet;
+    cp_to_lab(R, ax.Pc, P_lab);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Consistent tangent dP_ij/dH_kl in the lab frame, out[(3i+j)*ld + (3k+l)].
+//   ds/dF   = -J^-1 dr/dF   (f_jvp, models_copper.py:251-259),  dr/dF[dF] = -C : sym(Fe^T dF A_new)
+//   dP      = dF Z + [ dFe S A_new^T + Fe dS A_new^T + Fe S dA_new^T ] / det - P tr(A_new^-1 dA_new)
+//   with dLp = sum_a w_a (p_a . ds) d_a n_a^T,  dA_new = -Ac dLp,  dFe = -G dLp,
+//        tr(A_new^-1 dA_new) = -tr((I-Lp)^-1 dLp),  Z = A_new S A_new^T / det.
+// The loop runs over LAB directions dF = e_k e_l^T, i.e. crystal dF_c = (R^T e_k)(R^T e_l)^T, and rotates each
+// dP_c column back with R, which is cheaper than rotating the rank-4 tensor.
+// `scale` multiplies the whole tangent (JxW for the element integration).
+// ---------------------------------------------------------------------------------------------------
+template <int NS, typename OutT>
+CP_HD void cp_point_tangent(const CpSlip& sl, const CpPointParams& pm, const CpPointState<NS>& ps,
+                            const CpStressAux<NS>& ax, const double* R, double scale, OutT out, int ld) {
+    double N[36], piv[6];
+    cp_newton_matrix<NS>(sl, pm, ps.G, ps.Fe, ps.w, N, piv);
+    // constant pieces
+    double Z[9], T1[9] /* S A_new^T */, T2[9] /* Fe S */, Y[9] /* (I-Lp)^-1 */, tmp[9], dY;
+    m3_mul_nt(ax.S, ax.Anc, T1);
+    m3_mul(ax.Anc, T1, Z);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Z[i] *= ax.idet;
+    m3_mul(ps.Fe, ax.S, T2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tmp[i] = -ps.Lp[i];
+    tmp[0] += 1.0; tmp[4] += 1.0; tmp[8] += 1.0;
+    m3_inv(tmp, Y, &dY);
+    // U_k = Fe^T R^T e_k  -> rows of (R Fe) ; V_l = A_new^T-contracted: row l of (R A_new)
+    double RFe[9], RAn[9], RZ[9];
+    m3_mul(R, ps.Fe, RFe);      // RFe[k][:] = sum_c R[k][c] Fe[c][:]   (= Fe^T r_k as a row)
+    m3_mul(R, ax.Anc, RAn);     // RAn[l][:] = sum_c R[l][c] A_new[c][:]
+    m3_mul(R, Z, RZ);           // RZ[l][:]  = sum_c R[l][c] Z[c][:]
+#pragma unroll 1
+    for (int kl = 0; kl < 9; ++kl) {
+        const int k = kl / 3, l = kl - 3 * k;
+        const double* u = &RFe[3 * k];     // Fe^T r_k
+        const double* v = &RAn[3 * l];     // (r_l^T A_new)
+        // z = N^-1 voigt(sym(u v^T))
+        double z[6];
+        z[0] = u[0] * v[0]; z[1] = u[1] * v[1]; z[2] = u[2] * v[2];
+        z[3] = 0.5 * (u[1] * v[2] + u[2] * v[1]); z[4] = 0.5 * (u[0] * v[2] + u[2] * v[0]); z[5] = 0.5 * (u[0] * v[1] + u[1] * v[0]);
+        cp_lu_solve(N, piv, z);
+        // ds = D^-1 z ; dS full
+        double dS[9];
+        dS[0] = z[0]; dS[4] = z[1]; dS[8] = z[2];
+        dS[5] = dS[7] = 0.5 * z[3]; dS[2] = dS[6] = 0.5 * z[4]; dS[1] = dS[3] = 0.5 * z[5];
+        // dLp = sum_a w_a (d_a . dS n_a) d_a n_a^T
+        double dLp[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dLp[i] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NS; ++a) {
+            const double d0 = sl.d[3 * a], d1 = sl.d[3 * a + 1], d2 = sl.d[3 * a + 2];
+            const double n0 = sl.n[3 * a], n1 = sl.n[3 * a + 1], n2 = sl.n[3 * a + 2];
+            const double dtau = d0 * (dS[0] * n0 + dS[1] * n1 + dS[2] * n2) + d1 * (dS[3] * n0 + dS[4] * n1 + dS[5] * n2) +
+                                d2 * (dS[6] * n0 + dS[7] * n1 + dS[8] * n2);
+            const double dgm = ps.w[a] * dtau;
+            const double e0 = dgm * d0, e1 = dgm * d1, e2 = dgm * d2;
+            dLp[0] += e0 * n0; dLp[1] += e0 * n1; dLp[2] += e0 * n2;
+            dLp[3] += e1 * n0; dLp[4] += e1 * n1; dLp[5] += e1 * n2;
+            dLp[6] += e2 * n0; dLp[7] += e2 * n1; dLp[8] += e2 * n2;
+        }
+        // dPc = r_k (r_l^T Z)  +  [ -(G dLp) T1 + Fe dS A_new^T - T2 (Ac dLp)^T ] idet + Pc tr(Y dLp)
+        double GdL[9], AdL[9], M1[9], M2[9], M3[9], dPc[9];
+        m3_mul(ps.G, dLp, GdL);
+        m3_mul(GdL, T1, M1);
+        m3_mul(ps.Fe, dS, tmp);
+        m3_mul_nt(tmp, ax.Anc, M2);
+        m3_mul(ps.Ac, dLp, AdL);
+        m3_mul_nt(T2, AdL, M3);
+        const double tr = Y[0] * dLp[0] + Y[1] * dLp[3] + Y[2] * dLp[6] + Y[3] * dLp[1] + Y[4] * dLp[4] + Y[5] * dLp[7] +
+                          Y[6] * dLp[2] + Y[7] * dLp[5] + Y[8] * dLp[8];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                dPc[3 * i + j] = R[3 * k + i] * RZ[3 * l + j] + (M2[3 * i + j] - M1[3 * i + j] - M3[3 * i + j]) * ax.idet +
+                                 ax.Pc[3 * i + j] * tr;
+        double dP[9];
+        cp_to_lab(R, dPc, dP);
+#pragma unroll
+        for (int ij = 0; ij < 9; ++ij) out[ij * ld + kl] = dP[ij] * scale;
+    }
+}

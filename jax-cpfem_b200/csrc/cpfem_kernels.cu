@@ -1,0 +1,901 @@
+// cpfem_kernels.cu - sm_100a kernels + C ABI of the JAX-CPFEM hot path (see include/cpfem.h).
+//
+// Kernels
+//   k_update_state      K1  one thread per quadrature point: u_grad gather, local Newton, new state
+//   k_assemble<..>      K2/K3 one warp per 4 hex8 cells: phase 1 = 32 points (stress [+ tangent]) into
+//                           shared memory, phase 2 = lane (cell, node a) integrates 3 rows of K_e and
+//                           scatters them into the CSR pattern / residual with fp64 atomics
+//   k_avg_stress        K5  per-cell JxW-weighted Cauchy stress
+//   k_point_eval            tensor_map / jacfwd(tensor_map) on explicit u_grads
+//   plan kernels        K0  node valence -> node->cell lists -> sorted neighbour lists -> CSR pattern + slot map
+//
+// Reference lines replaced are cited in include/cpfem.h next to each entry point.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <new>
+
+#include "../../include/cpfem.h"
+#include "cp_point.cuh"
+
+static_assert(sizeof(cpfem_material) == sizeof(CpMaterial), "material struct mismatch");
+
+// -----------------------------------------------------------------------------------------------
+// error plumbing
+// -----------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int set_err(int code, const char* what, cudaError_t e = cudaSuccess) {
+    g_last_error = what;
+    if (e != cudaSuccess) {
+        g_last_error += ": ";
+        g_last_error += cudaGetErrorString(e);
+    }
+    return code;
+}
+#define CU_TRY(x)                                                  \
+    do {                                                           \
+        cudaError_t _e = (x);                                      \
+        if (_e != cudaSuccess) return set_err(-2, #x, _e);         \
+    } while (0)
+
+extern "C" const char* cpfem_last_error(void) { return g_last_error.c_str(); }
+extern "C" int cpfem_version(void) { return 100; }
+
+// -----------------------------------------------------------------------------------------------
+// plan
+// -----------------------------------------------------------------------------------------------
+struct cpfem_plan {
+    int64_t nc = 0, nn = 0, nnz = 0;
+    int32_t ns = 0;
+    int32_t max_valence = 0;
+    int32_t* cells = nullptr;     // (nc,8)
+    double* points = nullptr;     // (nn,3)
+    int64_t* indptr = nullptr;    // (3 nn + 1)
+    int32_t* indices = nullptr;   // (nnz)
+    uint8_t* rank = nullptr;      // (nc,8,8): rank of node b in the sorted neighbour list of node a
+    CpSlip slip;
+    int device = 0;
+    int sm_count = 148;
+};
+
+#define MAX_VALENCE 16
+
+__global__ void k_count_valence(const int32_t* __restrict__ cells, int64_t n, int64_t nn, int64_t* cnt, int* err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t v = cells[i];
+    if (v < 0 || v >= nn) { *err = 1; return; }
+    atomicAdd((unsigned long long*)&cnt[v], 1ULL);
+}
+
+__global__ void k_fill_n2c(const int32_t* __restrict__ cells, int64_t n, const int64_t* __restrict__ ptr,
+                           unsigned long long* cursor, int32_t* n2c) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t v = cells[i];
+    unsigned long long pos = atomicAdd(&cursor[v], 1ULL);
+    n2c[ptr[v] + (int64_t)pos] = (int32_t)(i >> 3);
+}
+
+// sorted unique neighbour nodes of node n (including n itself).  COUNT: only the count is written.
+template <bool COUNT>
+__global__ void k_node_neighbors(const int32_t* __restrict__ cells, const int64_t* __restrict__ n2c_ptr,
+                                 const int32_t* __restrict__ n2c, int64_t nn, int64_t* nneigh,
+                                 const int64_t* __restrict__ nbr_ptr, int32_t* nbr, int* err) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nn) return;
+    int32_t cand[MAX_VALENCE * 8];
+    int m = 0;
+    int64_t b = n2c_ptr[n], e = n2c_ptr[n + 1];
+    if (e - b > MAX_VALENCE) { *err = 2; if (COUNT) nneigh[n] = 0; return; }
+    for (int64_t k = b; k < e; ++k) {
+        const int32_t* cn = cells + (int64_t)n2c[k] * 8;
+        for (int a = 0; a < 8; ++a) {
+            int32_t v = cn[a];
+            // sorted insert, unique
+            int lo = 0;
+            while (lo < m && cand[lo] < v) ++lo;
+            if (lo < m && cand[lo] == v) continue;
+            for (int t = m; t > lo; --t) cand[t] = cand[t - 1];
+            cand[lo] = v;
+            ++m;
+        }
+    }
+    if (COUNT) {
+        nneigh[n] = m;
+    } else {
+        int64_t o = nbr_ptr[n];
+        for (int t = 0; t < m; ++t) nbr[o + t] = cand[t];
+    }
+}
+
+// indptr / indices from the neighbour lists: row 3n+i holds, for each neighbour nb (ascending), 3nb..3nb+2
+__global__ void k_fill_csr(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr, int64_t nn,
+                           int64_t* indptr, int32_t* indices) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n > nn) return;
+    if (n == nn) { indptr[3 * nn] = 9 * nbr_ptr[nn]; return; }
+    int64_t b = nbr_ptr[n];
+    int64_t m = nbr_ptr[n + 1] - b;
+    for (int i = 0; i < 3; ++i) {
+        int64_t r0 = 9 * b + (int64_t)i * 3 * m;
+        indptr[3 * n + i] = r0;
+        for (int64_t j = 0; j < m; ++j) {
+            int32_t col = 3 * nbr[b + j];
+            indices[r0 + 3 * j] = col;
+            indices[r0 + 3 * j + 1] = col + 1;
+            indices[r0 + 3 * j + 2] = col + 2;
+        }
+    }
+}
+
+__global__ void k_rank_map(const int32_t* __restrict__ cells, int64_t nc, const int64_t* __restrict__ nbr_ptr,
+                           const int32_t* __restrict__ nbr, uint8_t* rank) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (cell, a)
+    if (t >= nc * 8) return;
+    int64_t c = t >> 3;
+    const int32_t* cn = cells + c * 8;
+    int32_t na = cn[t & 7];
+    int64_t b0 = nbr_ptr[na];
+    int m = (int)(nbr_ptr[na + 1] - b0);
+    for (int b = 0; b < 8; ++b) {
+        int32_t v = cn[b];
+        int lo = 0, hi = m - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (nbr[b0 + mid] < v) lo = mid + 1; else hi = mid;
+        }
+        rank[t * 8 + b] = (uint8_t)lo;
+    }
+}
+
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+extern "C" int cpfem_plan_destroy(cpfem_plan* p) {
+    if (!p) return 0;
+    cudaFree(p->cells); cudaFree(p->points); cudaFree(p->indptr); cudaFree(p->indices); cudaFree(p->rank);
+    delete p;
+    return 0;
+}
+
+extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double* points, int64_t nnodes,
+                                 const double* slip, int32_t ns, void* stream_, cpfem_plan** out) {
+    if (!cells || !points || !slip || !out) return set_err(-1, "cpfem_plan_create: null argument");
+    if (ns != 12 && ns != 24) return set_err(-1, "cpfem_plan_create: ns must be 12 or 24");
+    if (nc <= 0 || nnodes <= 0) return set_err(-1, "cpfem_plan_create: empty mesh");
+    if (nnodes * 3 >= (int64_t)INT32_MAX) return set_err(-1, "cpfem_plan_create: too many dofs for int32 column indices");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cpfem_plan* p = new (std::nothrow) cpfem_plan();
+    if (!p) return set_err(-3, "cpfem_plan_create: out of host memory");
+    p->nc = nc; p->nn = nnodes; p->ns = ns;
+    cudaGetDevice(&p->device);
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
+    // slip table: normalise (models_copper.py:62-66)
+    memset(&p->slip, 0, sizeof(CpSlip));
+    for (int a = 0; a < ns; ++a) {
+        const double* row = slip + 6 * a;
+        double nn_ = sqrt(row[0] * row[0] + row[1] * row[1] + row[2] * row[2]);
+        double dn_ = sqrt(row[3] * row[3] + row[4] * row[4] + row[5] * row[5]);
+        if (!(nn_ > 0) || !(dn_ > 0)) { delete p; return set_err(-1, "cpfem_plan_create: zero slip vector"); }
+        for (int i = 0; i < 3; ++i) { p->slip.n[3 * a + i] = row[i] / nn_; p->slip.d[3 * a + i] = row[3 + i] / dn_; }
+    }
+    int64_t *cnt = nullptr, *n2c_ptr = nullptr, *nneigh = nullptr, *nbr_ptr = nullptr;
+    int32_t *n2c = nullptr, *nbr = nullptr;
+    unsigned long long* cursor = nullptr;
+    int* derr = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int herr = 0;
+    int rc = 0;
+    const int T = 256;
+    auto blocks = [&](int64_t n) { return (unsigned)((n + T - 1) / T); };
+#define PLAN_TRY(x)                                                           \
+    do {                                                                      \
+        cudaError_t _e = (x);                                                 \
+        if (_e != cudaSuccess) { rc = set_err(-2, #x, _e); goto done; }       \
+    } while (0)
+    PLAN_TRY(dev_alloc(&p->cells, nc * 8));
+    PLAN_TRY(dev_alloc(&p->points, nnodes * 3));
+    PLAN_TRY(cudaMemcpyAsync(p->cells, cells, nc * 8 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    PLAN_TRY(cudaMemcpyAsync(p->points, points, nnodes * 3 * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    PLAN_TRY(dev_alloc(&cnt, nnodes + 1));
+    PLAN_TRY(dev_alloc(&n2c_ptr, nnodes + 1));
+    PLAN_TRY(dev_alloc(&nneigh, nnodes + 1));
+    PLAN_TRY(dev_alloc(&nbr_ptr, nnodes + 1));
+    PLAN_TRY(dev_alloc(&cursor, nnodes));
+    PLAN_TRY(dev_alloc(&n2c, nc * 8));
+    PLAN_TRY(dev_alloc(&derr, 1));
+    PLAN_TRY(cudaMemsetAsync(cnt, 0, (nnodes + 1) * sizeof(int64_t), stream));
+    PLAN_TRY(cudaMemsetAsync(nneigh, 0, (nnodes + 1) * sizeof(int64_t), stream));
+    PLAN_TRY(cudaMemsetAsync(cursor, 0, nnodes * sizeof(unsigned long long), stream));
+    PLAN_TRY(cudaMemsetAsync(derr, 0, sizeof(int), stream));
+    k_count_valence<<<blocks(nc * 8), T, 0, stream>>>(p->cells, nc * 8, nnodes, cnt, derr);
+    PLAN_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, n2c_ptr, nnodes + 1, stream));
+    PLAN_TRY(cudaMalloc(&tmp, tmp_bytes));
+    PLAN_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, n2c_ptr, nnodes + 1, stream));
+    PLAN_TRY(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PLAN_TRY(cudaStreamSynchronize(stream));
+    if (herr) { rc = set_err(-1, "cpfem_plan_create: cell node index out of range"); goto done; }
+    k_fill_n2c<<<blocks(nc * 8), T, 0, stream>>>(p->cells, nc * 8, n2c_ptr, cursor, n2c);
+    k_node_neighbors<true><<<blocks(nnodes), T, 0, stream>>>(p->cells, n2c_ptr, n2c, nnodes, nneigh, nullptr, nullptr, derr);
+    PLAN_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nneigh, nbr_ptr, nnodes + 1, stream));
+    {
+        int64_t total = 0, maxv = 0;
+        PLAN_TRY(cudaMemcpyAsync(&total, nbr_ptr + nnodes, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        PLAN_TRY(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PLAN_TRY(cudaStreamSynchronize(stream));
+        if (herr) { rc = set_err(-1, "cpfem_plan_create: node valence above 16 cells is not supported"); goto done; }
+        p->nnz = 9 * total;
+        if (p->nnz <= 0) { rc = set_err(-1, "cpfem_plan_create: empty pattern"); goto done; }
+        PLAN_TRY(dev_alloc(&nbr, total));
+        k_node_neighbors<false><<<blocks(nnodes), T, 0, stream>>>(p->cells, n2c_ptr, n2c, nnodes, nullptr, nbr_ptr, nbr, derr);
+        PLAN_TRY(dev_alloc(&p->indptr, 3 * nnodes + 1));
+        PLAN_TRY(dev_alloc(&p->indices, p->nnz));
+        PLAN_TRY(dev_alloc(&p->rank, nc * 64));
+        k_fill_csr<<<blocks(nnodes + 1), T, 0, stream>>>(nbr_ptr, nbr, nnodes, p->indptr, p->indices);
+        k_rank_map<<<blocks(nc * 8), T, 0, stream>>>(p->cells, nc, nbr_ptr, nbr, p->rank);
+        // max valence (for info only)
+        void* t2 = nullptr; size_t t2b = 0;
+        int64_t* dmax = nullptr;
+        PLAN_TRY(dev_alloc(&dmax, 1));
+        cub::DeviceReduce::Max(nullptr, t2b, cnt, dmax, nnodes, stream);
+        if (t2b > tmp_bytes) { PLAN_TRY(cudaMalloc(&t2, t2b)); } else { t2 = tmp; t2b = tmp_bytes; }
+        cub::DeviceReduce::Max(t2, t2b, cnt, dmax, nnodes, stream);
+        PLAN_TRY(cudaMemcpyAsync(&maxv, dmax, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        PLAN_TRY(cudaStreamSynchronize(stream));
+        if (t2 != tmp) cudaFree(t2);
+        cudaFree(dmax);
+        p->max_valence = (int32_t)maxv;
+    }
+    PLAN_TRY(cudaGetLastError());
+done:
+    cudaFree(cnt); cudaFree(n2c_ptr); cudaFree(nneigh); cudaFree(nbr_ptr); cudaFree(cursor); cudaFree(n2c);
+    cudaFree(nbr); cudaFree(derr); cudaFree(tmp);
+    if (rc != 0) { cpfem_plan_destroy(p); return rc; }
+    *out = p;
+    return 0;
+#undef PLAN_TRY
+}
+
+extern "C" int cpfem_plan_csr(const cpfem_plan* p, const int64_t** indptr, const int32_t** indices, int64_t* nnz) {
+    if (!p) return set_err(-1, "cpfem_plan_csr: null plan");
+    if (indptr) *indptr = p->indptr;
+    if (indices) *indices = p->indices;
+    if (nnz) *nnz = p->nnz;
+    return 0;
+}
+extern "C" int cpfem_plan_info(const cpfem_plan* p, int64_t* o) {
+    if (!p || !o) return set_err(-1, "cpfem_plan_info: null argument");
+    o[0] = p->nc; o[1] = p->nn; o[2] = p->ns; o[3] = p->nnz; o[4] = p->max_valence;
+    return 0;
+}
+
+// -----------------------------------------------------------------------------------------------
+// device helpers
+// -----------------------------------------------------------------------------------------------
+struct StateView {
+    const double *Fp_inv, *g, *slip, *rot, *gss_a, *h, *t_sat, *xm, *r, *C;
+    int soa;
+};
+static StateView make_view(const cpfem_state* s) {
+    StateView v;
+    v.Fp_inv = s->Fp_inv; v.g = s->g; v.slip = s->slip; v.rot = s->rot;
+    v.gss_a = s->gss_a; v.h = s->h; v.t_sat = s->t_sat; v.xm = s->xm; v.r = s->r; v.C = s->C;
+    v.soa = (s->layout == CPFEM_LAYOUT_SOA);
+    return v;
+}
+
+__device__ __forceinline__ int64_t sidx(int soa, int64_t p, int i, int ncomp, int64_t np) {
+    return soa ? ((int64_t)i * np + p) : (p * ncomp + i);
+}
+
+__device__ __forceinline__ void load_point_params(const CpMaterial& m, const StateView& st, int64_t p, CpPointParams& pm) {
+    if (st.C) {
+        const double* C = st.C + p * 81;
+        pm.C11 = C[0]; pm.C12 = C[4]; pm.C44 = C[50];
+    } else {
+        pm.C11 = m.C11; pm.C12 = m.C12; pm.C44 = m.C44;
+    }
+    pm.h = st.h ? st.h[p] : m.h;
+    pm.t_sat = st.t_sat ? st.t_sat[p] : m.t_sat;
+    pm.gss_a = st.gss_a ? st.gss_a[p] : m.gss_a;
+    pm.r = st.r ? st.r[p] : m.r;
+    pm.n_exp = 1.0 / (st.xm ? st.xm[p] : m.xm);
+}
+
+// hex8 physical shape-function gradients and JxW at Gauss point q (2x2x2, x slowest / z fastest),
+// nodes in meshio/Gmsh order.  X[a][i] node coordinates.
+__device__ __forceinline__ void hex8_grads(const double (*X)[3], int q, double (*gN)[3], double& JxW) {
+    const double g0 = 0.21132486540518713, g1 = 0.7886751345948129;   // (1 -+ 1/sqrt 3)/2
+    const int bx = (q >> 2) & 1, by = (q >> 1) & 1, bz = q & 1;
+    double dN[8][3];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int ax = ((a + 1) >> 1) & 1;       // 0,1,1,0,0,1,1,0
+        const int ay = (a >> 1) & 1;             // 0,0,1,1,0,0,1,1
+        const int az = (a >> 2) & 1;             // 0,0,0,0,1,1,1,1
+        const double fx = (ax == bx) ? g1 : g0, fy = (ay == by) ? g1 : g0, fz = (az == bz) ? g1 : g0;
+        const double sx = ax ? 1.0 : -1.0, sy = ay ? 1.0 : -1.0, sz = az ? 1.0 : -1.0;
+        dN[a][0] = sx * fy * fz; dN[a][1] = sy * fx * fz; dN[a][2] = sz * fx * fy;
+    }
+    double J[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) s += X[a][i] * dN[a][j];
+            J[3 * i + j] = s;
+        }
+    double Ji[9], det;
+    m3_inv(J, Ji, &det);
+    JxW = det * 0.125;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) gN[a][i] = dN[a][0] * Ji[i] + dN[a][1] * Ji[3 + i] + dN[a][2] * Ji[6 + i];
+}
+
+// u_grad at point q of cell c: H_ij = sum_a u_a,i dN_a/dX_j   (models_copper.py:277-278)
+__device__ __forceinline__ void point_kinematics(const int32_t* __restrict__ cells, const double* __restrict__ points,
+                                                 const double* __restrict__ sol, int64_t c, int q, double* H,
+                                                 double (*gN)[3], double& JxW, int32_t* nodes_out) {
+    double X[8][3], U[8][3];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int32_t n = cells[c * 8 + a];
+        if (nodes_out) nodes_out[a] = n;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { X[a][i] = points[(int64_t)n * 3 + i]; U[a][i] = sol[(int64_t)n * 3 + i]; }
+    }
+    hex8_grads(X, q, gN, JxW);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) s += U[a][i] * gN[a][j];
+            H[3 * i + j] = s;
+        }
+}
+
+template <int NS>
+__device__ __forceinline__ void load_point_state(const StateView& st, int64_t p, int64_t np, double* A, double* g, double* R) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = st.Fp_inv[sidx(st.soa, p, i, 9, np)];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = st.rot[sidx(st.soa, p, i, 9, np)];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) g[a] = st.g[sidx(st.soa, p, a, NS, np)];
+}
+
+__device__ __forceinline__ void warp_status(const CpSolveInfo& info, bool valid, long long* status) {
+    if (!status) return;
+    const unsigned full = 0xffffffffu;
+    int capped = valid ? (info.status & 1) : 0;
+    int nonfin = valid ? ((info.status >> 1) & 1) : 0;
+    int it = valid ? info.iters : 0;
+    int sum = it, mx = it;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        capped += __shfl_xor_sync(full, capped, o);
+        nonfin += __shfl_xor_sync(full, nonfin, o);
+        sum += __shfl_xor_sync(full, sum, o);
+        mx = max(mx, __shfl_xor_sync(full, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (capped) atomicAdd((unsigned long long*)&status[0], (unsigned long long)capped);
+        if (nonfin) atomicAdd((unsigned long long*)&status[1], (unsigned long long)nonfin);
+        atomicMax(&status[2], (long long)mx);
+        atomicAdd((unsigned long long*)&status[3], (unsigned long long)sum);
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// K1: state update
+// -----------------------------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(128)
+k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
+               StateView st, cpfem_state_out out, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt,
+               int64_t np, long long* status) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < np;
+    if (!valid) p = np - 1;
+    const int64_t c = p >> 3;
+    const int q = (int)(p & 7);
+    double H[9], A[9], R[9], g[NS];
+    {
+        double gN[8][3], JxW;
+        point_kinematics(cells, points, sol, c, q, H, gN, JxW, nullptr);
+    }
+    load_point_state<NS>(st, p, np, A, g, R);
+    CpPointParams pm;
+    load_point_params(mat, st, p, pm);
+    CpPointState<NS> ps;
+    cp_point_solve<NS>(slip, mat, pm, dt, H, A, g, R, ps);
+    double sl_old[NS], An[9], gn[NS], sn[NS];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) sl_old[a] = st.slip[sidx(st.soa, p, a, NS, np)];
+    cp_point_state_update<NS>(slip, pm, ps, g, sl_old, R, An, gn, sn);
+    if (valid) {
+        const int so = (out.layout == CPFEM_LAYOUT_SOA);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) out.Fp_inv[sidx(so, p, i, 9, np)] = An[i];
+#pragma unroll
+        for (int a = 0; a < NS; ++a) out.g[sidx(so, p, a, NS, np)] = gn[a];
+#pragma unroll
+        for (int a = 0; a < NS; ++a) out.slip[sidx(so, p, a, NS, np)] = sn[a];
+    }
+    warp_status(ps.info, valid, status);
+}
+
+// -----------------------------------------------------------------------------------------------
+// K2/K3: residual (+ tangent) assembly.  One warp = 4 cells.
+// shared memory per warp (doubles):  TA 4 x TA_CELL (tangent*JxW, point stride TA_PT), GN 4 x GN_CELL
+// (shape gradients [q][a][3]), PJ 4 x PJ_CELL (P*JxW [q][9]).  Strides are padded so that the four cells
+// of a warp fall into different banks when their 8 lanes broadcast-read the same address.
+// -----------------------------------------------------------------------------------------------
+#define TA_PT 82
+#define TA_CELL (8 * TA_PT + 2)     // 658
+#define GN_CELL (8 * 24 + 2)        // 194
+#define PJ_CELL (8 * 9 + 2)         // 74
+
+static size_t assemble_smem_per_warp(bool tangent) {
+    return sizeof(double) * (size_t)((tangent ? 4 * TA_CELL : 0) + 4 * GN_CELL + 4 * PJ_CELL);
+}
+
+template <int NS, bool TANGENT>
+__global__ void __launch_bounds__(224, 1)
+k_assemble(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
+           StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t nc,
+           const int64_t* __restrict__ indptr, const uint8_t* __restrict__ rank, double* __restrict__ res,
+           double* __restrict__ csr_data, double* __restrict__ coo_V, long long* status, int warps_per_block) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = (TANGENT ? 4 * TA_CELL : 0) + 4 * GN_CELL + 4 * PJ_CELL;
+    double* TA = smem + (size_t)warp * per_warp;
+    double* GN = TA + (TANGENT ? 4 * TA_CELL : 0);
+    double* PJ = GN + 4 * GN_CELL;
+    const int cl = lane >> 3, q = lane & 7;
+    const int64_t nquads = (nc + 3) >> 2;
+    const int64_t np = nc * 8;
+    for (int64_t quad = (int64_t)blockIdx.x * warps_per_block + warp; quad < nquads;
+         quad += (int64_t)gridDim.x * warps_per_block) {
+        int64_t c = quad * 4 + cl;
+        const bool valid = c < nc;
+        if (!valid) c = nc - 1;
+        const int64_t p = c * 8 + q;
+        int32_t nodes[8];
+        CpSolveInfo info;
+        // ---------------- phase 1: lane = quadrature point q of cell cl ----------------
+        {
+            double H[9], A[9], R[9], g[NS], gN[8][3], JxW;
+            point_kinematics(cells, points, sol, c, q, H, gN, JxW, nodes);
+            double* gq = GN + cl * GN_CELL + q * 24;
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) gq[a * 3 + i] = gN[a][i];
+            load_point_state<NS>(st, p, np, A, g, R);
+            CpPointParams pm;
+            load_point_params(mat, st, p, pm);
+            CpPointState<NS> ps;
+            cp_point_solve<NS>(slip, mat, pm, dt, H, A, g, R, ps);
+            info = ps.info;
+            double P[9];
+            CpStressAux<NS> ax;
+            cp_point_stress<NS>(ps, R, P, ax);
+            double* pj = PJ + cl * PJ_CELL + q * 9;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) pj[i] = P[i] * JxW;
+            if (TANGENT) cp_point_tangent<NS>(slip, pm, ps, ax, R, JxW, TA + cl * TA_CELL + q * TA_PT, 9);
+        }
+        __syncwarp();
+        // ---------------- phase 2: lane = node a (= q) of cell cl ----------------
+        const int a = q;
+        const int32_t na = nodes[a];
+        {
+            // residual rows: r[a,i] = sum_q sum_j P_ij gN_a,j JxW
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+                const double* pj = PJ + cl * PJ_CELL + qq * 9;
+                const double* ga = GN + cl * GN_CELL + qq * 24 + a * 3;
+                const double g0 = ga[0], g1 = ga[1], g2 = ga[2];
+                r0 += pj[0] * g0 + pj[1] * g1 + pj[2] * g2;
+                r1 += pj[3] * g0 + pj[4] * g1 + pj[5] * g2;
+                r2 += pj[6] * g0 + pj[7] * g1 + pj[8] * g2;
+            }
+            if (valid && res) {
+                atomicAdd(&res[(int64_t)na * 3 + 0], r0);
+                atomicAdd(&res[(int64_t)na * 3 + 1], r1);
+                atomicAdd(&res[(int64_t)na * 3 + 2], r2);
+            }
+        }
+        if (TANGENT) {
+            double acc[3][24];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 24; ++j) acc[i][j] = 0.0;
+#pragma unroll 1
+            for (int qq = 0; qq < 8; ++qq) {
+                const double* ta = TA + cl * TA_CELL + qq * TA_PT;
+                const double* gq = GN + cl * GN_CELL + qq * 24;
+                const double ga0 = gq[a * 3], ga1 = gq[a * 3 + 1], ga2 = gq[a * 3 + 2];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    double T[9];
+#pragma unroll
+                    for (int kl = 0; kl < 9; ++kl)
+                        T[kl] = ga0 * ta[(3 * i) * 9 + kl] + ga1 * ta[(3 * i + 1) * 9 + kl] + ga2 * ta[(3 * i + 2) * 9 + kl];
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        const double gb0 = gq[b * 3], gb1 = gq[b * 3 + 1], gb2 = gq[b * 3 + 2];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            acc[i][3 * b + k] += T[3 * k] * gb0 + T[3 * k + 1] * gb1 + T[3 * k + 2] * gb2;
+                    }
+                }
+            }
+            if (valid) {
+                if (coo_V) {
+                    double* v = coo_V + c * 576 + (int64_t)(3 * a) * 24;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 24; ++j) v[i * 24 + j] = acc[i][j];
+                }
+                if (csr_data) {
+                    const uint8_t* rk = rank + (c * 8 + a) * 8;
+                    int rb[8];
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) rb[b] = 3 * (int)rk[b];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        double* row = csr_data + indptr[(int64_t)na * 3 + i];
+#pragma unroll
+                        for (int b = 0; b < 8; ++b)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) atomicAdd(&row[rb[b] + k], acc[i][3 * b + k]);
+                    }
+                }
+            }
+        }
+        warp_status(info, valid, status);
+        __syncwarp();
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// K5: average Cauchy stress per cell (models_copper.py:297-319)
+// -----------------------------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(128)
+k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
+             StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np,
+             double* __restrict__ sigma_cell, long long* status) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < np;
+    if (!valid) p = np - 1;
+    const int64_t c = p >> 3;
+    const int q = (int)(p & 7);
+    double H[9], A[9], R[9], g[NS], JxW;
+    {
+        double gN[8][3];
+        point_kinematics(cells, points, sol, c, q, H, gN, JxW, nullptr);
+    }
+    load_point_state<NS>(st, p, np, A, g, R);
+    CpPointParams pm;
+    load_point_params(mat, st, p, pm);
+    CpPointState<NS> ps;
+    cp_point_solve<NS>(slip, mat, pm, dt, H, A, g, R, ps);
+    double P[9];
+    CpStressAux<NS> ax;
+    cp_point_stress<NS>(ps, R, P, ax);
+    // sigma = P F^T / det F (:308-309)
+    double F[9], sg[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = H[i];
+    F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
+    m3_mul_nt(P, F, sg);
+    const double s = JxW / m3_det(F);
+    double wsum = JxW;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sg[i] *= s;
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sg[i] += __shfl_xor_sync(full, sg[i], o);
+        wsum += __shfl_xor_sync(full, wsum, o);
+    }
+    if (valid && q == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sigma_cell[c * 9 + i] = sg[i] / wsum;
+    }
+    warp_status(ps.info, valid, status);
+}
+
+// -----------------------------------------------------------------------------------------------
+// tensor_map on explicit u_grads (and its jacfwd)
+// -----------------------------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(128)
+k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip,
+             double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, long long* status) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < np;
+    if (!valid) p = np - 1;
+    double H[9], A[9], R[9], g[NS];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = u_grads[p * 9 + i];
+    load_point_state<NS>(st, p, np, A, g, R);
+    CpPointParams pm;
+    load_point_params(mat, st, p, pm);
+    CpPointState<NS> ps;
+    cp_point_solve<NS>(slip, mat, pm, dt, H, A, g, R, ps);
+    double P[9];
+    CpStressAux<NS> ax;
+    cp_point_stress<NS>(ps, R, P, ax);
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Pout[p * 9 + i] = P[i];
+        if (Aout) cp_point_tangent<NS>(slip, pm, ps, ax, R, 1.0, Aout + p * 81, 9);
+    }
+    warp_status(ps.info, valid, status);
+}
+
+// -----------------------------------------------------------------------------------------------
+// small utility kernels
+// -----------------------------------------------------------------------------------------------
+__global__ void k_dirichlet(const int64_t* __restrict__ rows, const double* __restrict__ vals, int64_t nbc,
+                            const double* __restrict__ sol, double* res, double* csr_data,
+                            const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbc) return;
+    const int64_t row = rows[i];
+    if (res) res[row] = sol[row] - vals[i];
+    if (csr_data) {
+        for (int64_t s = indptr[row]; s < indptr[row + 1]; ++s) csr_data[s] = (indices[s] == row) ? 1.0 : 0.0;
+    }
+}
+__global__ void k_scatter_add(const double* __restrict__ src, const int64_t* __restrict__ map, int64_t n, double* dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&dst[map[i]], src[i]);
+}
+__global__ void k_gather(const double* __restrict__ src, const int64_t* __restrict__ map, int64_t n, double* dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[map[i]];
+}
+__global__ void k_sumsq(const double* __restrict__ x, int64_t n, double* out) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += x[i] * x[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double sh[32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
+}
+// (rows, cols) -> (cols, rows) through a padded shared-memory tile; the long dimension rides on grid.x
+__global__ void k_transpose(const double* __restrict__ in, int64_t rows, int64_t cols, double* __restrict__ out,
+                            int rows_on_x) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = (int64_t)(rows_on_x ? blockIdx.x : blockIdx.y) * 32;
+    const int64_t c0 = (int64_t)(rows_on_x ? blockIdx.y : blockIdx.x) * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int64_t r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int64_t c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+__global__ void k_dfma_peak(int64_t iters, double* sink) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.999999999, c = 1e-9;
+    for (int64_t i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+// -----------------------------------------------------------------------------------------------
+// C ABI launchers
+// -----------------------------------------------------------------------------------------------
+static int check_common(const cpfem_plan* plan, const cpfem_material* mat, const cpfem_state* st, const char* who) {
+    if (!plan || !mat || !st) return set_err(-1, (std::string(who) + ": null argument").c_str());
+    if (!st->Fp_inv || !st->g || !st->rot) return set_err(-1, (std::string(who) + ": null state array").c_str());
+    if (mat->max_sub_step < 1) return set_err(-1, (std::string(who) + ": max_sub_step must be >= 1").c_str());
+    return 0;
+}
+static CpMaterial to_mat(const cpfem_material* m) {
+    CpMaterial r;
+    memcpy(&r, m, sizeof(CpMaterial));
+    if (r.max_iter <= 0) r.max_iter = 200;
+    return r;
+}
+
+extern "C" int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                                  const cpfem_state* in, const cpfem_state_out* out, double dt, int64_t* status,
+                                  void* stream_) {
+    int rc = check_common(plan, mat, in, "cpfem_update_state");
+    if (rc) return rc;
+    if (!sol || !out || !out->Fp_inv || !out->g || !out->slip || !in->slip)
+        return set_err(-1, "cpfem_update_state: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t np = plan->nc * 8;
+    const unsigned grid = (unsigned)((np + 127) / 128);
+    StateView v = make_view(in);
+    CpMaterial m = to_mat(mat);
+    if (plan->ns == 12)
+        k_update_state<12><<<grid, 128, 0, stream>>>(plan->cells, plan->points, sol, v, *out, m, plan->slip, dt, np, (long long*)status);
+    else
+        k_update_state<24><<<grid, 128, 0, stream>>>(plan->cells, plan->points, sol, v, *out, m, plan->slip, dt, np, (long long*)status);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <int NS, bool TANGENT>
+static int launch_assemble(const cpfem_plan* plan, const CpMaterial& m, const double* sol, const StateView& v, double dt,
+                           double* res, double* csr_data, double* coo_V, int64_t* status, cudaStream_t stream) {
+    const size_t per_warp = assemble_smem_per_warp(TANGENT);
+    int wpb = TANGENT ? 7 : 7;
+    const size_t smem = per_warp * wpb;
+    auto kern = k_assemble<NS, TANGENT>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 1;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem));
+    if (bps < 1) return set_err(-2, "cpfem assemble kernel does not fit on an SM");
+    const int64_t nquads = (plan->nc + 3) / 4;
+    int64_t grid = (int64_t)plan->sm_count * bps;
+    const int64_t need = (nquads + wpb - 1) / wpb;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, wpb * 32, smem, stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, plan->nc,
+                                                     plan->indptr, plan->rank, res, csr_data, coo_V, (long long*)status, wpb);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                              const cpfem_state* st, double dt, double* res, int64_t* status, void* stream_) {
+    int rc = check_common(plan, mat, st, "cpfem_residual");
+    if (rc) return rc;
+    if (!sol || !res) return set_err(-1, "cpfem_residual: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CU_TRY(cudaMemsetAsync(res, 0, plan->nn * 3 * sizeof(double), stream));
+    StateView v = make_view(st);
+    CpMaterial m = to_mat(mat);
+    if (plan->ns == 12) return launch_assemble<12, false>(plan, m, sol, v, dt, res, nullptr, nullptr, status, stream);
+    return launch_assemble<24, false>(plan, m, sol, v, dt, res, nullptr, nullptr, status, stream);
+}
+
+extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                                   const cpfem_state* st, double dt, double* res, double* csr_data, double* coo_V,
+                                   int64_t* status, void* stream_) {
+    int rc = check_common(plan, mat, st, "cpfem_newton_update");
+    if (rc) return rc;
+    if (!sol || !res) return set_err(-1, "cpfem_newton_update: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CU_TRY(cudaMemsetAsync(res, 0, plan->nn * 3 * sizeof(double), stream));
+    if (csr_data) CU_TRY(cudaMemsetAsync(csr_data, 0, plan->nnz * sizeof(double), stream));
+    StateView v = make_view(st);
+    CpMaterial m = to_mat(mat);
+    if (plan->ns == 12) return launch_assemble<12, true>(plan, m, sol, v, dt, res, csr_data, coo_V, status, stream);
+    return launch_assemble<24, true>(plan, m, sol, v, dt, res, csr_data, coo_V, status, stream);
+}
+
+extern "C" int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                                const cpfem_state* st, double dt, double* sigma_cell, int64_t* status, void* stream_) {
+    int rc = check_common(plan, mat, st, "cpfem_avg_stress");
+    if (rc) return rc;
+    if (!sol || !sigma_cell) return set_err(-1, "cpfem_avg_stress: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t np = plan->nc * 8;
+    const unsigned grid = (unsigned)((np + 127) / 128);
+    StateView v = make_view(st);
+    CpMaterial m = to_mat(mat);
+    if (plan->ns == 12)
+        k_avg_stress<12><<<grid, 128, 0, stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, np, sigma_cell, (long long*)status);
+    else
+        k_avg_stress<24><<<grid, 128, 0, stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, np, sigma_cell, (long long*)status);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads,
+                                          int64_t np, const cpfem_state* st, double dt, double* P, double* tangent,
+                                          int64_t* status, void* stream_) {
+    int rc = check_common(plan, mat, st, "cpfem_point_stress_tangent");
+    if (rc) return rc;
+    if (!u_grads || !P || np <= 0) return set_err(-1, "cpfem_point_stress_tangent: bad argument");
+    if (st->layout != CPFEM_LAYOUT_AOS) return set_err(-1, "cpfem_point_stress_tangent: AoS state only");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const unsigned grid = (unsigned)((np + 127) / 128);
+    StateView v = make_view(st);
+    CpMaterial m = to_mat(mat);
+    if (plan->ns == 12)
+        k_point_eval<12><<<grid, 128, 0, stream>>>(u_grads, v, m, plan->slip, dt, np, P, tangent, (long long*)status);
+    else
+        k_point_eval<24><<<grid, 128, 0, stream>>>(u_grads, v, m, plan->slip, dt, np, P, tangent, (long long*)status);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cpfem_apply_dirichlet(const cpfem_plan* plan, const int64_t* rows, const double* vals, int64_t nbc,
+                                     const double* sol, double* res, double* csr_data, void* stream_) {
+    if (!plan || !rows || !vals || !sol) return set_err(-1, "cpfem_apply_dirichlet: null argument");
+    if (nbc <= 0) return 0;
+    k_dirichlet<<<(unsigned)((nbc + 127) / 128), 128, 0, (cudaStream_t)stream_>>>(rows, vals, nbc, sol, res, csr_data,
+                                                                                 plan->indptr, plan->indices);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cpfem_scatter_add(const double* src, const int64_t* map, int64_t n, double* dst, void* stream_) {
+    if (n <= 0) return 0;
+    if (!src || !map || !dst) return set_err(-1, "cpfem_scatter_add: null argument");
+    k_scatter_add<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, map, n, dst);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int cpfem_gather(const double* src, const int64_t* map, int64_t n, double* dst, void* stream_) {
+    if (n <= 0) return 0;
+    if (!src || !map || !dst) return set_err(-1, "cpfem_gather: null argument");
+    k_gather<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, map, n, dst);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int cpfem_sumsq(const double* x, int64_t n, double* out, void* stream_) {
+    if (n <= 0) return 0;
+    if (!x || !out) return set_err(-1, "cpfem_sumsq: null argument");
+    int64_t blocks = (n + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_sumsq<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, n, out);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int cpfem_aos_to_soa(const double* aos, int64_t np, int32_t comps, double* soa, void* stream_) {
+    if (!aos || !soa || np <= 0 || comps <= 0) return set_err(-1, "cpfem_aos_to_soa: bad argument");
+    dim3 grid((unsigned)((np + 31) / 32), (unsigned)((comps + 31) / 32));
+    k_transpose<<<grid, dim3(32, 8), 0, (cudaStream_t)stream_>>>(aos, np, comps, soa, 1);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int cpfem_soa_to_aos(const double* soa, int64_t np, int32_t comps, double* aos, void* stream_) {
+    if (!aos || !soa || np <= 0 || comps <= 0) return set_err(-1, "cpfem_soa_to_aos: bad argument");
+    dim3 grid((unsigned)((np + 31) / 32), (unsigned)((comps + 31) / 32));
+    k_transpose<<<grid, dim3(32, 8), 0, (cudaStream_t)stream_>>>(soa, comps, np, aos, 0);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cpfem_dfma_peak_kernel(int64_t iters, double* sink, double* flops, void* stream_) {
+    if (!sink || !flops || iters <= 0) return set_err(-1, "cpfem_dfma_peak_kernel: bad argument");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256;
+    k_dfma_peak<<<blocks, threads, 0, (cudaStream_t)stream_>>>(iters, sink);
+    CU_TRY(cudaGetLastError());
+    *flops = (double)blocks * threads * 8.0 * 2.0 * (double)iters;
+    return 0;
+}
