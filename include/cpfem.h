@@ -91,6 +91,9 @@ int cpfem_plan_destroy(cpfem_plan* plan);
 
 /* CSR pattern owned by the plan (device pointers). indptr has 3*nnodes+1 entries. */
 int cpfem_plan_csr(const cpfem_plan* plan, const int64_t** indptr, const int32_t** indices, int64_t* nnz);
+/* Copy the pattern into caller-owned buffers (device or host; cudaMemcpyDefault): indptr_out int64
+ * (3*nnodes+1), indices_out int32 (nnz).  Either may be NULL. */
+int cpfem_plan_csr_copy(const cpfem_plan* plan, int64_t* indptr_out, int32_t* indices_out, void* stream);
 /* Sizes: nc, nnodes, ns, nnz, max node valence. out[5]. */
 int cpfem_plan_info(const cpfem_plan* plan, int64_t* out);
 

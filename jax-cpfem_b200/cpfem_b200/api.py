@@ -1,0 +1,218 @@
+"""Thin Python layer over the C ABI: device memory and streams come from torch, the work is done by the
+sm_100a kernels in libcpfem_b200.so.  Arrays are torch CUDA tensors (float64 / int32 / int64).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import numpy as onp
+import torch
+
+from . import _lib
+from ._lib import Material, State, StateOut, check
+
+LAYOUT_AOS, LAYOUT_SOA = 0, 1
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f64(x, device):
+    """float64 contiguous tensor on `device` (copies host arrays; no-op for resident tensors)."""
+    if isinstance(x, torch.Tensor):
+        if x.dtype != torch.float64 or not x.is_contiguous() or x.device != device:
+            x = x.to(device=device, dtype=torch.float64).contiguous()
+        return x
+    return torch.as_tensor(onp.ascontiguousarray(x, dtype=onp.float64)).to(device)
+
+
+def make_material(C11, C12, C44, h, t_sat, gss_a, xm, r=1.0, ao=0.001, tol=1e-8, max_sub_step=5, max_iter=200) -> Material:
+    return Material(C11, C12, C44, h, t_sat, gss_a, ao, xm, r, tol, int(max_sub_step), int(max_iter))
+
+
+class Plan:
+    """Per-mesh plan (cpfem_plan): device connectivity + coordinates, scipy-identical CSR pattern, slot map."""
+
+    def __init__(self, cells, points, slip, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('cpfem_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            cells_t = torch.as_tensor(onp.ascontiguousarray(cells, dtype=onp.int32)) if not isinstance(cells, torch.Tensor) else cells
+            self.cells = cells_t.to(device=self.device, dtype=torch.int32).contiguous()
+            self.points = _dev_f64(points, self.device)
+            slip = onp.ascontiguousarray(slip, dtype=onp.float64)
+            assert slip.ndim == 2 and slip.shape[1] == 6
+            self.slip = slip
+            self.ns = slip.shape[0]
+            self.nc = int(self.cells.shape[0])
+            self.nn = int(self.points.shape[0])
+            h = ctypes.c_void_p()
+            check(L.cpfem_plan_create(_ptr(self.cells), self.nc, _ptr(self.points), self.nn,
+                                      slip.ctypes.data_as(ctypes.c_void_p), self.ns, _stream(), ctypes.byref(h)),
+                  'cpfem_plan_create')
+            self._h = h
+            info = (ctypes.c_int64 * 5)()
+            check(L.cpfem_plan_info(self._h, info), 'cpfem_plan_info')
+            self.nnz = int(info[3])
+            self.max_valence = int(info[4])
+        self.ndof = 3 * self.nn
+        self.np = 8 * self.nc
+        self._indptr = None
+        self._indices = None
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                _lib.lib().cpfem_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- CSR pattern -------------------------------------------------------------------------
+    def csr_pattern(self):
+        """(indptr int64 (ndof+1), indices int32 (nnz)) as device tensors (copied once from the plan)."""
+        if self._indptr is None:
+            with torch.cuda.device(self.device):
+                ip = torch.empty(self.ndof + 1, dtype=torch.int64, device=self.device)
+                ix = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+                check(_lib.lib().cpfem_plan_csr_copy(self._h, _ptr(ip), _ptr(ix), _stream()), 'cpfem_plan_csr_copy')
+            self._indptr, self._indices = ip, ix
+        return self._indptr, self._indices
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _state(self, params: Sequence[torch.Tensor], layout=LAYOUT_AOS):
+        """cpfem_state from the reference's internal_vars list (4, 9 or 10 arrays)."""
+        n = len(params)
+        if n not in (4, 9, 10):
+            raise ValueError('internal_vars must have 4 (uniform), 9 (calibration) or 10 (DP steel) arrays')
+        ts = [_dev_f64(p, self.device) for p in params]
+        st = State()
+        st.Fp_inv, st.g, st.slip, st.rot = (t.data_ptr() for t in ts[:4])
+        if n >= 9:
+            st.gss_a, st.h, st.t_sat, st.xm, st.r = (t.data_ptr() for t in ts[4:9])
+        if n == 10:
+            st.C = ts[9].data_ptr()
+        st.layout = layout
+        return st, ts
+
+    def new_status(self):
+        return torch.zeros(4, dtype=torch.int64, device=self.device)
+
+    # ---- hot-path calls ----------------------------------------------------------------------
+    def update_state(self, mat: Material, sol, params, dt, out=None, status=None, layout=LAYOUT_AOS):
+        """cpfem_update_state.  Returns (Fp_inv_new, g_new, slip_new) with the shapes of the inputs."""
+        with torch.cuda.device(self.device):
+            st, ts = self._state(params, layout)
+            sol = _dev_f64(sol, self.device)
+            if out is None:
+                out = [torch.empty_like(ts[0]), torch.empty_like(ts[1]), torch.empty_like(ts[2])]
+            so = StateOut(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), layout)
+            check(_lib.lib().cpfem_update_state(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st), ctypes.byref(so),
+                                                float(dt), _ptr(status), _stream()), 'cpfem_update_state')
+        return out
+
+    def residual(self, mat: Material, sol, params, dt, res=None, status=None, layout=LAYOUT_AOS):
+        with torch.cuda.device(self.device):
+            st, ts = self._state(params, layout)
+            sol = _dev_f64(sol, self.device)
+            if res is None:
+                res = torch.empty(self.nn, 3, dtype=torch.float64, device=self.device)
+            check(_lib.lib().cpfem_residual(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st), float(dt), _ptr(res),
+                                            _ptr(status), _stream()), 'cpfem_residual')
+        return res
+
+    def newton_update(self, mat: Material, sol, params, dt, res=None, csr_data=None, coo_V=None, want_csr=True,
+                      want_V=False, status=None, layout=LAYOUT_AOS):
+        with torch.cuda.device(self.device):
+            st, ts = self._state(params, layout)
+            sol = _dev_f64(sol, self.device)
+            if res is None:
+                res = torch.empty(self.nn, 3, dtype=torch.float64, device=self.device)
+            if csr_data is None and want_csr:
+                csr_data = torch.empty(self.nnz, dtype=torch.float64, device=self.device)
+            if coo_V is None and want_V:
+                coo_V = torch.empty(self.nc * 576, dtype=torch.float64, device=self.device)
+            check(_lib.lib().cpfem_newton_update(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st), float(dt),
+                                                 _ptr(res), _ptr(csr_data), _ptr(coo_V), _ptr(status), _stream()),
+                  'cpfem_newton_update')
+        return res, csr_data, coo_V
+
+    def avg_stress(self, mat: Material, sol, params, dt, out=None, status=None, layout=LAYOUT_AOS):
+        with torch.cuda.device(self.device):
+            st, ts = self._state(params, layout)
+            sol = _dev_f64(sol, self.device)
+            if out is None:
+                out = torch.empty(self.nc, 3, 3, dtype=torch.float64, device=self.device)
+            check(_lib.lib().cpfem_avg_stress(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st), float(dt), _ptr(out),
+                                              _ptr(status), _stream()), 'cpfem_avg_stress')
+        return out
+
+    def point_stress_tangent(self, mat: Material, u_grads, params, dt, want_tangent=True, status=None):
+        """tensor_map (and its jacfwd) on explicit u_grads (np, 3, 3); state arrays have leading size np."""
+        with torch.cuda.device(self.device):
+            st, ts = self._state(params, LAYOUT_AOS)
+            ug = _dev_f64(u_grads, self.device)
+            n = int(ug.numel() // 9)
+            P = torch.empty(n, 3, 3, dtype=torch.float64, device=self.device)
+            A = torch.empty(n, 3, 3, 3, 3, dtype=torch.float64, device=self.device) if want_tangent else None
+            check(_lib.lib().cpfem_point_stress_tangent(self._h, ctypes.byref(mat), _ptr(ug), n, ctypes.byref(st), float(dt),
+                                                        _ptr(P), _ptr(A), _ptr(status), _stream()),
+                  'cpfem_point_stress_tangent')
+        return P, A
+
+    def apply_dirichlet(self, rows, vals, sol, res=None, csr_data=None):
+        with torch.cuda.device(self.device):
+            check(_lib.lib().cpfem_apply_dirichlet(self._h, _ptr(rows), _ptr(vals), int(rows.numel()), _ptr(sol), _ptr(res),
+                                                   _ptr(csr_data), _stream()), 'cpfem_apply_dirichlet')
+
+
+# ---- free helpers ------------------------------------------------------------------------------
+def scatter_add(src, index_map, dst):
+    check(_lib.lib().cpfem_scatter_add(_ptr(src), _ptr(index_map), int(src.numel()), _ptr(dst), _stream()), 'cpfem_scatter_add')
+
+
+def gather(src, index_map, dst):
+    check(_lib.lib().cpfem_gather(_ptr(src), _ptr(index_map), int(index_map.numel()), _ptr(dst), _stream()), 'cpfem_gather')
+
+
+def sumsq(x, out):
+    check(_lib.lib().cpfem_sumsq(_ptr(x), int(x.numel()), _ptr(out), _stream()), 'cpfem_sumsq')
+
+
+def aos_to_soa(aos: torch.Tensor, comps: int) -> torch.Tensor:
+    n = aos.numel() // comps
+    out = torch.empty(comps, n, dtype=torch.float64, device=aos.device)
+    check(_lib.lib().cpfem_aos_to_soa(_ptr(aos), n, comps, _ptr(out), _stream()), 'cpfem_aos_to_soa')
+    return out
+
+
+def soa_to_aos(soa: torch.Tensor, comps: int) -> torch.Tensor:
+    n = soa.numel() // comps
+    out = torch.empty(n, comps, dtype=torch.float64, device=soa.device)
+    check(_lib.lib().cpfem_soa_to_aos(_ptr(soa), n, comps, _ptr(out), _stream()), 'cpfem_soa_to_aos')
+    return out
+
+
+def dfma_peak(iters=20000, repeats=3):
+    """Measured FP64 FMA throughput of the current device in TFLOP/s (CUDA events, best of `repeats`)."""
+    sink = torch.zeros(1, dtype=torch.float64, device='cuda')
+    flops = ctypes.c_double()
+    best = 0.0
+    for _ in range(repeats + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.lib().cpfem_dfma_peak_kernel(int(iters), _ptr(sink), ctypes.byref(flops), _stream()), 'cpfem_dfma_peak_kernel')
+        e1.record()
+        e1.synchronize()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

@@ -1,0 +1,309 @@
+"""Host-side mirror of the reference's plugin interface for the hot path.
+
+`Problem` / `FiniteElement` carry the attribute and method names the reference consumes from
+`jax_fem.problem.Problem` (singlecrystal_copper/models_copper.py:9,84,277,315;
+crystal_plasticity_OR_design/solver.py:119-133,244,281,290-293,391-392):
+
+    problem.fes[0].cells / points / num_quads / num_total_nodes / vec / shape_grads / JxW
+    problem.fes[0].node_inds_list / vec_inds_list / vals_list / update_Dirichlet_boundary_conditions
+    problem.newton_update(sol_list) -> res_list   (side effect: problem.V / problem.csr_data)
+    problem.compute_residual(sol_list) -> res_list
+    problem.I, problem.J, problem.V, problem.unflatten_fn_sol_list, num_total_dofs_all_vars, offset
+
+`CrystalPlasticityBase` carries the model-level methods of `CrystalPlasticity(Problem)`
+(models_copper.py:51-319): custom_init, get_tensor_map, get_maps, set_params, update_int_vars_gp,
+compute_avg_stress, inspect_interval_vars, attribute `dt`, attribute `internal_vars`.
+
+Arrays are torch CUDA tensors where the reference uses JAX arrays; numpy inputs are accepted and copied
+to the device.  All arithmetic is done by the CUDA kernels behind the C ABI (api.Plan); nothing here
+computes stresses, tangents or state on the host.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import numpy as onp
+import torch
+
+from . import api
+from .generate_mesh import Mesh
+
+SLIP_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
+
+
+def get_rot_mat(q):
+    """models_copper.py:37-45 (quaternion (w,x,y,z) -> rotation matrix), numpy, batched."""
+    q = onp.asarray(q, dtype=onp.float64)
+    q0, q1, q2, q3 = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    return onp.stack([
+        onp.stack([q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, 2 * q1 * q2 - 2 * q0 * q3, 2 * q1 * q3 + 2 * q0 * q2], -1),
+        onp.stack([2 * q1 * q2 + 2 * q0 * q3, q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, 2 * q2 * q3 - 2 * q0 * q1], -1),
+        onp.stack([2 * q1 * q3 - 2 * q0 * q2, 2 * q2 * q3 + 2 * q0 * q1, q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3], -1)], -2)
+
+
+get_rot_mat_vmap = get_rot_mat
+
+
+def _hex8_ref_grads():
+    g = onp.array([(1 - 1 / onp.sqrt(3)) / 2, (1 + 1 / onp.sqrt(3)) / 2])
+    nodes = onp.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]])
+    quad = onp.array([[g[i], g[j], g[k]] for i in range(2) for j in range(2) for k in range(2)])
+    dN = onp.zeros((8, 8, 3))
+    for q in range(8):
+        f = onp.where(nodes == 1, quad[q][None, :], 1 - quad[q][None, :])        # (a, 3)
+        s = onp.where(nodes == 1, 1.0, -1.0)
+        dN[q, :, 0] = s[:, 0] * f[:, 1] * f[:, 2]
+        dN[q, :, 1] = s[:, 1] * f[:, 0] * f[:, 2]
+        dN[q, :, 2] = s[:, 2] * f[:, 0] * f[:, 1]
+    return dN
+
+
+class FiniteElement:
+    """The slice of jax_fem.fe.FiniteElement the reference touches."""
+
+    def __init__(self, mesh: Mesh, vec, dim, ele_type, dirichlet_bc_info):
+        if ele_type != 'HEX8' or vec != 3 or dim != 3:
+            raise NotImplementedError('the crystal-plasticity hot path is HEX8, vec = dim = 3')
+        self.mesh = mesh
+        self.points = mesh.points
+        self.cells = mesh.cells
+        self.vec, self.dim, self.ele_type = vec, dim, ele_type
+        self.num_cells = len(self.cells)
+        self.num_total_nodes = len(self.points)
+        self.num_total_dofs = self.num_total_nodes * vec
+        self.num_quads = 8
+        self.num_nodes = 8
+        self._shape_grads = None
+        self._JxW = None
+        self.dirichlet_bc_info = dirichlet_bc_info
+        self.node_inds_list, self.vec_inds_list, self.vals_list = [], [], []
+        if dirichlet_bc_info is not None:
+            self.update_Dirichlet_boundary_conditions(dirichlet_bc_info)
+
+    # geometry arrays kept for API parity (the kernels recompute them from points/cells on the fly)
+    def _geometry(self):
+        dN = _hex8_ref_grads()
+        X = self.points[self.cells]
+        jac = onp.einsum('cai,qaj->cqij', X, dN)
+        self._shape_grads = onp.einsum('qaj,cqji->cqai', dN, onp.linalg.inv(jac))
+        self._JxW = onp.linalg.det(jac) * 0.125
+
+    @property
+    def shape_grads(self):
+        if self._shape_grads is None:
+            self._geometry()
+        return self._shape_grads
+
+    @property
+    def JxW(self):
+        if self._JxW is None:
+            self._geometry()
+        return self._JxW
+
+    @staticmethod
+    def _eval_location(fn, points):
+        try:
+            m = onp.asarray(fn(points.T))
+            if m.shape == (len(points),):
+                return m.astype(bool)
+        except Exception:
+            pass
+        return onp.array([bool(fn(p)) for p in points])
+
+    @staticmethod
+    def _eval_value(fn, pts):
+        try:
+            v = onp.asarray(fn(pts.T), dtype=onp.float64)
+            if v.shape == (len(pts),):
+                return v
+            if v.shape == ():
+                return onp.full(len(pts), float(v))
+        except Exception:
+            pass
+        return onp.array([float(fn(p)) for p in pts], dtype=onp.float64)
+
+    def update_Dirichlet_boundary_conditions(self, dirichlet_bc_info):
+        """jax_fem: node_inds_list[i] = argwhere(location_fn(points)); vec_inds_list[i]; vals_list[i]."""
+        self.dirichlet_bc_info = dirichlet_bc_info
+        location_fns, vecs, value_fns = dirichlet_bc_info
+        self.node_inds_list, self.vec_inds_list, self.vals_list = [], [], []
+        for loc, v, val in zip(location_fns, vecs, value_fns):
+            inds = onp.argwhere(self._eval_location(loc, self.points)).reshape(-1)
+            self.node_inds_list.append(inds)
+            self.vec_inds_list.append(onp.full(len(inds), v, dtype=onp.int32))
+            self.vals_list.append(self._eval_value(val, self.points[inds]))
+
+
+class Problem:
+    """The slice of jax_fem.problem.Problem on the hot path (see module docstring)."""
+
+    def __init__(self, mesh, vec=3, dim=3, ele_type='HEX8', dirichlet_bc_info=None, additional_info=(), device=None,
+                 keep_V=False):
+        self.mesh = [mesh]
+        self.vec, self.dim, self.ele_type = [vec], dim, [ele_type]
+        self.fes = [FiniteElement(mesh, vec, dim, ele_type, dirichlet_bc_info)]
+        self.num_vars = 1
+        self.offset = [0]
+        self.num_total_dofs_all_vars = self.fes[0].num_total_dofs
+        self.num_cells = self.fes[0].num_cells
+        self.additional_info = additional_info
+        self.keep_V = keep_V
+        self.dt = None
+        self.internal_vars = []
+        self._I = self._J = None
+        self._V = None
+        self.csr_data = None
+        self.last_status = None
+        self._last_sol = None
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.custom_init(*additional_info)
+        self.plan = api.Plan(self.fes[0].cells, self.fes[0].points, self.slip_table, device=self.device)
+        self.internal_vars = [api._dev_f64(v, self.device) for v in self.internal_vars]
+
+    def custom_init(self, *args):
+        raise NotImplementedError
+
+    # ---- dof bookkeeping (solver.py:119-133,391) ---------------------------------------------
+    def unflatten_fn_sol_list(self, dofs):
+        return [dofs.reshape(self.fes[0].num_total_nodes, self.fes[0].vec)]
+
+    # ---- COO indices (jax_fem rule, consumed at solver.py:281) -------------------------------
+    def _coo(self):
+        cells = self.fes[0].cells.astype(onp.int64)
+        inds = (3 * cells[:, :, None] + onp.arange(3)[None, None, :]).reshape(len(cells), -1)
+        self._I = onp.repeat(inds[:, :, None], 24, axis=2).reshape(-1)
+        self._J = onp.repeat(inds[:, None, :], 24, axis=1).reshape(-1)
+
+    @property
+    def I(self):
+        if self._I is None:
+            self._coo()
+        return self._I
+
+    @property
+    def J(self):
+        if self._J is None:
+            self._coo()
+        return self._J
+
+    @property
+    def V(self):
+        """problem.V (nc*576,) in the reference layout.  Materialised only on request (keep_V) - the CSR data
+        assembled on the device (problem.csr_data on problem.csr_pattern()) is the product's hand-off."""
+        if self._V is None:
+            if self._last_sol is None:
+                raise RuntimeError('problem.V: call newton_update first')
+            keep, self.keep_V = self.keep_V, True
+            self.newton_update([self._last_sol])
+            self.keep_V = keep
+        return self._V
+
+    def csr_pattern(self):
+        return self.plan.csr_pattern()
+
+    def csr_scipy(self):
+        """Assembled tangent as a scipy CSR (host copy) - what get_A builds at solver.py:281."""
+        import scipy.sparse
+        ip, ix = self.plan.csr_pattern()
+        n = self.num_total_dofs_all_vars
+        return scipy.sparse.csr_array((self.csr_data.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(n, n))
+
+    # ---- the two assembly entry points ---------------------------------------------------------
+    def newton_update(self, sol_list):
+        sol = api._dev_f64(sol_list[0], self.device)
+        self._last_sol = sol
+        st = self.plan.new_status()
+        res, self.csr_data, V = self.plan.newton_update(self.material, sol, self.internal_vars, self.dt,
+                                                        want_csr=True, want_V=self.keep_V, status=st)
+        self._V = V
+        self.last_status = st
+        return [res]
+
+    def compute_residual(self, sol_list):
+        sol = api._dev_f64(sol_list[0], self.device)
+        st = self.plan.new_status()
+        res = self.plan.residual(self.material, sol, self.internal_vars, self.dt, status=st)
+        self.last_status = st
+        return [res]
+
+    def set_params(self, params):
+        """models_copper.py:284-285."""
+        self.internal_vars = [api._dev_f64(v, self.device) for v in params]
+
+
+class CrystalPlasticityBase(Problem):
+    """Model-level methods shared by the four `models_*.py` files of the reference; subclasses only supply
+    the parameter set (class attributes below) - the reference files differ in nothing else."""
+    slip_file = None          # (ns, 6) numpy table
+    gss_initial = None
+    C11 = C12 = C44 = None
+    h = t_sat = gss_a = xm = None
+    r = 1.0
+    ao = 0.001
+    max_sub_step = 5
+    tol = 1e-8
+
+    def custom_init(self, quat, cell_ori_inds):
+        """models_copper.py:52-133."""
+        self.slip_table = onp.asarray(self.slip_file, dtype=onp.float64)
+        ns = len(self.slip_table)
+        nc, nq = self.fes[0].num_cells, self.fes[0].num_quads
+        quat = onp.asarray(quat, dtype=onp.float64)
+        # JAX clamps out-of-range gathers; numpy would raise
+        ori = onp.clip(onp.asarray(cell_ori_inds, dtype=onp.int64), 0, len(quat) - 1)
+        rot_mats = get_rot_mat(quat)[ori]
+        Fp_inv_gp = onp.tile(onp.eye(3)[None, None], (nc, nq, 1, 1))
+        slip_resistance_gp = self.gss_initial * onp.ones((nc, nq, ns))
+        slip_gp = onp.zeros_like(slip_resistance_gp)
+        rot_mats_gp = onp.repeat(rot_mats[:, None, :, :], nq, axis=1)
+        self.material = api.make_material(self.C11, self.C12, self.C44, self.h, self.t_sat, self.gss_a, self.xm, self.r,
+                                          self.ao, self.tol, self.max_sub_step)
+        self.internal_vars = [Fp_inv_gp, slip_resistance_gp, slip_gp, rot_mats_gp]
+
+    # ---- models_copper.py:135-137 --------------------------------------------------------------
+    def get_tensor_map(self):
+        tensor_map, _ = self.get_maps()
+        return tensor_map
+
+    def get_maps(self):
+        """Returns (tensor_map, update_int_vars_map) acting on BATCHES of points: the reference returns scalar
+        functions that jax_fem vmaps over (cell, quad); here the batch axis is explicit (leading axes are
+        flattened) because the device kernel is the vmap."""
+        def tensor_map(u_grad, *state):
+            ug = api._dev_f64(u_grad, self.device)
+            lead = ug.shape[:-2]
+            flat = [api._dev_f64(s, self.device) for s in state]
+            P, _ = self.plan.point_stress_tangent(self.material, ug.reshape(-1, 3, 3), flat, self.dt, want_tangent=False)
+            return P.reshape(*lead, 3, 3)
+
+        def update_int_vars_map(u_grad, *state):
+            raise NotImplementedError('use update_int_vars_gp (the reference only calls the map through it)')
+        return tensor_map, update_int_vars_map
+
+    def tensor_map_jacobian(self, u_grad, *state):
+        """jax.jacfwd(tensor_map) w.r.t. u_grad on a batch: (..., 3, 3, 3, 3)."""
+        ug = api._dev_f64(u_grad, self.device)
+        lead = ug.shape[:-2]
+        flat = [api._dev_f64(s, self.device) for s in state]
+        P, A = self.plan.point_stress_tangent(self.material, ug.reshape(-1, 3, 3), flat, self.dt, want_tangent=True)
+        return P.reshape(*lead, 3, 3), A.reshape(*lead, 3, 3, 3, 3)
+
+    # ---- models_copper.py:273-282 --------------------------------------------------------------
+    def update_int_vars_gp(self, sol, params):
+        params = [api._dev_f64(v, self.device) for v in params]
+        st = self.plan.new_status()
+        new = self.plan.update_state(self.material, sol, params, self.dt, status=st)
+        self.last_status = st
+        return [new[0], new[1], new[2]] + list(params[3:])
+
+    # ---- models_copper.py:297-319 --------------------------------------------------------------
+    def compute_avg_stress(self, sol, params):
+        params = [api._dev_f64(v, self.device) for v in params]
+        return self.plan.avg_stress(self.material, sol, params, self.dt)
+
+    def inspect_interval_vars(self, params):
+        """models_copper.py:287-295 (post-processing only)."""
+        Fp_inv_gp, slip_resistance_gp, slip_gp = params[0], params[1], params[2]
+        F_p = torch.linalg.inv(torch.as_tensor(Fp_inv_gp)[0, 0])
+        return float(F_p[2, 2]), float(slip_resistance_gp[0, 0, 0]), float(slip_gp[0, 0, 0])

@@ -268,6 +268,13 @@ extern "C" int cpfem_plan_csr(const cpfem_plan* p, const int64_t** indptr, const
     if (nnz) *nnz = p->nnz;
     return 0;
 }
+extern "C" int cpfem_plan_csr_copy(const cpfem_plan* p, int64_t* indptr_out, int32_t* indices_out, void* stream_) {
+    if (!p) return set_err(-1, "cpfem_plan_csr_copy: null plan");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (indptr_out) CU_TRY(cudaMemcpyAsync(indptr_out, p->indptr, (3 * p->nn + 1) * sizeof(int64_t), cudaMemcpyDefault, stream));
+    if (indices_out) CU_TRY(cudaMemcpyAsync(indices_out, p->indices, p->nnz * sizeof(int32_t), cudaMemcpyDefault, stream));
+    return 0;
+}
 extern "C" int cpfem_plan_info(const cpfem_plan* p, int64_t* o) {
     if (!p || !o) return set_err(-1, "cpfem_plan_info: null argument");
     o[0] = p->nc; o[1] = p->nn; o[2] = p->ns; o[3] = p->nnz; o[4] = p->max_valence;

@@ -1,0 +1,58 @@
+"""CPU suite: the C-ABI library builds, loads and exports every symbol include/cpfem.h declares.
+No compute calls are made here (no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, 'include', 'cpfem.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(cpfem_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_symbols_exported():
+    import cpfem_b200
+    cpfem_b200.build()
+    lib = ctypes.CDLL(cpfem_b200.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/cpfem.h but not exported'
+
+
+def test_binding_table_matches_header():
+    from cpfem_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_struct_layouts():
+    from cpfem_b200 import _lib
+    assert ctypes.sizeof(_lib.Material) == 10 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.State) == 10 * 8 + 8
+    assert ctypes.sizeof(_lib.StateOut) == 3 * 8 + 8
+
+
+def test_no_cpu_fallback():
+    """The product raises without a CUDA device instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import cpfem_b200
+    import numpy as np
+    from cpfem_b200 import slip_systems
+    with pytest.raises(RuntimeError):
+        cpfem_b200.Plan(np.zeros((1, 8), np.int32), np.zeros((8, 3)), slip_systems.FCC12)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'jax-cpfem_b200')
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dp, fn)).read()
+                assert 'cpfem_oracle' not in txt and 'hostcheck' not in txt.replace('tests/hostcheck', ''), fn

@@ -1,0 +1,258 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI (cpfem_b200.Plan / the Problem mirror), against the
+CPU oracle on the same seeded inputs.  Tolerance: 1e-10 relative to the field maximum for fp64 values (north_star),
+bit-exact for the CSR pattern."""
+import numpy as np
+import pytest
+import scipy.sparse
+import torch
+
+import cases
+import cpfem_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _mat(m):
+    from cpfem_b200 import make_material
+    return make_material(m.C11, m.C12, m.C44, m.h, m.t_sat, m.gss_a, m.xm, m.r, m.ao, m.tol, m.max_sub_step)
+
+
+def _dummy_plan(slip):
+    from cpfem_b200 import Plan
+    pts, cells = O.box_mesh(1, 1, 1)
+    return Plan(cells, pts, slip)
+
+
+@pytest.mark.parametrize('name', list(cases.MATERIALS))
+def test_point_stress_tangent(name):
+    """tensor_map and jacfwd(tensor_map) on explicit u_grads (cpfem_point_stress_tangent) vs oracle."""
+    plan = None
+    for step, mat, dt, H, A, g, sl, R in cases.point_history(name, n=75, steps=8):
+        if plan is None:
+            plan = _dummy_plan(mat.slip)
+        pb = O.PointBatch(A, g, sl, R, mat)
+        y, it_o, _ = pb.newton_solver(H, dt, True)
+        P_o = pb.first_PK_stress(H, dt, y).numpy()
+        T_o = pb.tangent(H, dt, y).numpy()
+        st = plan.new_status()
+        P, T = plan.point_stress_tangent(_mat(mat), H, [A, g, sl, R], dt, status=st)
+        st = st.cpu().numpy()
+        assert st[0] == 0 and st[1] == 0
+        assert st[2] == it_o.max().item() and st[3] == it_o.sum().item()      # identical iteration counts
+        assert cases.relerr(P.cpu().numpy(), P_o) < TOL
+        assert cases.relerr(T.cpu().numpy(), T_o) < TOL
+
+
+@pytest.mark.parametrize('name', ['304steel', 'tantalum'])
+def test_fe_update_residual_tangent(name):
+    """update_int_vars_gp / compute_residual / newton_update (V and CSR) / compute_avg_stress on a small distorted
+    polycrystal mesh vs the oracle's FE layer."""
+    from cpfem_b200 import Plan
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case(name, N=3, steps=6)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    m = _mat(mat)
+    # state update
+    new_o = fe.update_int_vars_gp(sol, params, dt)
+    new = plan.update_state(m, sol, params, dt)
+    for k in range(2):
+        assert cases.relerr(new[k].cpu().numpy(), new_o[k]) < TOL
+    assert np.abs(new[2].cpu().numpy() - new_o[2]).max() < TOL * max(np.abs(new_o[2]).max(), mat.ao * dt)
+    # residual only
+    res_o = fe.compute_residual(sol, params, dt)
+    res = plan.residual(m, sol, params, dt)
+    scale = np.abs(fe.cell_residual(sol, params, dt)).max()          # nodal sums cancel in the interior
+    assert np.abs(res.cpu().numpy() - res_o).max() < TOL * scale
+    # residual + tangent
+    res_o2, V_o = fe.newton_update(sol, params, dt)
+    res2, data, V = plan.newton_update(m, sol, params, dt, want_V=True)
+    assert np.abs(res2.cpu().numpy() - res_o2).max() < TOL * scale
+    assert cases.relerr(V.cpu().numpy(), V_o) < TOL
+    A_o = O.csr_from_coo(V_o, fe.I, fe.J, fe.nn * 3)
+    indptr, indices = plan.csr_pattern()
+    assert np.array_equal(indptr.cpu().numpy(), A_o.indptr.astype(np.int64))          # bit-exact pattern
+    assert np.array_equal(indices.cpu().numpy(), A_o.indices.astype(np.int32))
+    assert cases.relerr(data.cpu().numpy(), A_o.data) < TOL
+    # CSR data must equal scipy's canonicalisation of OUR V up to atomic summation order
+    A_v = O.csr_from_coo(V.cpu().numpy(), fe.I, fe.J, fe.nn * 3)
+    assert np.abs(data.cpu().numpy() - A_v.data).max() < 1e-13 * np.abs(A_v.data).max()
+    # average stress
+    sg_o = fe.compute_avg_stress(sol, params, dt)
+    sg = plan.avg_stress(m, sol, params, dt)
+    assert cases.relerr(sg.cpu().numpy(), sg_o) < TOL
+
+
+def test_dp_steel_per_point_parameters():
+    """DP-steel form: 10 internal_vars arrays (per-point a, h, t_sat, xm, r, C), 24 slip systems."""
+    from cpfem_b200 import Plan
+    N = 2
+    pts, cells = O.box_mesh(N, N, N)
+    nc = len(cells)
+    params, ph, quat, ori = cases.dp_params(nc)
+    fe = O.FEOracle(pts, cells, O.make_dp_batch_factory())
+    plan = Plan(cells, pts, O.SLIP_BCC24)
+    m = _mat(O.dp_ferrite())
+    dt = 0.2
+    rng = np.random.default_rng(5)
+    for s in range(1, 8):
+        eps = 5e-4 * s
+        sol = np.stack([-0.3 * eps * pts[:, 0], -0.3 * eps * pts[:, 1], eps * pts[:, 2]], 1) + rng.uniform(-1, 1, pts.shape) * 2e-5
+        if s == 7:
+            break
+        params = fe.update_int_vars_gp(sol, params, dt)
+    res_o, V_o = fe.newton_update(sol, params, dt)
+    res, data, V = plan.newton_update(m, sol, params, dt, want_V=True)
+    assert cases.relerr(V.cpu().numpy(), V_o) < TOL
+    new_o = fe.update_int_vars_gp(sol, params, dt)
+    new = plan.update_state(m, sol, params, dt)
+    assert cases.relerr(new[0].cpu().numpy(), new_o[0]) < TOL and cases.relerr(new[1].cpu().numpy(), new_o[1]) < TOL
+
+
+def test_soa_layout_and_transposes():
+    """Native SoA state layout gives the same bits as the reference AoS layout; the transposes round-trip."""
+    from cpfem_b200 import Plan, api
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('copper', N=3, steps=4)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    m = _mat(mat)
+    dev = [torch.as_tensor(p).cuda().contiguous() for p in params]
+    comps = [9, 12, 12, 9]
+    soa = [api.aos_to_soa(t, c) for t, c in zip(dev, comps)]
+    for t, s, c in zip(dev, soa, comps):
+        assert torch.equal(s, t.reshape(-1, c).T.contiguous())
+        assert torch.equal(api.soa_to_aos(s, c).reshape(t.shape), t)
+    a = plan.update_state(m, sol, dev, dt)
+    b = plan.update_state(m, sol, soa, dt, layout=api.LAYOUT_SOA)
+    for x, y, c in zip(a, b, [9, 12, 12]):
+        assert torch.equal(api.soa_to_aos(y, c).reshape(x.shape), x)
+    r_a = plan.residual(m, sol, dev, dt)
+    r_b = plan.residual(m, sol, soa, dt, layout=api.LAYOUT_SOA)
+    assert (r_a - r_b).abs().max().item() < 1e-13 * r_a.abs().max().item() + 1e-12
+
+
+def test_csr_pattern_ragged_and_unstructured():
+    """Pattern vs scipy on meshes that are not boxes: an L-shaped cell subset with a permuted node numbering."""
+    from cpfem_b200 import Plan
+    pts, cells = O.box_mesh(4, 3, 3)
+    keep = np.array([c for c in range(len(cells)) if not (c % 4 >= 2 and (c // 4) % 3 >= 1)])
+    cells = cells[keep]
+    used = np.unique(cells)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(used))
+    remap = -np.ones(len(pts), dtype=np.int64)
+    remap[used] = perm
+    cells2 = remap[cells].astype(np.int32)
+    pts2 = np.zeros((len(used), 3))
+    pts2[perm] = pts[used]
+    plan = Plan(cells2, pts2, O.SLIP_FCC12)
+    I, J = O.coo_indices(cells2)
+    A = scipy.sparse.csr_array((np.ones(len(I)), (I, J)), shape=(3 * len(used),) * 2)
+    indptr, indices = plan.csr_pattern()
+    assert np.array_equal(indptr.cpu().numpy(), A.indptr.astype(np.int64))
+    assert np.array_equal(indices.cpu().numpy(), A.indices.astype(np.int32))
+    assert plan.nnz == A.nnz
+
+
+def test_dirichlet_rows():
+    """apply_bc_vec + zeroRows on device (solver.py:119-133,290-293)."""
+    from cpfem_b200 import Plan
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('copper', N=2, steps=3)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    res, data, _ = plan.newton_update(_mat(mat), sol, params, dt)
+    A0 = scipy.sparse.csr_array((data.cpu().numpy(), plan.csr_pattern()[1].cpu().numpy(), plan.csr_pattern()[0].cpu().numpy()))
+    rows = np.array([0, 5, 13, 40], dtype=np.int64)
+    vals = np.array([0., 0.1, -0.2, 0.3])
+    sol_t = torch.as_tensor(sol).cuda().contiguous()
+    plan.apply_dirichlet(torch.as_tensor(rows).cuda(), torch.as_tensor(vals).cuda(), sol_t, res, data)
+    r = res.cpu().numpy().reshape(-1)
+    assert np.allclose(r[rows], sol.reshape(-1)[rows] - vals, rtol=0, atol=0)
+    A1 = scipy.sparse.csr_array((data.cpu().numpy(), A0.indices, A0.indptr)).toarray()
+    A0 = A0.toarray()
+    for i in range(A0.shape[0]):
+        if i in rows:
+            e = np.zeros(A0.shape[0]); e[i] = 1
+            assert np.array_equal(A1[i], e)
+        else:
+            assert np.array_equal(A1[i], A0[i])
+
+
+def test_problem_mirror_driver_loop():
+    """The reference's load-step call sequence (singlecrystal_copper.py:179-233) through the Problem mirror:
+    set_params -> newton_update / compute_residual -> compute_avg_stress -> update_int_vars_gp, vs the oracle."""
+    from cpfem_b200.generate_mesh import Mesh, box_mesh
+    from cpfem_b200.models_copper import CrystalPlasticity
+    mm = box_mesh(2, 2, 2, 0.1, 0.1, 0.1)
+    mesh = Mesh(mm.points, mm.cells_dict['hexahedron'])
+    quat = np.array([[1., 0, 0, 0], [0.5, 0.5, 0.5, 0.5]])
+    ori = np.arange(8) % 2
+    bottom = lambda p: np.isclose(p[2], 0., atol=1e-5)
+    top = lambda p: np.isclose(p[2], 0.1, atol=1e-5)
+    bc = [[bottom, top], [2, 2], [lambda p: 0., lambda p: 1e-4]]
+    problem = CrystalPlasticity(mesh, vec=3, dim=3, ele_type='HEX8', dirichlet_bc_info=bc, additional_info=(quat, ori))
+    assert len(problem.fes[0].node_inds_list[0]) == 9 and problem.fes[0].vals_list[1][0] == 1e-4
+    mat = O.copper()
+    fe = O.FEOracle(mesh.points, mesh.cells, O.make_uniform_batch_factory(mat))
+    params_o = O.initial_internal_vars(8, mat, O.get_rot_mat(quat)[ori])
+    params = problem.internal_vars
+    rng = np.random.default_rng(2)
+    for step in range(1, 5):
+        problem.dt = 0.01
+        eps = 1e-3 * step
+        sol = np.stack([-0.3 * eps * mesh.points[:, 0], -0.3 * eps * mesh.points[:, 1], eps * mesh.points[:, 2]], 1)
+        sol += rng.uniform(-1, 1, sol.shape) * 1e-6
+        problem.set_params(params)
+        res = problem.newton_update([sol])[0]
+        res_o, V_o = fe.newton_update(sol, params_o, 0.01)
+        A_o = O.csr_from_coo(V_o, fe.I, fe.J, fe.nn * 3)
+        assert cases.relerr(problem.csr_data.cpu().numpy(), A_o.data) < TOL
+        assert np.array_equal(problem.I, fe.I) and np.array_equal(problem.J, fe.J)
+        assert cases.relerr(problem.V.cpu().numpy(), V_o) < TOL
+        sg = problem.compute_avg_stress(sol, params)
+        assert cases.relerr(sg.cpu().numpy(), fe.compute_avg_stress(sol, params_o, 0.01)) < TOL
+        P = problem.get_tensor_map()(fe.u_grads(sol).reshape(8, 8, 3, 3), *params)
+        assert cases.relerr(P.cpu().numpy(), fe.point_stress(sol, params_o, 0.01)) < TOL
+        params = problem.update_int_vars_gp(sol, params)
+        params_o = fe.update_int_vars_gp(sol, params_o, 0.01)
+        for k in range(2):
+            assert cases.relerr(params[k].cpu().numpy(), params_o[k]) < TOL
+    assert int(problem.last_status[2]) > 3
+
+
+def test_full_size_properties():
+    """Size-independent properties on a mesh the oracle cannot follow (64^3, 2.1 M points): the residual of a rigid
+    translation of the converged field is unchanged, the tangent annihilates rigid translations, CSR row sums of the
+    x-translation vanish, nnz = 9(3N+1)^3, run-to-run determinism of the non-atomic outputs."""
+    from cpfem_b200 import Plan, synthetic
+    N = 64
+    mesh, quat, gid = synthetic.polycrystal(N)
+    mat = O.steel304()
+    plan = Plan(mesh.cells, mesh.points, mat.slip)
+    assert plan.nnz == 9 * (3 * N + 1) ** 3
+    m = _mat(mat)
+    R = torch.as_tensor(O.get_rot_mat(quat)).cuda()[torch.as_tensor(gid).cuda()]
+    nc = plan.nc
+    params = [torch.eye(3, dtype=torch.float64, device='cuda').expand(nc, 8, 3, 3).contiguous(),
+              torch.full((nc, 8, 12), mat.gss_initial, dtype=torch.float64, device='cuda'),
+              torch.zeros(nc, 8, 12, dtype=torch.float64, device='cuda'),
+              R[:, None].expand(nc, 8, 3, 3).contiguous()]
+    dt = 2e-3
+    for s in range(1, 8):
+        sol = torch.as_tensor(synthetic.displacement(mesh.points, 2e-4 * s, N)).cuda()
+        new = plan.update_state(m, sol, params, dt)
+        params = [new[0], new[1], new[2], params[3]]
+    sol = torch.as_tensor(synthetic.displacement(mesh.points, 2e-4 * 8, N)).cuda()
+    st = plan.new_status()
+    res, data, _ = plan.newton_update(m, sol, params, dt, status=st)
+    st = st.cpu().numpy()
+    assert st[0] == 0 and st[1] == 0 and st[2] >= 5
+    shift = torch.tensor([0.3, -0.2, 0.1], dtype=torch.float64, device='cuda')
+    res2 = plan.residual(m, sol + shift, params, dt)
+    assert (res - res2).abs().max().item() < 1e-9 * res.abs().max().item()
+    indptr, indices = plan.csr_pattern()
+    A = torch.sparse_csr_tensor(indptr, indices.to(torch.int64), data, size=(plan.ndof, plan.ndof))
+    t = torch.zeros(plan.nn, 3, dtype=torch.float64, device='cuda')
+    t[:, 0] = 1.0
+    y = A @ t.reshape(-1)
+    assert y.abs().max().item() < 1e-9 * data.abs().max().item()
+    a = plan.update_state(m, sol, params, dt)
+    b = plan.update_state(m, sol, params, dt)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))

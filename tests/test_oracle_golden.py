@@ -1,0 +1,138 @@
+"""CPU suite: pins the oracle against the reference's golden artefacts and checks the product's per-point
+algebra (host build of csrc/cp_point.cuh) against the oracle.  No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import cpfem_oracle as O
+import hostcheck_build
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _one_element_curve(mat, disps, ts, nsteps):
+    """1 hex8 element, BCs corner(x,y) / bottom(z) / top(z)=disp  (calibration_case1_...py:125-149)."""
+    pts, cells = O.box_mesh(1, 1, 1)
+    fe = O.FEOracle(pts, cells, O.make_uniform_batch_factory(mat))
+    R = O.get_rot_mat(np.array([[1., 0, 0, 0]]))[np.zeros(1, int)]
+    params = O.initial_internal_vars(1, mat, R)
+    sol = np.zeros((8, 3))
+    corner = np.where((np.abs(pts[:, 0]) < 1e-5) & (np.abs(pts[:, 1]) < 1e-5) & (np.abs(pts[:, 2]) < 1e-5))[0]
+    bottom = np.where(np.abs(pts[:, 2]) < 1e-5)[0]
+    top = np.where(np.abs(pts[:, 2] - 1) < 1e-5)[0]
+    nodes = np.concatenate([corner, corner, bottom, top])
+    comps = np.concatenate([0 * corner, 0 * corner + 1, 0 * bottom + 2, 0 * top + 2])
+    out = []
+    for i in range(nsteps):
+        dt = ts[i + 1] - ts[i]
+        vals = np.concatenate([0. * corner, 0. * corner, 0. * bottom, 0. * top + disps[i + 1]])
+        sol, _ = O.solve_load_step(fe, sol, params, dt, nodes, comps, vals, tol=1e-7, dense_lstsq=True)
+        out.append(fe.compute_avg_stress(sol, params, dt)[0, 2, 2])        # driver order: stress, then update
+        params = fe.update_int_vars_gp(sol, params, dt)
+    return np.array(out)
+
+
+def test_golden_curve_tantalum():
+    """calibration_case2: BCC Ta, disps = linspace(0,-0.10,41), ts = linspace(0,10,41).  Tolerance 1e-10 relative:
+    the reference's own outer Newton stops at rel 1e-8 on the residual, which leaves ~1e-12 on the stress here."""
+    gold = np.loadtxt(os.path.join(GOLD, 'tantalum_ss_curve.txt'))
+    n = 8
+    got = _one_element_curve(O.tantalum(), np.linspace(0., -0.10, 41), np.linspace(0., 10., 41), n)
+    assert np.abs(got / gold[:n] - 1).max() < 1e-10
+
+
+def test_golden_curve_copper():
+    """calibration_case1: FCC Cu, disps = linspace(0,0.025,21), ts = linspace(0,2.5,21).  The file holds the
+    reference's BiCGStab/outer-Newton answer (tol 1e-7), good to ~3e-9 on the first step: tolerance 1e-8."""
+    gold = np.loadtxt(os.path.join(GOLD, 'copper_ss_curve.txt'))
+    n = 8
+    got = _one_element_curve(O.copper(), np.linspace(0., 0.025, 21), np.linspace(0., 2.5, 21), n)
+    assert np.abs(got / gold[:n] - 1).max() < 1e-8
+
+
+@pytest.mark.parametrize('name', list(cases.MATERIALS))
+def test_point_algebra_vs_oracle(name, hostcheck):
+    """Hand-derived crystal-frame / 6x6 formulation (product header, host build) vs autodiff oracle:
+    same local-Newton iteration and residual-evaluation counts at every point, stress / tangent / state within
+    1e-10 of the field maximum (north_star tolerance)."""
+    for step, mat, dt, H, A, g, sl, R in cases.point_history(name, n=32, steps=8):
+        pb = O.PointBatch(A, g, sl, R, mat)
+        y, it_o, ev_o = pb.newton_solver(H, dt, True)
+        P_o = pb.first_PK_stress(H, dt, y).numpy()
+        T_o = pb.tangent(H, dt, y).numpy()
+        An_o, gn_o, sn_o = [x.numpy() for x in pb.update_int_vars(H, dt, y)]
+        P_h, T_h, An_h, gn_h, sn_h, info = hostcheck_build.evaluate(hostcheck, mat, dt, H, A, g, sl, R)
+        assert (info[:, 0] == it_o.numpy()).all() and (info[:, 1] == ev_o.numpy()).all() and (info[:, 2] == 0).all()
+        assert cases.relerr(P_h, P_o) < 1e-10
+        assert cases.relerr(T_h, T_o) < 1e-10
+        assert cases.relerr(An_h, An_o) < 1e-10 and cases.relerr(gn_h, gn_o) < 1e-10
+        # accumulated slip: compare on the physical scale ao*dt (values 1e-100 below it are amplified noise of
+        # the exponent-120 power law in both implementations)
+        assert np.abs(sn_h - sn_o).max() < 1e-10 * max(np.abs(sn_o).max(), mat.ao * dt)
+
+
+def test_tangent_vs_central_differences():
+    """The tangent is 'parity unpinned' by reference artefacts: check the oracle's autodiff tangent against central
+    differences of its own stress (FD-limited, 1e-6)."""
+    hist = list(cases.point_history('304steel', n=6, steps=7))
+    step, mat, dt, H, A, g, sl, R = hist[-1]
+    pb = O.PointBatch(A, g, sl, R, mat)
+    T = pb.tangent(H, dt).numpy()
+    d = 1e-7
+    for k in range(3):
+        for l in range(3):
+            Hp, Hm = H.copy(), H.copy()
+            Hp[:, k, l] += d
+            Hm[:, k, l] -= d
+            fd = (pb.first_PK_stress(Hp, dt).numpy() - pb.first_PK_stress(Hm, dt).numpy()) / (2 * d)
+            assert np.abs(fd - T[:, :, :, k, l]).max() < 2e-6 * np.abs(T).max()
+
+
+def test_dp_per_point_parameters(hostcheck):
+    """DP-steel form (per-point h, t_sat, a, xm, r, C; 24 slip systems): product header vs oracle."""
+    nc = 6
+    params, ph, quat, ori = cases.dp_params(nc)
+    rng = np.random.default_rng(3)
+    flat = lambda a, k: a.reshape(nc * 8, *a.shape[2:])
+    Fp, g, sl, R, a, h, ts, xm, r, C = params
+    n = nc * 8
+    A_, g_, sl_, R_ = Fp.reshape(n, 3, 3), g.reshape(n, 24), sl.reshape(n, 24), R.reshape(n, 3, 3)
+    dt = 0.2
+    for step in range(1, 9):
+        eps = 4e-4 * step
+        H = np.zeros((n, 3, 3)); H[:, 2, 2] = eps; H[:, 0, 0] = H[:, 1, 1] = -0.3 * eps
+        H += rng.uniform(-1, 1, size=H.shape) * 4e-5
+        pb = O.PointBatch(A_, g_, sl_, R_, gss_a=a.reshape(-1), h=h.reshape(-1), t_sat=ts.reshape(-1), xm=xm.reshape(-1),
+                          r=r.reshape(-1), C=C.reshape(n, 3, 3, 3, 3), slip_table=O.SLIP_BCC24)
+        y, it_o, ev_o = pb.newton_solver(H, dt, True)
+        P_o = pb.first_PK_stress(H, dt, y).numpy()
+        T_o = pb.tangent(H, dt, y).numpy()
+        An_o, gn_o, sn_o = [x.numpy() for x in pb.update_int_vars(H, dt, y)]
+        Cf = C.reshape(n, 81)
+        pp = np.stack([Cf[:, 0], Cf[:, 4], Cf[:, 50], h.reshape(-1), ts.reshape(-1), a.reshape(-1), xm.reshape(-1), r.reshape(-1)], 1)
+        P_h, T_h, An_h, gn_h, sn_h, info = hostcheck_build.evaluate(hostcheck, O.dp_ferrite(), dt, H, A_, g_, sl_, R_, pp=pp)
+        assert (info[:, 0] == it_o.numpy()).all()
+        assert cases.relerr(P_h, P_o) < 1e-10 and cases.relerr(T_h, T_o) < 1e-10
+        assert cases.relerr(An_h, An_o) < 1e-10 and cases.relerr(gn_h, gn_o) < 1e-10
+        A_, g_, sl_ = An_o, gn_o, sn_o
+    assert it_o.max() > 3          # the history reached plastic flow
+
+
+def test_fe_layer_consistency():
+    """FE layer of the oracle: V is the derivative of the scattered residual (central differences), I/J follow the
+    jax_fem rule, CSR from scipy sums duplicates / sorts columns / keeps the full pattern."""
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('304steel', N=2, steps=5)
+    res, V = fe.newton_update(sol, params, dt)
+    ndof = fe.nn * 3
+    A = O.csr_from_coo(V, fe.I, fe.J, ndof)
+    assert A.has_canonical_format
+    rng = np.random.default_rng(0)
+    du = rng.normal(size=sol.shape)
+    d = 1e-8       # exponent-120 flow rule: the FD error falls as d^2 down to ~1e-8 here
+    fd = (fe.compute_residual(sol + d * du, params, dt) - fe.compute_residual(sol - d * du, params, dt)) / (2 * d)
+    lin = (A @ du.reshape(-1)).reshape(-1, 3)
+    assert np.abs(fd - lin).max() < 2e-7 * np.abs(lin).max()
+    # nnz of a structured N^3 mesh: 9 (3N+1)^3  
+    assert A.nnz == 9 * (3 * 2 + 1) ** 3
