@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200-native JAX-CPFEM hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--n 200] [--impl reference]
+
+Workload (BASELINE.json configs[4]): synthetic n^3 hex8 polycrystal (default 200^3 = 8 M cells,
+64 M quadrature points, 8^3-cell grains with random orientations), 304-steel parameter set (FCC12, rate exponent
+120), advanced 10 load steps from the virgin state with the state-update kernel so that every point flows
+plastically; the timed "step" is load step 11: one state-update pass (update_int_vars_gp) + one Newton-iteration
+assembly (newton_update: stress + consistent tangent at every point, hex8 integration, residual scatter, CSR
+fill; multi-GPU: + interface exchange + residual-norm allreduce).  The mesh is element-partitioned into z-slabs
+over the N GPUs (strong scaling: total work fixed).
+
+One JSON line on rank 0.  `value` = quadrature-point updates / s of the update pass with inputs resident in HBM;
+`assembly_ms` = ms per Newton-iteration assembly; `e2e` = the same update pass through the public API with HOST
+(pinned) buffers: H2D of sol + state and D2H of the new state inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'jax-cpfem_b200'))
+
+import numpy as np
+import torch
+
+# ---- algorithmic work model (DESIGN.md "Work model"; flops with FMA = 2, integer pow(x,119) = 13 flops) ----------
+F_RES = 840.0            # one residual evaluation, 12 slip systems
+F_ITER = 2620.0          # one local Newton iteration = Newton matrix + 6x6 LU/solve + one residual evaluation
+F_UPDATE_FIXED = 2400.0  # kinematics + frame change + first residual + hardening/state update
+F_ASSEMBLY_FIXED = 17600.0  # kinematics + frame change + first residual + stress + tangent (11 k) + element K_e share (4.9 k)
+B_UPDATE = 610.0         # bytes/point: state in 336 + state out 264 + mesh/sol share 10
+B_ASSEMBLY = 740.0       # bytes/point: state in 240 + mesh/sol 10 + CSR memset 244 + CSR write 244 (+ residual)
+
+MESH_N = 200
+D_EPS, DT, PRE_STEPS = 2e-4, 2e-3, 10
+
+
+def _peaks():
+    p = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+            except Exception:
+                vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+                phys = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
+                     0x80: 'hw_power_brake_slowdown'}
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:          # sampling must never break the bench
+            self.reasons.add('sampler_error:' + type(e).__name__)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=2)
+        s = sorted(self.samples)
+        return {'sm_mhz': (s[len(s) // 2] if s else None), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle (torch fp64 autodiff restatement of the reference, all host threads)
+# on a bounded sample of the same workload
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference(n_mesh, sample_cells, steps, warmup):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import cpfem_oracle as O
+    from cpfem_b200 import synthetic
+    mat = O.steel304()
+    # the sample = the first `sample_cells` cells of the n^3 mesh (x-fastest numbering), same grains / load history
+    sx, sy = n_mesh + 1, (n_mesh + 1) ** 2
+    c = np.arange(sample_cells, dtype=np.int64)
+    i, j, k = c % n_mesh, (c // n_mesh) % n_mesh, c // (n_mesh * n_mesh)
+    b = i + sx * j + sy * k
+    cells_g = np.stack([b, b + 1, b + 1 + sx, b + sx, b + sy, b + 1 + sy, b + 1 + sx + sy, b + sx + sy], axis=1)
+    node_gid = np.unique(cells_g)
+    cells = np.searchsorted(node_gid, cells_g)
+    gi, gj, gk = node_gid % sx, (node_gid // sx) % sx, node_gid // sy
+    pts = np.stack([gi, gj, gk], axis=1) / float(n_mesh)
+    G = (n_mesh + 7) // 8
+    gid = (i // 8) + G * (j // 8) + G * G * (k // 8)
+    quat = synthetic.grain_quaternions(G ** 3, 0)
+    fe = O.FEOracle(pts, cells, O.make_uniform_batch_factory(mat))
+    params = O.initial_internal_vars(sample_cells, mat, O.get_rot_mat(quat)[gid])
+    noise = synthetic.noise_field(n_mesh)[node_gid]
+    disp = lambda s: synthetic.affine_displacement(pts, D_EPS * s) + noise
+    for s in range(1, PRE_STEPS + 1):
+        params = fe.update_int_vars_gp(disp(s), params, DT)
+    sol = disp(PRE_STEPS + 1)
+    t_upd, t_asm = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        fe.update_int_vars_gp(sol, params, DT)
+        t1 = time.perf_counter()
+        res, V = fe.newton_update(sol, params, DT)
+        A = O.csr_from_coo(V, fe.I, fe.J, fe.nn * 3)
+        t2 = time.perf_counter()
+        if it >= warmup:
+            t_upd.append(t1 - t0)
+            t_asm.append(t2 - t1)
+    npts = sample_cells * 8
+    return {'updates_per_s': npts * len(t_upd) / sum(t_upd), 'assembly_ms_sample': 1e3 * sum(t_asm) / len(t_asm),
+            'assembly_us_per_cell': 1e6 * sum(t_asm) / len(t_asm) / sample_cells, 'sample_points': npts,
+            'ms_per_step': 1e3 * (sum(t_upd) + sum(t_asm)) / len(t_upd), 'cores': torch.get_num_threads()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sample_cells = args.cpu_sample_cells
+    r = cpu_reference(args.n, sample_cells, args.steps, args.warmup)
+    sample = (f'first {sample_cells} cells ({r["sample_points"]} quad points) of the {args.n}^3 polycrystal, 10 load steps '
+              f'then the timed step, oracle port (torch fp64 + torch.func.jacfwd) on {r["cores"]} host threads')
+    line = {'metric': 'cp_quad_point_updates_per_s', 'value': r['updates_per_s'], 'unit': 'quad-point updates/s',
+            'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'synthetic {args.n}^3 hex8 polycrystal, 304 steel FCC12, load step 11 (bounded sample)',
+                       'sample_cells': sample_cells},
+            'assembly_ms': None, 'assembly_us_per_cell': r['assembly_us_per_cell'],
+            'cpu_baseline': {'value': r['updates_per_s'], 'unit': 'quad-point updates/s', 'cores': r['cores'], 'kind': 'port',
+                             'sample': sample, 'assembly_us_per_cell': r['assembly_us_per_cell']},
+            'e2e': {'value': r['updates_per_s'], 'unit': 'quad-point updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--n', type=int, default=MESH_N, help='mesh cells per edge (default 200 = BASELINE config)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample-cells', type=int, default=1024)
+    ap.add_argument('--layout', default='aos', choices=['aos', 'soa'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import cpfem_b200
+    from cpfem_b200 import Plan, api, make_material, synthetic, slip_systems
+    from cpfem_b200.partition import slab_partition_structured, ExchangePlan
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    N = args.n
+    K, W = args.steps, max(args.warmup, 0)
+
+    # ---- setup (untimed) ---------------------------------------------------------------------------------
+    rm = slab_partition_structured(N, world, rank)
+    plan = Plan(rm.cells, rm.points, slip_systems.FCC12)
+    plan.set_active_cells(rm.n_owned_cells)
+    nc = rm.n_owned_cells
+    npts = nc * 8
+    npts_global = 8 * N ** 3
+    mat = make_material(2.622e5, 1.120e5, 0.746e5, 392.9772, 7295.1754, 8.0, 1.0 / 120.0, 1.0, 0.001, 1e-8, 8)
+    G = (N + 7) // 8
+    cg = torch.as_tensor(rm.cell_gid[:nc], device=dev)
+    gid = (cg % N) // 8 + G * (((cg // N) % N) // 8) + G * G * ((cg // (N * N)) // 8)
+    from cpfem_b200.problem import get_rot_mat
+    Rg = torch.as_tensor(get_rot_mat(synthetic.grain_quaternions(G ** 3, 0)), device=dev)
+    rot = Rg[gid][:, None].expand(nc, 8, 3, 3).contiguous()
+    del gid, cg
+    Fp = torch.eye(3, dtype=torch.float64, device=dev).expand(nc, 8, 3, 3).contiguous()
+    g = torch.full((nc, 8, 12), 90.0, dtype=torch.float64, device=dev)
+    sl = torch.zeros(nc, 8, 12, dtype=torch.float64, device=dev)
+    noise = torch.as_tensor(synthetic.noise_field(N)[rm.node_gid], device=dev)
+    pts_d = torch.as_tensor(rm.points, device=dev)
+    scale = torch.tensor([-0.3, -0.3, 1.0], dtype=torch.float64, device=dev)
+    disp = lambda s: (pts_d * scale * (D_EPS * s) + noise).contiguous()
+    layout = api.LAYOUT_SOA if args.layout == 'soa' else api.LAYOUT_AOS
+    if layout == api.LAYOUT_SOA:
+        Fp, g, sl, rot = (api.aos_to_soa(t, c) for t, c in ((Fp, 9), (g, 12), (sl, 12), (rot, 9)))
+    cur = [Fp, g, sl, rot]
+    nxt = [torch.empty_like(Fp), torch.empty_like(g), torch.empty_like(sl)]
+    for s in range(1, PRE_STEPS + 1):
+        plan.update_state(mat, disp(s), cur, DT, out=nxt, layout=layout)
+        cur, nxt = [nxt[0], nxt[1], nxt[2], rot], [cur[0], cur[1], cur[2]]
+    sol = disp(PRE_STEPS + 1)
+    state = cur
+    out = nxt
+    res = torch.empty(plan.nn, 3, dtype=torch.float64, device=dev)
+    csr = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+    ex = None
+    if world > 1:
+        ip, ix = plan.csr_pattern()
+        ex = ExchangePlan(rm, ip, ix)
+        ex.prepare()
+    status_u = plan.new_status()
+    status_a = plan.new_status()
+    norm_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def do_update():
+        plan.update_state(mat, sol, state, DT, out=out, status=status_u, layout=layout)
+
+    def do_assembly():
+        plan.newton_update(mat, sol, state, DT, res=res, csr_data=csr, status=status_a, layout=layout)
+        if ex is not None:
+            ex.exchange(res, csr)
+            s = ex.owned_sumsq(res, norm_buf)
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        else:
+            norm_buf.zero_()
+            api.sumsq(res.reshape(-1), norm_buf)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        do_update()
+        do_assembly()
+    status_u.zero_()
+    status_a.zero_()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    for k in range(K):
+        ev[k][0].record()
+        do_update()
+        ev[k][1].record()
+        do_assembly()
+        ev[k][2].record()
+    barrier()
+    clocks = sampler.stop()
+    t_upd = sum(e[0].elapsed_time(e[1]) for e in ev)
+    t_asm = sum(e[1].elapsed_time(e[2]) for e in ev)
+    t_tot = ev[0][0].elapsed_time(ev[-1][2])
+    times = torch.tensor([t_upd, t_asm, t_tot], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_upd, t_asm, t_tot = times.tolist()
+    st_u = status_u.clone()
+    st_a = status_a.clone()
+    if world > 1:
+        dist.all_reduce(st_u[:2]); dist.all_reduce(st_a[:2])
+        s3 = torch.stack([st_u[3], st_a[3]]); dist.all_reduce(s3)
+        st_u[3], st_a[3] = s3[0], s3[1]
+    k_mean_u = float(st_u[3]) / (npts_global * K)
+    k_mean_a = float(st_a[3]) / (npts_global * K)
+    res_norm = float(torch.sqrt(norm_buf)[0])
+
+    # ---- e2e: host (pinned) buffers through the public API ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hin = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (sol, state[0], state[1], state[2], state[3])]
+        for h, t in zip(hin, (sol, state[0], state[1], state[2], state[3])):
+            h.copy_(t)
+        hout = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (out[0], out[1], out[2], res)]
+        dsol = torch.empty_like(sol)
+        dstate = [torch.empty_like(t) for t in state]
+        h2d = sum(h.numel() * 8 for h in hin)
+        d2h_state = sum(h.numel() * 8 for h in hout[:3])
+        d2h_res = hout[3].numel() * 8
+        Ke = max(1, min(K, 3))
+        te = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(Ke + 1)]
+        barrier()
+        for k in range(Ke + 1):                      # first pass is warm-up
+            te[k][0].record()
+            dsol.copy_(hin[0], non_blocking=True)
+            for d, h in zip(dstate, hin[1:]):
+                d.copy_(h, non_blocking=True)
+            te[k][1].record()
+            plan.update_state(mat, dsol, dstate, DT, out=out, layout=layout)
+            te[k][2].record()
+            for h, d in zip(hout[:3], out):
+                h.copy_(d, non_blocking=True)
+            te[k][3].record()
+            plan.newton_update(mat, dsol, dstate, DT, res=res, csr_data=csr, layout=layout)
+            if ex is not None:
+                ex.exchange(res, csr)
+            hout[3].copy_(res, non_blocking=True)
+            te[k][4].record()
+        barrier()
+        t_h2d = sum(e[0].elapsed_time(e[1]) for e in te[1:])
+        t_k = sum(e[1].elapsed_time(e[2]) for e in te[1:])
+        t_d2h = sum(e[2].elapsed_time(e[3]) for e in te[1:])
+        t_a = sum(e[3].elapsed_time(e[4]) for e in te[1:])
+        tt = torch.tensor([t_h2d + t_k + t_d2h, t_h2d + t_a], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tb = torch.tensor([h2d, d2h_state + d2h_res], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb)
+        e2e = {'value': npts_global * Ke / (tt[0].item() * 1e-3), 'unit': 'quad-point updates/s',
+               'h2d_bytes_per_step': int(tb[0].item()), 'd2h_bytes_per_step': int(tb[1].item()),
+               'assembly_ms': tt[1].item() / Ke, 'steps': Ke,
+               'what': 'update_int_vars_gp with pinned-host sol+state in, new state out; assembly_ms = H2D of sol+state + '
+                       'newton_update + D2H of the residual (CSR stays on the device for the device linear solver)'}
+        del hin, hout, dsol, dstate
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline (update kernel = the metric's kernel; assembly kernel reported beside it) ---------------------
+    peaks = _peaks()
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    hbm_src = 'measured (MEASURED_PEAKS.json, burst copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    fp64_peak = api.dfma_peak()
+    upd_s = t_upd * 1e-3 / K
+    asm_s = t_asm * 1e-3 / K
+    pts_rank = npts_global / world
+    f_upd = F_UPDATE_FIXED + F_ITER * k_mean_u
+    f_asm = F_ASSEMBLY_FIXED + F_ITER * k_mean_a
+    roof = {'bound': 'fp64', 'kernel': 'k_update_state<12>', 'achieved': pts_rank * f_upd / upd_s / 1e12, 'peak': fp64_peak,
+            'unit': 'TFLOP/s', 'frac': pts_rank * f_upd / upd_s / 1e12 / fp64_peak, 'traffic': None,
+            'peak_source': 'DFMA microbenchmark (cpfem_dfma_peak_kernel) measured in this run; B200 has no published '
+                           'measured FP64 figure in MEASURED_PEAKS.json',
+            'flops_per_point': f_upd, 'mean_local_newton_iters': k_mean_u,
+            'hbm': {'achieved': pts_rank * B_UPDATE / upd_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': pts_rank * B_UPDATE / upd_s / 1e9 / hbm_peak, 'bytes_per_point': B_UPDATE, 'peak_source': hbm_src},
+            'note': 'arithmetic intensity ~%.0f flop/B >> B200 balance (~5.7): the FP64 pipe is the bound; duration '
+                    'includes the interface exchange for the assembly figures' % (f_upd / B_UPDATE)}
+    roof_asm = {'bound': 'fp64', 'kernel': 'k_assemble<12,true>', 'achieved': pts_rank * f_asm / asm_s / 1e12, 'peak': fp64_peak,
+                'unit': 'TFLOP/s', 'frac': pts_rank * f_asm / asm_s / 1e12 / fp64_peak, 'traffic': None,
+                'flops_per_point': f_asm, 'mean_local_newton_iters': k_mean_a,
+                'hbm': {'achieved': pts_rank * B_ASSEMBLY / asm_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                        'frac': pts_rank * B_ASSEMBLY / asm_s / 1e9 / hbm_peak, 'bytes_per_point': B_ASSEMBLY}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(N, args.cpu_sample_cells, 2, 1)
+        cpu = {'value': r['updates_per_s'], 'unit': 'quad-point updates/s', 'cores': r['cores'], 'kind': 'port',
+               'sample': f'first {args.cpu_sample_cells} cells ({r["sample_points"]} points) of the same {N}^3 workload, oracle port '
+                         f'(torch fp64 + torch.func.jacfwd, restatement - JAX is not installable here)',
+               'assembly_us_per_cell': r['assembly_us_per_cell']}
+
+    line = {
+        'metric': 'cp_quad_point_updates_per_s', 'value': npts_global * K / (t_upd * 1e-3), 'unit': 'quad-point updates/s',
+        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': t_tot / K, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'synthetic {N}^3 hex8 polycrystal ({N ** 3} cells, {npts_global} quad points), 304 steel FCC12 '
+                               f'exponent 120, load step {PRE_STEPS + 1} (all points plastic), z-slab element partition',
+                   'partition': f'{world} slab(s)', 'state_layout': args.layout,
+                   'l2': 'inputs (>= 2 GB of state per pass) are larger than the 126 MB L2; no flush needed'},
+        'update_ms': t_upd / K, 'assembly_ms': t_asm / K, 'assembly_metric': 'ms per Newton-iteration assembly '
+        '(stress+tangent, hex8 integration, residual scatter, CSR fill, interface exchange, norm allreduce)',
+        'mean_local_newton_iters': k_mean_u, 'points_at_iter_cap': int(st_u[0]) + int(st_a[0]),
+        'nonfinite_points': int(st_u[1]) + int(st_a[1]), 'residual_norm': res_norm,
+        'roofline': roof, 'roofline_assembly': roof_asm, 'cpu_baseline': cpu, 'e2e': e2e,
+        'gpu_launches': K * (2 + (1 if world == 1 else 2 + 2 * len(rm.recv_nodes))), 'clocks': clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -66,6 +66,7 @@ class Plan:
             self.nnz = int(info[3])
             self.max_valence = int(info[4])
         self.ndof = 3 * self.nn
+        self.nc_active = self.nc
         self.np = 8 * self.nc
         self._indptr = None
         self._indices = None
@@ -77,6 +78,12 @@ class Plan:
                 self._h = None
         except Exception:
             pass
+
+    def set_active_cells(self, n_active):
+        """Element-partitioned runs: kernels loop over the first n_active (owned) cells; ghost cells keep their slots."""
+        check(_lib.lib().cpfem_plan_set_active_cells(self._h, int(n_active)), 'cpfem_plan_set_active_cells')
+        self.nc_active = int(n_active)
+        self.np = 8 * self.nc_active
 
     # ---- CSR pattern -------------------------------------------------------------------------
     def csr_pattern(self):
@@ -141,7 +148,7 @@ class Plan:
             if csr_data is None and want_csr:
                 csr_data = torch.empty(self.nnz, dtype=torch.float64, device=self.device)
             if coo_V is None and want_V:
-                coo_V = torch.empty(self.nc * 576, dtype=torch.float64, device=self.device)
+                coo_V = torch.empty(self.nc_active * 576, dtype=torch.float64, device=self.device)
             check(_lib.lib().cpfem_newton_update(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st), float(dt),
                                                  _ptr(res), _ptr(csr_data), _ptr(coo_V), _ptr(status), _stream()),
                   'cpfem_newton_update')
@@ -152,7 +159,7 @@ class Plan:
             st, ts = self._state(params, layout)
             sol = _dev_f64(sol, self.device)
             if out is None:
-                out = torch.empty(self.nc, 3, 3, dtype=torch.float64, device=self.device)
+                out = torch.empty(self.nc_active, 3, 3, dtype=torch.float64, device=self.device)
             check(_lib.lib().cpfem_avg_stress(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st), float(dt), _ptr(out),
                                               _ptr(status), _stream()), 'cpfem_avg_stress')
         return out

@@ -1,0 +1,282 @@
+"""Element partition of a hex8 mesh over ranks and the interface exchange that follows an assembly.
+
+Design (DESIGN.md "Multi-GPU"):
+  * cells are split into contiguous ranges (z-slabs for the structured meshes of the reference); the constitutive
+    update needs no communication at all;
+  * a node belongs to the LOWEST rank whose cells touch it; the global CSR is row-partitioned by that owner;
+  * each rank's local mesh = its owned cells followed by GHOST cells (cells of other ranks that touch one of its
+    owned nodes).  Ghost cells only contribute their sparsity pattern, so that the owner's rows already have a slot
+    for every column a neighbour will send; kernels run over the owned cells only (n_active);
+  * after the local assembly every rank sends, per neighbour, the residual entries and CSR rows of the nodes that
+    neighbour owns (packed in the sender's row order) and the owner adds them through a precomputed slot map.
+    One scalar allreduce gives the global residual norm over owned rows.
+
+The exchange is index plumbing around torch.distributed (NCCL on GPUs, gloo in the CPU tests); on CUDA tensors the
+pack / unpack-add / sum-of-squares steps are the library's own kernels (cpfem_gather / cpfem_scatter_add /
+cpfem_sumsq), on CPU tensors (tests only) they are torch index ops.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Optional
+
+import numpy as onp
+import torch
+
+
+@dataclasses.dataclass
+class RankMesh:
+    rank: int
+    world: int
+    cells: onp.ndarray            # (n_local_cells, 8) int32, LOCAL node ids; owned cells first, ghost cells last
+    n_owned_cells: int
+    points: onp.ndarray           # (n_local_nodes, 3)
+    node_gid: onp.ndarray         # (n_local_nodes,) int64 ascending
+    node_owner: onp.ndarray       # (n_local_nodes,) int32 owner rank of each local node
+    cell_gid: onp.ndarray         # (n_local_cells,) int64
+    send_nodes: Dict[int, onp.ndarray]   # peer -> local node ids (ascending gid) whose owner is `peer`
+    recv_nodes: Dict[int, onp.ndarray]   # peer -> local node ids (ascending gid) owned here, touched by peer's cells
+    n_global_nodes: int
+
+    @property
+    def owned_node_mask(self):
+        return self.node_owner == self.rank
+
+
+def cell_ranges(nc, world):
+    """Contiguous, balanced cell ranges."""
+    b = [(nc * r) // world for r in range(world + 1)]
+    return b
+
+
+def partition_cells(cells, points, world, rank, bounds=None) -> RankMesh:
+    """Generic partition of any hex8 mesh by contiguous cell ranges (host numpy)."""
+    cells = onp.asarray(cells, dtype=onp.int64)
+    nc, nn = len(cells), len(points)
+    bounds = cell_ranges(nc, world) if bounds is None else list(bounds)
+    rank_of_cell = onp.searchsorted(onp.asarray(bounds[1:]), onp.arange(nc), side='right').astype(onp.int32)
+    owner = onp.full(nn, world, dtype=onp.int32)
+    onp.minimum.at(owner, cells.reshape(-1), onp.repeat(rank_of_cell, 8))
+    c0, c1 = bounds[rank], bounds[rank + 1]
+    owned = onp.arange(c0, c1)
+    touches_mine = (owner[cells] == rank).any(axis=1)
+    ghost = onp.nonzero(touches_mine & (rank_of_cell != rank))[0]
+    cell_gid = onp.concatenate([owned, ghost])
+    lc = cells[cell_gid]
+    node_gid = onp.unique(lc)
+    local = onp.searchsorted(node_gid, lc).astype(onp.int32)
+    # nodes touched by my OWNED cells but owned elsewhere -> send to owner
+    mine_touched = onp.unique(cells[owned])
+    send, recv = {}, {}
+    own_t = owner[mine_touched]
+    for p in onp.unique(own_t):
+        if p != rank:
+            send[int(p)] = onp.searchsorted(node_gid, mine_touched[own_t == p]).astype(onp.int64)
+    # nodes I own that other ranks' owned cells touch -> receive from them
+    for p in range(world):
+        if p == rank:
+            continue
+        pt = onp.unique(cells[bounds[p]:bounds[p + 1]])
+        sel = pt[owner[pt] == rank]
+        if len(sel):
+            recv[p] = onp.searchsorted(node_gid, sel).astype(onp.int64)
+    return RankMesh(rank, world, local, len(owned), onp.asarray(points)[node_gid], node_gid.astype(onp.int64),
+                    owner[node_gid], cell_gid.astype(onp.int64), send, recv, nn)
+
+
+def slab_partition_structured(N, world, rank, lengths=(1., 1., 1.)) -> RankMesh:
+    """Analytic z-slab partition of the N^3 box mesh (generate_mesh.box_mesh numbering) - same result as
+    partition_cells(box_mesh(N,N,N), bounds = whole layers) without ever building the global mesh."""
+    layers = [(N * r) // world for r in range(world + 1)]
+    k0, k1 = layers[rank], layers[rank + 1]
+    has_ghost = rank < world - 1
+    kk1 = k1 + (1 if has_ghost else 0)               # cell layers in the local mesh: [k0, kk1)
+    sx, sy = N + 1, (N + 1) ** 2
+    xs = onp.linspace(0, lengths[0], N + 1)
+    ys = onp.linspace(0, lengths[1], N + 1)
+    zs = onp.linspace(0, lengths[2], N + 1)[k0:kk1 + 1]
+    Z, Y, X = onp.meshgrid(zs, ys, xs, indexing='ij')
+    points = onp.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    n0 = k0 * sy
+    node_gid = onp.arange(n0, (kk1 + 1) * sy, dtype=onp.int64)
+    k, j, i = onp.meshgrid(onp.arange(kk1 - k0, dtype=onp.int64), onp.arange(N, dtype=onp.int64),
+                           onp.arange(N, dtype=onp.int64), indexing='ij')
+    b = (i + sx * j + sy * k).ravel()
+    cells = onp.stack([b, b + 1, b + 1 + sx, b + sx, b + sy, b + 1 + sy, b + 1 + sx + sy, b + sx + sy], axis=1).astype(onp.int32)
+    cell_gid = onp.arange(k0 * N * N, kk1 * N * N, dtype=onp.int64)
+    plane = (node_gid - n0) // sy + k0                # global node-plane index of each local node
+    owner = onp.full(len(node_gid), rank, dtype=onp.int32)
+    if rank > 0:
+        owner[plane == k0] = rank - 1
+    if has_ghost:
+        # plane k1 is shared with rank+1 and owned here; the ghost plane k1+1 belongs to rank+1 (its lowest toucher)
+        owner[plane == kk1] = rank + 1
+    send, recv = {}, {}
+    if rank > 0:
+        send[rank - 1] = onp.nonzero(plane == k0)[0].astype(onp.int64)
+    if has_ghost:
+        recv[rank + 1] = onp.nonzero(plane == k1)[0].astype(onp.int64)
+    return RankMesh(rank, world, cells, (k1 - k0) * N * N, points, node_gid, owner, cell_gid, send, recv, (N + 1) ** 3)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# exchange plan
+# ----------------------------------------------------------------------------------------------------------
+def _rows_of_nodes(nodes: torch.Tensor):
+    return (3 * nodes[:, None] + torch.arange(3, device=nodes.device)[None, :]).reshape(-1)
+
+
+def _slots_of_rows(indptr: torch.Tensor, rows: torch.Tensor):
+    """Concatenated CSR slot ranges of `rows` (+ per-row lengths)."""
+    start = indptr[rows]
+    length = indptr[rows + 1] - start
+    total = int(length.sum())
+    off = torch.cumsum(length, 0) - length
+    rid = torch.repeat_interleave(torch.arange(len(rows), device=rows.device), length, output_size=total)
+    slots = start[rid] + (torch.arange(total, device=rows.device) - off[rid])
+    return slots, length, rid
+
+
+def _is_contiguous_range(idx: torch.Tensor):
+    if idx.numel() == 0:
+        return True
+    return bool((idx[-1] - idx[0] + 1 == idx.numel()).item()) and bool((idx[1:] - idx[:-1] == 1).all().item())
+
+
+class ExchangePlan:
+    """Send/receive maps of one rank, built once per mesh.  indptr/indices: the LOCAL CSR pattern (local column ids);
+    pg: torch.distributed process group (None = default)."""
+
+    def __init__(self, rm: RankMesh, indptr: torch.Tensor, indices: torch.Tensor, pg=None):
+        import torch.distributed as dist
+        self.rm, self.pg = rm, pg
+        dev = indptr.device
+        self.device = dev
+        gid = torch.as_tensor(rm.node_gid, device=dev)
+        self.send_rows, self.send_slots, self.recv_rows, self.recv_slots = {}, {}, {}, {}
+        self.send_contig = {}
+        ndof_g = 3 * rm.n_global_nodes
+        meta_send = {}
+        for p, nodes in sorted(rm.send_nodes.items()):
+            rows = _rows_of_nodes(torch.as_tensor(nodes, device=dev))
+            slots, length, rid = _slots_of_rows(indptr, rows)
+            self.send_rows[p], self.send_slots[p] = rows, slots
+            self.send_contig[p] = (_is_contiguous_range(rows), _is_contiguous_range(slots))
+            # keys = global_row * ndof_g + global_col of every entry sent
+            cols_l = indices[slots].to(torch.int64)
+            gcol = 3 * gid[cols_l // 3] + cols_l % 3
+            grow = (3 * gid[rows // 3] + rows % 3)[rid]
+            meta_send[p] = grow * ndof_g + gcol
+        # exchange the key lists (sizes first)
+        peers_s, peers_r = sorted(rm.send_nodes), sorted(rm.recv_nodes)
+        sizes_r = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p in peers_r}
+        ops = [dist.P2POp(dist.isend, torch.tensor([meta_send[p].numel()], dtype=torch.int64, device=dev), p, group=pg) for p in peers_s]
+        ops += [dist.P2POp(dist.irecv, sizes_r[p], p, group=pg) for p in peers_r]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        keys_r = {p: torch.empty(int(sizes_r[p].item()), dtype=torch.int64, device=dev) for p in peers_r}
+        ops = [dist.P2POp(dist.isend, meta_send[p], p, group=pg) for p in peers_s]
+        ops += [dist.P2POp(dist.irecv, keys_r[p], p, group=pg) for p in peers_r]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for p in peers_r:
+            rows = _rows_of_nodes(torch.as_tensor(rm.recv_nodes[p], device=dev))
+            slots, length, rid = _slots_of_rows(indptr, rows)
+            cols_l = indices[slots].to(torch.int64)
+            mykeys = (3 * gid[rows // 3] + rows % 3)[rid] * ndof_g + (3 * gid[cols_l // 3] + cols_l % 3)
+            pos = torch.searchsorted(mykeys, keys_r[p])
+            if pos.numel() and (int(pos.max()) >= mykeys.numel() or not bool((mykeys[pos] == keys_r[p]).all())):
+                raise RuntimeError('ExchangePlan: a neighbour sends a CSR entry this rank has no slot for '
+                                   '(ghost cells missing from the local pattern)')
+            self.recv_slots[p] = slots[pos]
+            # residual rows arrive in the sender's row order = ascending global dof = our `rows` order
+            self.recv_rows[p] = rows
+        owned = torch.as_tensor(rm.owned_node_mask, device=dev)
+        self.owned_rows = _rows_of_nodes(torch.nonzero(owned).reshape(-1))
+        self.owned_contig = _is_contiguous_range(self.owned_rows)
+        self._bufs = {}
+
+    # ---- runtime -------------------------------------------------------------------------------------
+    def _gather(self, src, idx, contig):
+        if contig and idx.numel():
+            return src[int(idx[0]):int(idx[0]) + idx.numel()]
+        if src.is_cuda:
+            from . import api
+            out = torch.empty(idx.numel(), dtype=src.dtype, device=src.device)
+            api.gather(src, idx, out)
+            return out
+        return src[idx]
+
+    def _scatter_add(self, dst, idx, val):
+        if dst.is_cuda:
+            from . import api
+            api.scatter_add(val, idx, dst)
+        else:
+            dst.index_add_(0, idx, val)
+
+    def prepare(self):
+        """Cache python ints for the contiguous fast paths (no device syncs at exchange time)."""
+        self._s0 = {p: (int(self.send_rows[p][0]), self.send_rows[p].numel(), int(self.send_slots[p][0]), self.send_slots[p].numel())
+                    for p in self.send_rows}
+        self._own = (int(self.owned_rows[0]), self.owned_rows.numel()) if self.owned_rows.numel() else (0, 0)
+
+    def exchange(self, res: torch.Tensor, csr_data: Optional[torch.Tensor]):
+        """Adds the neighbours' interface contributions into this rank's owned rows (res: (nn,3) or flat)."""
+        import torch.distributed as dist
+        if not hasattr(self, '_s0'):
+            self.prepare()
+        r = res.reshape(-1)
+        ops, recv_bufs = [], {}
+        keep = []
+        for p in sorted(self.send_rows):
+            r0, rn, s0, sn = self._s0[p]
+            rc, sc = self.send_contig[p]
+            sb = r[r0:r0 + rn] if rc else self._gather(r, self.send_rows[p], False)
+            ops.append(dist.P2POp(dist.isend, sb, p, group=self.pg))
+            keep.append(sb)
+            if csr_data is not None:
+                cb = csr_data[s0:s0 + sn] if sc else self._gather(csr_data, self.send_slots[p], False)
+                ops.append(dist.P2POp(dist.isend, cb, p, group=self.pg))
+                keep.append(cb)
+        for p in sorted(self.recv_rows):
+            key = (p, csr_data is not None)
+            if key not in self._bufs:
+                self._bufs[key] = (torch.empty(self.recv_rows[p].numel(), dtype=r.dtype, device=r.device),
+                                   torch.empty(self.recv_slots[p].numel(), dtype=r.dtype, device=r.device) if csr_data is not None else None)
+            rb, cb = self._bufs[key]
+            ops.append(dist.P2POp(dist.irecv, rb, p, group=self.pg))
+            if csr_data is not None:
+                ops.append(dist.P2POp(dist.irecv, cb, p, group=self.pg))
+            recv_bufs[p] = (rb, cb)
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for p, (rb, cb) in recv_bufs.items():
+            self._scatter_add(r, self.recv_rows[p], rb)
+            if csr_data is not None:
+                self._scatter_add(csr_data, self.recv_slots[p], cb)
+
+    def owned_sumsq(self, res: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """sum of squares of the residual over the rows this rank owns (device scalar)."""
+        if not hasattr(self, '_s0'):
+            self.prepare()
+        r = res.reshape(-1)
+        o0, on = self._own
+        seg = r[o0:o0 + on] if self.owned_contig else r[self.owned_rows]
+        if r.is_cuda:
+            from . import api
+            if out is None:
+                out = torch.zeros(1, dtype=torch.float64, device=r.device)
+            else:
+                out.zero_()
+            api.sumsq(seg.contiguous(), out)
+            return out
+        return (seg * seg).sum().reshape(1)
+
+    def global_res_norm(self, res: torch.Tensor):
+        import torch.distributed as dist
+        s = self.owned_sumsq(res).clone()
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=self.pg)
+        return torch.sqrt(s)

@@ -51,13 +51,19 @@ def polycrystal(N, grain=8, seed=0, z_range=None):
     return mesh, quat, gid
 
 
-def displacement(points, eps, N, seed=1, node_gid=None, n_total=None):
-    """Affine uniaxial field + nodal noise.  The noise is drawn for the whole N^3 mesh so that slabs see the
-    same values as the undivided mesh."""
+def noise_field(N, seed=1):
+    """Nodal noise U(-1,1) * 1e-6 / N for the whole (N+1)^3 node set (slabs index it with their global node ids)."""
     rng = onp.random.default_rng(seed)
-    n_all = (N + 1) ** 3 if n_total is None else n_total
-    noise = rng.uniform(-1, 1, size=(n_all, 3)) * (1e-6 / N)
+    return rng.uniform(-1, 1, size=((N + 1) ** 3, 3)) * (1e-6 / N)
+
+
+def affine_displacement(points, eps):
+    return onp.stack([-0.3 * eps * points[:, 0], -0.3 * eps * points[:, 1], eps * points[:, 2]], axis=1)
+
+
+def displacement(points, eps, N, seed=1, node_gid=None):
+    """Affine uniaxial field + nodal noise (same noise values whether the mesh is whole or cut into slabs)."""
+    noise = noise_field(N, seed)
     if node_gid is not None:
         noise = noise[node_gid]
-    u = onp.stack([-0.3 * eps * points[:, 0], -0.3 * eps * points[:, 1], eps * points[:, 2]], axis=1)
-    return u + noise
+    return affine_displacement(points, eps) + noise

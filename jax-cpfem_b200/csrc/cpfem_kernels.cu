@@ -49,6 +49,7 @@ extern "C" int cpfem_version(void) { return 100; }
 // -----------------------------------------------------------------------------------------------
 struct cpfem_plan {
     int64_t nc = 0, nn = 0, nnz = 0;
+    int64_t nc_active = 0;        // kernels loop over the first nc_active cells (owned cells of a partition)
     int32_t ns = 0;
     int32_t max_valence = 0;
     int32_t* cells = nullptr;     // (nc,8)
@@ -171,7 +172,7 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
     cudaStream_t stream = (cudaStream_t)stream_;
     cpfem_plan* p = new (std::nothrow) cpfem_plan();
     if (!p) return set_err(-3, "cpfem_plan_create: out of host memory");
-    p->nc = nc; p->nn = nnodes; p->ns = ns;
+    p->nc = nc; p->nc_active = nc; p->nn = nnodes; p->ns = ns;
     cudaGetDevice(&p->device);
     cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
     // slip table: normalise (models_copper.py:62-66)
@@ -273,6 +274,12 @@ extern "C" int cpfem_plan_csr_copy(const cpfem_plan* p, int64_t* indptr_out, int
     cudaStream_t stream = (cudaStream_t)stream_;
     if (indptr_out) CU_TRY(cudaMemcpyAsync(indptr_out, p->indptr, (3 * p->nn + 1) * sizeof(int64_t), cudaMemcpyDefault, stream));
     if (indices_out) CU_TRY(cudaMemcpyAsync(indices_out, p->indices, p->nnz * sizeof(int32_t), cudaMemcpyDefault, stream));
+    return 0;
+}
+extern "C" int cpfem_plan_set_active_cells(cpfem_plan* p, int64_t n_active) {
+    if (!p) return set_err(-1, "cpfem_plan_set_active_cells: null plan");
+    if (n_active < 1 || n_active > p->nc) return set_err(-1, "cpfem_plan_set_active_cells: out of range");
+    p->nc_active = n_active;
     return 0;
 }
 extern "C" int cpfem_plan_info(const cpfem_plan* p, int64_t* o) {
@@ -749,7 +756,7 @@ extern "C" int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* 
     if (!sol || !out || !out->Fp_inv || !out->g || !out->slip || !in->slip)
         return set_err(-1, "cpfem_update_state: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int64_t np = plan->nc * 8;
+    const int64_t np = plan->nc_active * 8;
     const unsigned grid = (unsigned)((np + 127) / 128);
     StateView v = make_view(in);
     CpMaterial m = to_mat(mat);
@@ -772,11 +779,11 @@ static int launch_assemble(const cpfem_plan* plan, const CpMaterial& m, const do
     int bps = 1;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem));
     if (bps < 1) return set_err(-2, "cpfem assemble kernel does not fit on an SM");
-    const int64_t nquads = (plan->nc + 3) / 4;
+    const int64_t nquads = (plan->nc_active + 3) / 4;
     int64_t grid = (int64_t)plan->sm_count * bps;
     const int64_t need = (nquads + wpb - 1) / wpb;
     if (grid > need) grid = need;
-    kern<<<(unsigned)grid, wpb * 32, smem, stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, plan->nc,
+    kern<<<(unsigned)grid, wpb * 32, smem, stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, plan->nc_active,
                                                      plan->indptr, plan->rank, res, csr_data, coo_V, (long long*)status, wpb);
     CU_TRY(cudaGetLastError());
     return 0;
@@ -816,7 +823,7 @@ extern "C" int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* ma
     if (rc) return rc;
     if (!sol || !sigma_cell) return set_err(-1, "cpfem_avg_stress: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int64_t np = plan->nc * 8;
+    const int64_t np = plan->nc_active * 8;
     const unsigned grid = (unsigned)((np + 127) / 128);
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
