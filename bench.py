@@ -368,7 +368,7 @@ def main():
                     'frac': pts_rank * B_UPDATE / upd_s / 1e9 / hbm_peak, 'bytes_per_point': B_UPDATE, 'peak_source': hbm_src},
             'note': 'arithmetic intensity ~%.0f flop/B >> B200 balance (~5.7): the FP64 pipe is the bound; duration '
                     'includes the interface exchange for the assembly figures' % (f_upd / B_UPDATE)}
-    roof_asm = {'bound': 'fp64', 'kernel': 'k_assemble<12,true>', 'achieved': pts_rank * f_asm / asm_s / 1e12, 'peak': fp64_peak,
+    roof_asm = {'bound': 'fp64', 'kernel': 'k_point_tangent<12,119> + k_element_tangent', 'achieved': pts_rank * f_asm / asm_s / 1e12, 'peak': fp64_peak,
                 'unit': 'TFLOP/s', 'frac': pts_rank * f_asm / asm_s / 1e12 / fp64_peak, 'traffic': None,
                 'flops_per_point': f_asm, 'mean_local_newton_iters': k_mean_a,
                 'hbm': {'achieved': pts_rank * B_ASSEMBLY / asm_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
@@ -395,7 +395,7 @@ def main():
         'mean_local_newton_iters': k_mean_u, 'points_at_iter_cap': int(st_u[0]) + int(st_a[0]),
         'nonfinite_points': int(st_u[1]) + int(st_a[1]), 'residual_norm': res_norm,
         'roofline': roof, 'roofline_assembly': roof_asm, 'cpu_baseline': cpu, 'e2e': e2e,
-        'gpu_launches': K * (2 + (1 if world == 1 else 2 + 2 * len(rm.recv_nodes))), 'clocks': clocks,
+        'gpu_launches': K * (1 + 2 * (-(-nc // plan.chunk_cells)) + (1 if world == 1 else 2 + 2 * len(rm.recv_nodes))), 'clocks': clocks,
     }
     print(json.dumps(line))
     if world > 1:

@@ -97,7 +97,7 @@ int cpfem_plan_csr_copy(const cpfem_plan* plan, int64_t* indptr_out, int32_t* in
 /* Element-partitioned runs: the plan's mesh is "owned cells followed by ghost cells" (ghost cells only contribute
  * sparsity); restrict the kernels to the first n_active cells.  State arrays then have n_active*8 points. */
 int cpfem_plan_set_active_cells(cpfem_plan* plan, int64_t n_active);
-/* Sizes: nc, nnodes, ns, nnz, max node valence. out[5]. */
+/* Sizes: nc, nnodes, ns, nnz, max node valence, cells per assembly chunk. out[6]. */
 int cpfem_plan_info(const cpfem_plan* plan, int64_t* out);
 
 /* update_int_vars_gp: sol (nnodes,3) + old state -> new state.  in/out may alias array-wise. */

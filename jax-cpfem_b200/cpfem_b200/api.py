@@ -61,10 +61,11 @@ class Plan:
                                       slip.ctypes.data_as(ctypes.c_void_p), self.ns, _stream(), ctypes.byref(h)),
                   'cpfem_plan_create')
             self._h = h
-            info = (ctypes.c_int64 * 5)()
+            info = (ctypes.c_int64 * 6)()
             check(L.cpfem_plan_info(self._h, info), 'cpfem_plan_info')
             self.nnz = int(info[3])
             self.max_valence = int(info[4])
+            self.chunk_cells = int(info[5])
         self.ndof = 3 * self.nn
         self.nc_active = self.nc
         self.np = 8 * self.nc

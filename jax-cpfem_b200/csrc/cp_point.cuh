@@ -20,6 +20,17 @@
 // scaled form  N z = -C^-1 r,  N = C^-1 D^-1 + sum_a w_a e_a etilde_a^T,  inc = D^-1 z  (D = diag(1,1,1,2,2,2)),
 // which is symmetric positive definite up to O(strain) terms, so the LU needs no pivoting.
 //
+// Code shape (sm_100a: 64 DFMA/clk/SM, 32 KB L1.5 instruction cache, 64 K registers per SM):
+//   * the loops over slip systems are ROLLED (unrolled by 4 / 2 only, for ILP in the power-law chains); the
+//     per-system arrays (1/g and w = d dgamma / d tau) live behind an accessor `Arr` that the kernels point at a
+//     per-thread column of shared memory, so they cost no registers and the Newton loop body stays inside the
+//     instruction cache;
+//   * the per-system constants (etilde, d n^T, d, n) are one 192-byte record in the kernel-parameter constant bank;
+//   * |x|^(n-1) with a compile-time integer exponent (POWN = 9, 19, 119: copper, DP steel, 304 steel) is a
+//     straight-line square-and-multiply chain; POWN = 0 takes the exponent at run time (per point);
+//   * the local Newton solve is ONE loop over residual evaluations (a small state machine), so that the residual
+//     code exists once and lanes of a warp that are at different line-search trials still share every evaluation.
+//
 // The functions are __host__ __device__ so that tests can compile this header with g++ and compare the
 // algebra with the oracle on a machine without a GPU (tests/hostcheck).  The product only ever calls
 // them from the CUDA kernels in cpfem_kernels.cu.
@@ -48,15 +59,48 @@ struct CpMaterial {
     int max_iter;           // safety cap (reference has none; hitting it is reported in the status word)
 };
 
-// Normalised slip normals / directions of the crystal (models_copper.py:62-66), passed by value as a
-// kernel parameter so that every access is a uniform constant-bank read.
-struct CpSlip {
-    double d[CP_MAX_NS * 3];
-    double n[CP_MAX_NS * 3];
+// One slip system in the crystal frame, from the normalised normal n and direction d of the slip table
+// (models_copper.py:62-69).  24 doubles = 192 bytes.
+struct CpSlipSys {
+    double Et[6];   // strain-like Voigt of sym(d n^T): d0n0, d1n1, d2n2, (d1n2+d2n1)/2, (d0n2+d2n0)/2, (d0n1+d1n0)/2
+    double M[9];    // d n^T, row-major
+    double d[3];
+    double n[3];
+    double pad[3];
 };
+struct CpSlip {
+    CpSlipSys sys[CP_MAX_NS];
+};
+
+// rows of `slip6`: normal(3) direction(3), un-normalised, as in data/csv/input_slip_sys*.txt.  Returns false on a zero vector.
+inline bool cp_slip_init(CpSlip* sl, const double* slip6, int ns) {
+    for (int a = 0; a < CP_MAX_NS; ++a)
+        for (int i = 0; i < 24; ++i) ((double*)&sl->sys[a])[i] = 0.0;
+    for (int a = 0; a < ns; ++a) {
+        const double* row = slip6 + 6 * a;
+        const double nn = sqrt(row[0] * row[0] + row[1] * row[1] + row[2] * row[2]);
+        const double dn = sqrt(row[3] * row[3] + row[4] * row[4] + row[5] * row[5]);
+        if (!(nn > 0.0) || !(dn > 0.0)) return false;
+        CpSlipSys& y = sl->sys[a];
+        for (int i = 0; i < 3; ++i) { y.n[i] = row[i] / nn; y.d[i] = row[3 + i] / dn; }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) y.M[3 * i + j] = y.d[i] * y.n[j];
+        y.Et[0] = y.M[0]; y.Et[1] = y.M[4]; y.Et[2] = y.M[8];
+        y.Et[3] = 0.5 * (y.M[5] + y.M[7]); y.Et[4] = 0.5 * (y.M[2] + y.M[6]); y.Et[5] = 0.5 * (y.M[1] + y.M[3]);
+    }
+    return true;
+}
 
 struct CpPointParams {   // per-point values actually used at one quadrature point
     double C11, C12, C44, h, t_sat, gss_a, n_exp /* = 1/xm */, r;
+};
+
+// Per-thread array of one double per slip system.  STRIDE = 1 on the host; on the device the kernels point it at
+// column threadIdx.x of a [NS][blockDim] shared-memory tile (conflict-free).
+template <int STRIDE>
+struct CpArr {
+    double* p;
+    CP_HD double& operator[](int a) const { return p[a * STRIDE]; }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -101,12 +145,22 @@ CP_HD void sym6_to_m3(const double* s, double* S) {
     S[5] = S[7] = s[3]; S[2] = S[6] = s[4]; S[1] = S[3] = s[5];
 }
 
-// |x|^e for x >= 0.  Exactly-integer exponents (9, 19, 119 for the Cu/DP/304 parameter sets) take the
-// square-and-multiply path; everything else (tantalum: 44.2726) goes through pow().
+// x^N, N a compile-time integer >= 0: straight-line square-and-multiply (x^119 = 11 multiplications)
+template <int N>
+CP_HD double cp_ipow(double x) {
+    if (N == 0) return 1.0;
+    if (N == 1) return x;
+    const double h = cp_ipow<N / 2>(x);
+    return (N & 1) ? h * h * x : h * h;
+}
+
+// x^e for x >= 0, run-time e.  Integers take the square-and-multiply loop, half-integers add one sqrt
+// (copper's hardening exponent 2.5), everything else (tantalum: 44.2726) goes through pow().
 CP_HD double cp_pow_pos(double x, double e) {
-    if (e == floor(e) && e >= 0.0 && e < 2048.0) {
+    const double e2 = e + e;
+    if (e2 == floor(e2) && e >= 0.0 && e < 2048.0) {
         int k = (int)e;
-        double r = 1.0;
+        double r = ((double)k == e) ? 1.0 : sqrt(x);
         while (k) {
             if (k & 1) r *= x;
             x *= x;
@@ -117,38 +171,79 @@ CP_HD double cp_pow_pos(double x, double e) {
     return pow(x, e);
 }
 
+// |x_u|^(n-1) for U slip systems at once.  POWN > 0: compile-time integer exponent; POWN == 0: run-time n1.
+template <int POWN, int U>
+CP_HD void cp_rate_pow(const double* ax /*U, >= 0*/, double n1, double* out) {
+    if (POWN > 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) out[u] = cp_ipow<(POWN > 0 ? POWN : 1)>(ax[u]);
+    } else {
+        if (n1 == floor(n1) && n1 >= 0.0 && n1 < 2048.0) {
+            int k = (int)n1;
+            double x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { out[u] = 1.0; x[u] = ax[u]; }
+            while (k) {
+                if (k & 1) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) out[u] *= x[u];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) x[u] *= x[u];
+                k >>= 1;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) out[u] = pow(ax[u], n1);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
-// One residual evaluation at s (crystal frame).  Also returns what the next Jacobian needs.
-//   tau_a  = d_a . S n_a                          (models_copper.py:173)
-//   dg_a   = ao dt |tau/g|^(1/xm) sign(tau)       (:174)
+// One residual evaluation at s (crystal frame).  Also leaves what the next Newton matrix needs (w, Fe).
+//   tau_a  = d_a . S n_a = etilde_a . (D s)            (models_copper.py:173)
+//   dg_a   = ao dt |tau/g|^(1/xm) sign(tau)            (:174)
 //   w_a    = d dg_a / d tau_a = ao dt n |tau/g|^(n-1) / g
-//   Fe     = G (I - sum_a dg_a d_a n_a^T)         (:188-191)
-//   r      = s - C : 1/2 (Fe^T Fe - I)            (:199)
-// returns ||r||_F over the 9 entries (:212, np.linalg.norm of the 9-vector)
+//   Fe     = G (I - sum_a dg_a d_a n_a^T)              (:188-191)
+//   r      = s - C : 1/2 (Fe^T Fe - I)                 (:199)
+// returns ||r||_F over the 9 entries (:212, np.linalg.norm of the 9-vector).
+// `s_is_zero`: the caller knows s == 0 and n > 1, where every tau, dg and w vanishes (first evaluation of every solve).
 // ---------------------------------------------------------------------------------------------------
-template <int NS>
-CP_HD double cp_residual(const CpSlip& sl, const CpPointParams& pm, double cdt, const double* G, const double* ginv,
-                         const double* s, double* r, double* w, double* Fe, double* Lp) {
-    const double n1 = pm.n_exp - 1.0;
+template <int NS, int POWN, class Arr>
+CP_HD double cp_residual(const CpSlip& sl, const CpPointParams& pm, double cdt, const double* G, const Arr& ginv,
+                         const Arr& w, const double* s, bool s_is_zero, double* r, double* Fe, double* Lp) {
+    constexpr int U = 4;
+    static_assert(NS % U == 0, "slip systems are processed four at a time");
 #pragma unroll
     for (int i = 0; i < 9; ++i) Lp[i] = 0.0;
+    if (s_is_zero) {
+#pragma unroll 1
+        for (int a = 0; a < NS; ++a) w[a] = 0.0;
+    } else {
+        const double n1 = pm.n_exp - 1.0;
+        const double cn = cdt * pm.n_exp;
+        const double s3 = s[3] + s[3], s4 = s[4] + s[4], s5 = s[5] + s[5];
+#pragma unroll 1
+        for (int a0 = 0; a0 < NS; a0 += U) {
+            double x[U], ax[U], pw[U], gi[U];
 #pragma unroll
-    for (int a = 0; a < NS; ++a) {
-        const double d0 = sl.d[3 * a], d1 = sl.d[3 * a + 1], d2 = sl.d[3 * a + 2];
-        const double n0 = sl.n[3 * a], nn1 = sl.n[3 * a + 1], n2 = sl.n[3 * a + 2];
-        const double v0 = s[0] * n0 + s[5] * nn1 + s[4] * n2;
-        const double v1 = s[5] * n0 + s[1] * nn1 + s[3] * n2;
-        const double v2 = s[4] * n0 + s[3] * nn1 + s[2] * n2;
-        const double tau = d0 * v0 + d1 * v1 + d2 * v2;
-        const double x = tau * ginv[a];
-        const double pn1 = cp_pow_pos(fabs(x), n1);
-        const double cp = cdt * pn1;
-        const double dg = cp * x;
-        w[a] = cp * pm.n_exp * ginv[a];
-        const double e0 = dg * d0, e1 = dg * d1, e2 = dg * d2;
-        Lp[0] += e0 * n0; Lp[1] += e0 * nn1; Lp[2] += e0 * n2;
-        Lp[3] += e1 * n0; Lp[4] += e1 * nn1; Lp[5] += e1 * n2;
-        Lp[6] += e2 * n0; Lp[7] += e2 * nn1; Lp[8] += e2 * n2;
+            for (int u = 0; u < U; ++u) {
+                const CpSlipSys& y = sl.sys[a0 + u];
+                const double tau = y.Et[0] * s[0] + y.Et[1] * s[1] + y.Et[2] * s[2] + y.Et[3] * s3 + y.Et[4] * s4 + y.Et[5] * s5;
+                gi[u] = ginv[a0 + u];
+                x[u] = tau * gi[u];
+                ax[u] = fabs(x[u]);
+            }
+            cp_rate_pow<POWN, U>(ax, n1, pw);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const CpSlipSys& y = sl.sys[a0 + u];
+                const double dg = (cdt * pw[u]) * x[u];
+                w[a0 + u] = (cn * pw[u]) * gi[u];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Lp[i] += dg * y.M[i];
+            }
+        }
     }
     // Fe = G - G Lp
 #pragma unroll
@@ -178,9 +273,9 @@ CP_HD double cp_residual(const CpSlip& sl, const CpPointParams& pm, double cdt, 
 //   etilde_a = voigt(sym(d_a n_a^T))   (strain-like: shear entries carry the 1/2)
 // After the call N holds L (unit lower) and U; piv[i] = 1/U_ii.
 // ---------------------------------------------------------------------------------------------------
-template <int NS>
+template <int NS, class Arr>
 CP_HD void cp_newton_matrix(const CpSlip& sl, const CpPointParams& pm, const double* G, const double* Fe,
-                            const double* w, double* N /*36*/, double* piv /*6*/) {
+                            const Arr& w, double* N /*36*/, double* piv /*6*/) {
     double K[9];
     m3_mul_tn(Fe, G, K);
     const double den = (pm.C11 - pm.C12) * (pm.C11 + 2.0 * pm.C12);
@@ -190,23 +285,20 @@ CP_HD void cp_newton_matrix(const CpSlip& sl, const CpPointParams& pm, const dou
     N[0] = N[7] = N[14] = S11;
     N[1] = N[2] = N[6] = N[8] = N[12] = N[13] = S12;
     N[21] = N[28] = N[35] = S44q;
-#pragma unroll
+#pragma unroll 2
     for (int a = 0; a < NS; ++a) {
-        const double d0 = sl.d[3 * a], d1 = sl.d[3 * a + 1], d2 = sl.d[3 * a + 2];
-        const double n0 = sl.n[3 * a], n1 = sl.n[3 * a + 1], n2 = sl.n[3 * a + 2];
-        const double k0 = K[0] * d0 + K[1] * d1 + K[2] * d2;
-        const double k1 = K[3] * d0 + K[4] * d1 + K[5] * d2;
-        const double k2 = K[6] * d0 + K[7] * d1 + K[8] * d2;
-        double e[6], t[6];
-        const double wa = w[a];
-        e[0] = wa * (k0 * n0); e[1] = wa * (k1 * n1); e[2] = wa * (k2 * n2);
-        e[3] = wa * 0.5 * (k1 * n2 + k2 * n1); e[4] = wa * 0.5 * (k0 * n2 + k2 * n0); e[5] = wa * 0.5 * (k0 * n1 + k1 * n0);
-        t[0] = d0 * n0; t[1] = d1 * n1; t[2] = d2 * n2;
-        t[3] = 0.5 * (d1 * n2 + d2 * n1); t[4] = 0.5 * (d0 * n2 + d2 * n0); t[5] = 0.5 * (d0 * n1 + d1 * n0);
+        const CpSlipSys& y = sl.sys[a];
+        const double k0 = K[0] * y.d[0] + K[1] * y.d[1] + K[2] * y.d[2];
+        const double k1 = K[3] * y.d[0] + K[4] * y.d[1] + K[5] * y.d[2];
+        const double k2 = K[6] * y.d[0] + K[7] * y.d[1] + K[8] * y.d[2];
+        const double wa = w[a], wh = 0.5 * wa;
+        double e[6];
+        e[0] = wa * (k0 * y.n[0]); e[1] = wa * (k1 * y.n[1]); e[2] = wa * (k2 * y.n[2]);
+        e[3] = wh * (k1 * y.n[2] + k2 * y.n[1]); e[4] = wh * (k0 * y.n[2] + k2 * y.n[0]); e[5] = wh * (k0 * y.n[1] + k1 * y.n[0]);
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-            for (int j = 0; j < 6; ++j) N[6 * i + j] += e[i] * t[j];
+            for (int j = 0; j < 6; ++j) N[6 * i + j] += e[i] * y.Et[j];
     }
     // in-place LU (Doolittle), no pivoting
 #pragma unroll
@@ -253,50 +345,61 @@ struct CpSolveInfo {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// Local Newton solve, literal control flow of models_copper.py:204-249:
+// Local Newton solve, control flow of models_copper.py:204-249:
 //   y = 0 ; r = res(y)
 //   while ||r|| > tol:  inc = solve(J(y), -r); relax = 1; crt = r; sub = 0
 //        while ||crt|| >= ||r|| and sub < max_sub_step:  crt = res(y + relax inc); relax /= 2; sub++
 //        y += 2 relax inc ; r = crt
+// written as ONE loop over residual evaluations: `st` is the point being evaluated, (s, rn) the accepted iterate.
+// The first Newton step needs no matrix: at y = 0 every w_a is 0 (n > 1), J = I and inc = -r exactly.
 // On return s, w, Fe, Lp are consistent with the last residual evaluation, which is the one at the
 // returned s (bitwise: y + relax*inc and y + 2*(relax/2)*inc are the same number).
 // ---------------------------------------------------------------------------------------------------
-template <int NS>
+template <int NS, int POWN, class Arr>
 CP_HD void cp_newton(const CpSlip& sl, const CpPointParams& pm, double cdt, double tol, int max_sub, int max_iter,
-                     const double* G, const double* ginv, double* s, double* w, double* Fe, double* Lp,
+                     const double* G, const Arr& ginv, const Arr& w, double* s, double* Fe, double* Lp,
                      CpSolveInfo& info) {
-    double r[6];
+    double r[6], st[6], inc[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) s[i] = 0.0;
-    double rn = cp_residual<NS>(sl, pm, cdt, G, ginv, s, r, w, Fe, Lp);
-    info.iters = 0; info.evals = 1; info.status = 0;
-    while (rn > tol) {
-        if (info.iters >= max_iter) { info.status |= 1; break; }
-        double N[36], piv[6], inc[6];
-        cp_newton_matrix<NS>(sl, pm, G, Fe, w, N, piv);
-        cp_compliance_neg(pm, r, inc);
-        cp_lu_solve(N, piv, inc);
-        inc[3] *= 0.5; inc[4] *= 0.5; inc[5] *= 0.5;          // inc = D^-1 z
-        double relax = 1.0, crtn = rn;
-        int sub = 0;
-        double st[6];
-        while (crtn >= rn && sub < max_sub) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) st[i] = s[i] + relax * inc[i];
-            crtn = cp_residual<NS>(sl, pm, cdt, G, ginv, st, r, w, Fe, Lp);
+    for (int i = 0; i < 6; ++i) { s[i] = 0.0; st[i] = 0.0; inc[i] = 0.0; }
+    const bool zero_ok = pm.n_exp > 1.0;
+    double rn = 0.0, relax = 1.0;
+    int sub = 0;
+    bool first = true;
+    info.iters = 0; info.evals = 0; info.status = 0;
+    for (;;) {
+        const double crtn = cp_residual<NS, POWN>(sl, pm, cdt, G, ginv, w, st, first && zero_ok, r, Fe, Lp);
+        ++info.evals;
+        if (!first) {
             relax *= 0.5;
             ++sub;
-            ++info.evals;
-        }
-        if (sub == 0) {
-            // only reachable when rn is NaN (comparison false): mimic the reference, which would leave y as is
-            info.status |= 2;
-            break;
-        }
+            if (crtn >= rn && sub < max_sub) {           // line search: next trial y + relax inc
 #pragma unroll
-        for (int i = 0; i < 6; ++i) s[i] = s[i] + 2.0 * relax * inc[i];
+                for (int i = 0; i < 6; ++i) st[i] = s[i] + relax * inc[i];
+                continue;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s[i] = st[i];    // accept: y + 2 relax inc == the point just evaluated
+            ++info.iters;
+        }
         rn = crtn;
-        ++info.iters;
+        if (!(rn > tol)) break;
+        if (info.iters >= max_iter) { info.status |= 1; break; }
+        if (first && zero_ok) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) inc[i] = -r[i];
+        } else {
+            double N[36], piv[6];
+            cp_newton_matrix<NS>(sl, pm, G, Fe, w, N, piv);
+            cp_compliance_neg(pm, r, inc);
+            cp_lu_solve(N, piv, inc);
+            inc[3] *= 0.5; inc[4] *= 0.5; inc[5] *= 0.5;          // inc = D^-1 z
+        }
+        first = false;
+        relax = 1.0;
+        sub = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) st[i] = s[i] + inc[i];
     }
     if (!(rn == rn)) info.status |= 2;
 }
@@ -315,91 +418,95 @@ CP_HD void cp_to_lab(const double* R, const double* Mc, double* M) {         // 
     m3_mul_nt(T, R, M);
 }
 
-template <int NS>
+template <class Arr>
 struct CpPointState {       // everything the output stages need, crystal frame
-    double G[9], Ac[9], Fc[9];
-    double s[6], w[NS], Fe[9], Lp[9];
-    double ginv[NS];
+    double G[9], Ac[9];
+    double s[6], Fe[9], Lp[9];
+    Arr ginv, w;            // per-slip-system arrays (1/g_old, d dgamma / d tau at the solution)
     double cdt;
     CpSolveInfo info;
 };
 
-// Set-up + solve for one point.  H = u_grad (lab), A = Fp_inv_old (lab), g = slip resistances, R = rot_mat.
-template <int NS>
+// Set-up + solve for one point.  H = u_grad (lab), A = Fp_inv_old (lab), g = slip resistances (any indexable),
+// R = rot_mat.  ps.ginv / ps.w must point at storage for NS doubles each.
+template <int NS, int POWN, class Arr, class GIn>
 CP_HD void cp_point_solve(const CpSlip& sl, const CpMaterial& mat, const CpPointParams& pm, double dt,
-                          const double* H, const double* A, const double* g, const double* R, CpPointState<NS>& ps) {
-    double F[9];
+                          const double* H, const double* A, const GIn& g, const double* R, CpPointState<Arr>& ps) {
+    {
+        double F[9], Fc[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) F[i] = H[i];
-    F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
-    cp_to_crystal(R, F, ps.Fc);
-    cp_to_crystal(R, A, ps.Ac);
-    m3_mul(ps.Fc, ps.Ac, ps.G);
-#pragma unroll
+        for (int i = 0; i < 9; ++i) F[i] = H[i];
+        F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
+        cp_to_crystal(R, F, Fc);
+        cp_to_crystal(R, A, ps.Ac);
+        m3_mul(Fc, ps.Ac, ps.G);
+    }
+#pragma unroll 4
     for (int a = 0; a < NS; ++a) ps.ginv[a] = 1.0 / g[a];
     ps.cdt = mat.ao * dt;
-    cp_newton<NS>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.s, ps.w, ps.Fe, ps.Lp, ps.info);
+    cp_newton<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp, ps.info);
 }
 
 // New state (models_copper.py:164-169 via helper :172-192): Fp_inv_new (lab), g_new, slip_new.
-template <int NS>
-CP_HD void cp_point_state_update(const CpSlip& sl, const CpPointParams& pm, const CpPointState<NS>& ps,
-                                 const double* g, const double* slip_old, const double* R,
-                                 double* A_new_lab, double* g_new, double* slip_new) {
-    double ImL[9], Anc[9];
+// g / slip_old are read and g_new / slip_new written through indexable accessors (global memory in the kernels);
+// ps.w is overwritten with the hardening terms t_a.
+template <int NS, class Arr, class GIn, class GOut>
+CP_HD void cp_point_state_update(const CpSlip& sl, const CpPointParams& pm, const CpPointState<Arr>& ps,
+                                 const GIn& g, const GIn& slip_old, const double* R,
+                                 double* A_new_lab, const GOut& g_new, const GOut& slip_new) {
+    {
+        double ImL[9], Anc[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) ImL[i] = -ps.Lp[i];
-    ImL[0] += 1.0; ImL[4] += 1.0; ImL[8] += 1.0;
-    m3_mul(ps.Ac, ImL, Anc);
-    cp_to_lab(R, Anc, A_new_lab);
-    double S[9];
-    sym6_to_m3(ps.s, S);
+        for (int i = 0; i < 9; ++i) ImL[i] = -ps.Lp[i];
+        ImL[0] += 1.0; ImL[4] += 1.0; ImL[8] += 1.0;
+        m3_mul(ps.Ac, ImL, Anc);
+        cp_to_lab(R, Anc, A_new_lab);
+    }
+    const double s3 = ps.s[3] + ps.s[3], s4 = ps.s[4] + ps.s[4], s5 = ps.s[5] + ps.s[5];
+    const double inv_n = 1.0 / pm.n_exp, inv_tsat = 1.0 / pm.t_sat;
     double tsum = 0.0;
-    double t[NS];
-#pragma unroll
+#pragma unroll 2
     for (int a = 0; a < NS; ++a) {
+        const CpSlipSys& y = sl.sys[a];
         // dgamma_a recomputed from w_a: dg = w tau / n
-        const double d0 = sl.d[3 * a], d1 = sl.d[3 * a + 1], d2 = sl.d[3 * a + 2];
-        const double n0 = sl.n[3 * a], n1 = sl.n[3 * a + 1], n2 = sl.n[3 * a + 2];
-        const double tau = d0 * (S[0] * n0 + S[1] * n1 + S[2] * n2) + d1 * (S[3] * n0 + S[4] * n1 + S[5] * n2) +
-                           d2 * (S[6] * n0 + S[7] * n1 + S[8] * n2);
-        const double dg = ps.w[a] * tau / pm.n_exp;
+        const double tau = y.Et[0] * ps.s[0] + y.Et[1] * ps.s[1] + y.Et[2] * ps.s[2] + y.Et[3] * s3 + y.Et[4] * s4 + y.Et[5] * s5;
+        const double dg = ps.w[a] * tau * inv_n;
         slip_new[a] = slip_old[a] + dg;
-        const double y = 1.0 - g[a] / pm.t_sat;
-        const double sg = (y > 0.0) ? 1.0 : ((y < 0.0) ? -1.0 : 0.0);
-        t[a] = pm.h * fabs(dg) * pow(fabs(y), pm.gss_a) * sg;       // :178
-        tsum += t[a];
+        const double yy = 1.0 - g[a] * inv_tsat;
+        const double sg = (yy > 0.0) ? 1.0 : ((yy < 0.0) ? -1.0 : 0.0);
+        const double t = pm.h * fabs(dg) * cp_pow_pos(fabs(yy), pm.gss_a) * sg;       // :178
+        ps.w[a] = t;
+        tsum += t;
     }
     // g_inc = q t with q = r everywhere, 1 on the triples {3k,3k+1,3k+2}  (:71-76,179)
+#pragma unroll 1
+    for (int b0 = 0; b0 < NS; b0 += 3) {
+        const double trip = ps.w[b0] + ps.w[b0 + 1] + ps.w[b0 + 2];
+        const double ginc = pm.r * (tsum - trip) + trip;
 #pragma unroll
-    for (int a = 0; a < NS; ++a) {
-        const int b0 = (a / 3) * 3;
-        const double trip = t[b0] + t[b0 + 1] + t[b0 + 2];
-        g_new[a] = g[a] + (pm.r * (tsum - trip) + trip);
+        for (int u = 0; u < 3; ++u) g_new[b0 + u] = g[b0 + u] + ginc;
     }
 }
 
 // First Piola-Kirchhoff stress (lab): P = Fe S A_new^T / det A_new  (== det F sigma F^-T, :160-161).
 // Also returns the crystal-frame pieces the tangent needs.
-template <int NS>
 struct CpStressAux {
     double Anc[9];     // A_new crystal
     double idet;       // 1/det(A_new)
     double Pc[9];      // P crystal
-    double S[9];
 };
 
-template <int NS>
-CP_HD void cp_point_stress(const CpPointState<NS>& ps, const double* R, double* P_lab, CpStressAux<NS>& ax) {
-    double ImL[9];
+template <class Arr>
+CP_HD void cp_point_stress(const CpPointState<Arr>& ps, const double* R, double* P_lab, CpStressAux& ax) {
+    double ImL[9], S[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) ImL[i] = -ps.Lp[i];
     ImL[0] += 1.0; ImL[4] += 1.0; ImL[8] += 1.0;
     m3_mul(ps.Ac, ImL, ax.Anc);
     ax.idet = 1.0 / m3_det(ax.Anc);
-    sym6_to_m3(ps.s, ax.S);
+    sym6_to_m3(ps.s, S);
     double T[9], T2[9];
-    m3_mul(ps.Fe, ax.S, T);
+    m3_mul(ps.Fe, S, T);
     m3_mul_nt(T, ax.Anc, T2);
 #pragma unroll
     for (int i = 0; i < 9; ++i) ax.Pc[i] = T2[i] * ax.idet;
@@ -407,7 +514,7 @@ CP_HD void cp_point_stress(const CpPointState<NS>& ps, const double* R, double* 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Consistent tangent dP_ij/dH_kl in the lab frame, out[(3i+j)*ld + (3k+l)].
+// Consistent tangent dP_ij/dH_kl in the lab frame, out[(3i+j)*ld + (3k+l)*ls].
 //   ds/dF   = -J^-1 dr/dF   (f_jvp, models_copper.py:251-259),  dr/dF[dF] = -C : sym(Fe^T dF A_new)
 //   dP      = dF Z + [ dFe S A_new^T + Fe dS A_new^T + Fe S dA_new^T ] / det - P tr(A_new^-1 dA_new)
 //   with dLp = sum_a w_a (p_a . ds) d_a n_a^T,  dA_new = -Ac dLp,  dFe = -G dLp,
@@ -416,18 +523,19 @@ CP_HD void cp_point_stress(const CpPointState<NS>& ps, const double* R, double* 
 // dP_c column back with R, which is cheaper than rotating the rank-4 tensor.
 // `scale` multiplies the whole tangent (JxW for the element integration).
 // ---------------------------------------------------------------------------------------------------
-template <int NS, typename OutT>
-CP_HD void cp_point_tangent(const CpSlip& sl, const CpPointParams& pm, const CpPointState<NS>& ps,
-                            const CpStressAux<NS>& ax, const double* R, double scale, OutT out, int ld) {
+template <int NS, class Arr, typename OutT>
+CP_HD void cp_point_tangent(const CpSlip& sl, const CpPointParams& pm, const CpPointState<Arr>& ps,
+                            const CpStressAux& ax, const double* R, double scale, OutT out, long ld, long ls) {
     double N[36], piv[6];
     cp_newton_matrix<NS>(sl, pm, ps.G, ps.Fe, ps.w, N, piv);
     // constant pieces
-    double Z[9], T1[9] /* S A_new^T */, T2[9] /* Fe S */, Y[9] /* (I-Lp)^-1 */, tmp[9], dY;
-    m3_mul_nt(ax.S, ax.Anc, T1);
+    double S[9], Z[9], T1[9] /* S A_new^T */, T2[9] /* Fe S */, Y[9] /* (I-Lp)^-1 */, tmp[9], dY;
+    sym6_to_m3(ps.s, S);
+    m3_mul_nt(S, ax.Anc, T1);
     m3_mul(ax.Anc, T1, Z);
 #pragma unroll
     for (int i = 0; i < 9; ++i) Z[i] *= ax.idet;
-    m3_mul(ps.Fe, ax.S, T2);
+    m3_mul(ps.Fe, S, T2);
 #pragma unroll
     for (int i = 0; i < 9; ++i) tmp[i] = -ps.Lp[i];
     tmp[0] += 1.0; tmp[4] += 1.0; tmp[8] += 1.0;
@@ -451,21 +559,17 @@ CP_HD void cp_point_tangent(const CpSlip& sl, const CpPointParams& pm, const CpP
         double dS[9];
         dS[0] = z[0]; dS[4] = z[1]; dS[8] = z[2];
         dS[5] = dS[7] = 0.5 * z[3]; dS[2] = dS[6] = 0.5 * z[4]; dS[1] = dS[3] = 0.5 * z[5];
-        // dLp = sum_a w_a (d_a . dS n_a) d_a n_a^T
+        // dLp = sum_a w_a (etilde_a . z) d_a n_a^T      (p_a . ds == etilde_a . z)
         double dLp[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) dLp[i] = 0.0;
-#pragma unroll
+#pragma unroll 4
         for (int a = 0; a < NS; ++a) {
-            const double d0 = sl.d[3 * a], d1 = sl.d[3 * a + 1], d2 = sl.d[3 * a + 2];
-            const double n0 = sl.n[3 * a], n1 = sl.n[3 * a + 1], n2 = sl.n[3 * a + 2];
-            const double dtau = d0 * (dS[0] * n0 + dS[1] * n1 + dS[2] * n2) + d1 * (dS[3] * n0 + dS[4] * n1 + dS[5] * n2) +
-                                d2 * (dS[6] * n0 + dS[7] * n1 + dS[8] * n2);
+            const CpSlipSys& y = sl.sys[a];
+            const double dtau = y.Et[0] * z[0] + y.Et[1] * z[1] + y.Et[2] * z[2] + y.Et[3] * z[3] + y.Et[4] * z[4] + y.Et[5] * z[5];
             const double dgm = ps.w[a] * dtau;
-            const double e0 = dgm * d0, e1 = dgm * d1, e2 = dgm * d2;
-            dLp[0] += e0 * n0; dLp[1] += e0 * n1; dLp[2] += e0 * n2;
-            dLp[3] += e1 * n0; dLp[4] += e1 * n1; dLp[5] += e1 * n2;
-            dLp[6] += e2 * n0; dLp[7] += e2 * n1; dLp[8] += e2 * n2;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dLp[i] += dgm * y.M[i];
         }
         // dPc = r_k (r_l^T Z)  +  [ -(G dLp) T1 + Fe dS A_new^T - T2 (Ac dLp)^T ] idet + Pc tr(Y dLp)
         double GdL[9], AdL[9], M1[9], M2[9], M3[9], dPc[9];
@@ -486,6 +590,6 @@ CP_HD void cp_point_tangent(const CpSlip& sl, const CpPointParams& pm, const CpP
         double dP[9];
         cp_to_lab(R, dPc, dP);
 #pragma unroll
-        for (int ij = 0; ij < 9; ++ij) out[ij * ld + kl] = dP[ij] * scale;
+        for (int ij = 0; ij < 9; ++ij) out[ij * ld + kl * ls] = dP[ij] * scale;
     }
 }

@@ -2,9 +2,12 @@
 //
 // Kernels
 //   k_update_state      K1  one thread per quadrature point: u_grad gather, local Newton, new state
-//   k_assemble<..>      K2/K3 one warp per 4 hex8 cells: phase 1 = 32 points (stress [+ tangent]) into
-//                           shared memory, phase 2 = lane (cell, node a) integrates 3 rows of K_e and
-//                           scatters them into the CSR pattern / residual with fp64 atomics
+//   k_residual          K2  one warp per 4 hex8 cells: 32 points (stress) into shared memory, then lane (cell, node a)
+//                           integrates its residual rows and scatter-adds them
+//   k_point_tangent     K3a one thread per point: stress + consistent tangent (x JxW) into a component-major scratch
+//   k_element_tangent   K3b one warp per 4 cells: stages the 32 points of the scratch in shared memory, lane
+//                           (cell, node a) integrates 3 rows of K_e and scatters them into the CSR pattern /
+//                           residual with fp64 atomics (optional COO V)
 //   k_avg_stress        K5  per-cell JxW-weighted Cauchy stress
 //   k_point_eval            tensor_map / jacfwd(tensor_map) on explicit u_grads
 //   plan kernels        K0  node valence -> node->cell lists -> sorted neighbour lists -> CSR pattern + slot map
@@ -57,12 +60,15 @@ struct cpfem_plan {
     int64_t* indptr = nullptr;    // (3 nn + 1)
     int32_t* indices = nullptr;   // (nnz)
     uint8_t* rank = nullptr;      // (nc,8,8): rank of node b in the sorted neighbour list of node a
+    double* scratch = nullptr;    // (90, 8*chunk_cells): P JxW and dP/dH JxW of one chunk of cells, component-major
+    int64_t chunk_cells = 0;      // cells per assembly chunk
     CpSlip slip;
     int device = 0;
     int sm_count = 148;
 };
 
 #define MAX_VALENCE 16
+#define CPFEM_CHUNK_CELLS (1 << 19)   // 4 Mi points per assembly chunk: 3.0 GB of scratch
 
 __global__ void k_count_valence(const int32_t* __restrict__ cells, int64_t n, int64_t nn, int64_t* cnt, int* err) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,6 +165,7 @@ static cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc((void**)p, n *
 extern "C" int cpfem_plan_destroy(cpfem_plan* p) {
     if (!p) return 0;
     cudaFree(p->cells); cudaFree(p->points); cudaFree(p->indptr); cudaFree(p->indices); cudaFree(p->rank);
+    cudaFree(p->scratch);
     delete p;
     return 0;
 }
@@ -175,15 +182,8 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
     p->nc = nc; p->nc_active = nc; p->nn = nnodes; p->ns = ns;
     cudaGetDevice(&p->device);
     cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
-    // slip table: normalise (models_copper.py:62-66)
-    memset(&p->slip, 0, sizeof(CpSlip));
-    for (int a = 0; a < ns; ++a) {
-        const double* row = slip + 6 * a;
-        double nn_ = sqrt(row[0] * row[0] + row[1] * row[1] + row[2] * row[2]);
-        double dn_ = sqrt(row[3] * row[3] + row[4] * row[4] + row[5] * row[5]);
-        if (!(nn_ > 0) || !(dn_ > 0)) { delete p; return set_err(-1, "cpfem_plan_create: zero slip vector"); }
-        for (int i = 0; i < 3; ++i) { p->slip.n[3 * a + i] = row[i] / nn_; p->slip.d[3 * a + i] = row[3 + i] / dn_; }
-    }
+    // slip table: normalise (models_copper.py:62-66) and build the per-system constant records
+    if (!cp_slip_init(&p->slip, slip, ns)) { delete p; return set_err(-1, "cpfem_plan_create: zero slip vector"); }
     int64_t *cnt = nullptr, *n2c_ptr = nullptr, *nneigh = nullptr, *nbr_ptr = nullptr;
     int32_t *n2c = nullptr, *nbr = nullptr;
     unsigned long long* cursor = nullptr;
@@ -237,6 +237,8 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
         PLAN_TRY(dev_alloc(&p->indptr, 3 * nnodes + 1));
         PLAN_TRY(dev_alloc(&p->indices, p->nnz));
         PLAN_TRY(dev_alloc(&p->rank, nc * 64));
+        p->chunk_cells = nc < CPFEM_CHUNK_CELLS ? nc : CPFEM_CHUNK_CELLS;
+        PLAN_TRY(dev_alloc(&p->scratch, (size_t)90 * 8 * p->chunk_cells));
         k_fill_csr<<<blocks(nnodes + 1), T, 0, stream>>>(nbr_ptr, nbr, nnodes, p->indptr, p->indices);
         k_rank_map<<<blocks(nc * 8), T, 0, stream>>>(p->cells, nc, nbr_ptr, nbr, p->rank);
         // max valence (for info only)
@@ -284,7 +286,7 @@ extern "C" int cpfem_plan_set_active_cells(cpfem_plan* p, int64_t n_active) {
 }
 extern "C" int cpfem_plan_info(const cpfem_plan* p, int64_t* o) {
     if (!p || !o) return set_err(-1, "cpfem_plan_info: null argument");
-    o[0] = p->nc; o[1] = p->nn; o[2] = p->ns; o[3] = p->nnz; o[4] = p->max_valence;
+    o[0] = p->nc; o[1] = p->nn; o[2] = p->ns; o[3] = p->nnz; o[4] = p->max_valence; o[5] = p->chunk_cells;
     return 0;
 }
 
@@ -303,8 +305,28 @@ static StateView make_view(const cpfem_state* s) {
     return v;
 }
 
-__device__ __forceinline__ int64_t sidx(int soa, int64_t p, int i, int ncomp, int64_t np) {
-    return soa ? ((int64_t)i * np + p) : (p * ncomp + i);
+// one point's column of a (np, comps) [AoS] or (comps, np) [SoA] array
+struct GIn {
+    const double* p;
+    int64_t stride;
+    __device__ __forceinline__ double operator[](int a) const { return p[a * stride]; }
+};
+struct GOut {
+    double* p;
+    int64_t stride;
+    __device__ __forceinline__ double& operator[](int a) const { return p[a * stride]; }
+};
+__device__ __forceinline__ GIn gin(const double* base, int soa, int64_t p, int ncomp, int64_t np) {
+    GIn g;
+    g.p = soa ? base + p : base + p * ncomp;
+    g.stride = soa ? np : 1;
+    return g;
+}
+__device__ __forceinline__ GOut gout(double* base, int soa, int64_t p, int ncomp, int64_t np) {
+    GOut g;
+    g.p = soa ? base + p : base + p * ncomp;
+    g.stride = soa ? np : 1;
+    return g;
 }
 
 __device__ __forceinline__ void load_point_params(const CpMaterial& m, const StateView& st, int64_t p, CpPointParams& pm) {
@@ -355,38 +377,43 @@ __device__ __forceinline__ void hex8_grads(const double (*X)[3], int q, double (
         for (int i = 0; i < 3; ++i) gN[a][i] = dN[a][0] * Ji[i] + dN[a][1] * Ji[3 + i] + dN[a][2] * Ji[6 + i];
 }
 
-// u_grad at point q of cell c: H_ij = sum_a u_a,i dN_a/dX_j   (models_copper.py:277-278)
+// shape gradients at point q of cell c; if sol != nullptr also u_grad H_ij = sum_a u_a,i dN_a/dX_j (models_copper.py:277-278)
 __device__ __forceinline__ void point_kinematics(const int32_t* __restrict__ cells, const double* __restrict__ points,
                                                  const double* __restrict__ sol, int64_t c, int q, double* H,
-                                                 double (*gN)[3], double& JxW, int32_t* nodes_out) {
-    double X[8][3], U[8][3];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int32_t n = cells[c * 8 + a];
-        if (nodes_out) nodes_out[a] = n;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { X[a][i] = points[(int64_t)n * 3 + i]; U[a][i] = sol[(int64_t)n * 3 + i]; }
+                                                 double (*gN)[3], double& JxW) {
+    int32_t nd[8];
+    {
+        const int4* cp = reinterpret_cast<const int4*>(cells + c * 8);
+        const int4 lo = cp[0], hi = cp[1];
+        nd[0] = lo.x; nd[1] = lo.y; nd[2] = lo.z; nd[3] = lo.w; nd[4] = hi.x; nd[5] = hi.y; nd[6] = hi.z; nd[7] = hi.w;
     }
-    hex8_grads(X, q, gN, JxW);
+    {
+        double X[8][3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            double s = 0.0;
+            for (int i = 0; i < 3; ++i) X[a][i] = points[(int64_t)nd[a] * 3 + i];
+        hex8_grads(X, q, gN, JxW);
+    }
+    if (sol) {
 #pragma unroll
-            for (int a = 0; a < 8; ++a) s += U[a][i] * gN[a][j];
-            H[3 * i + j] = s;
+        for (int i = 0; i < 9; ++i) H[i] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double u = sol[(int64_t)nd[a] * 3 + i];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) H[3 * i + j] += u * gN[a][j];
+            }
         }
+    }
 }
 
-template <int NS>
-__device__ __forceinline__ void load_point_state(const StateView& st, int64_t p, int64_t np, double* A, double* g, double* R) {
+__device__ __forceinline__ void load9(const double* base, int soa, int64_t p, int64_t np, double* out) {
+    const GIn a = gin(base, soa, p, 9, np);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) A[i] = st.Fp_inv[sidx(st.soa, p, i, 9, np)];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = st.rot[sidx(st.soa, p, i, 9, np)];
-#pragma unroll
-    for (int a = 0; a < NS; ++a) g[a] = st.g[sidx(st.soa, p, a, NS, np)];
+    for (int i = 0; i < 9; ++i) out[i] = a[i];
 }
 
 __device__ __forceinline__ void warp_status(const CpSolveInfo& info, bool valid, long long* status) {
@@ -411,112 +438,218 @@ __device__ __forceinline__ void warp_status(const CpSolveInfo& info, bool valid,
     }
 }
 
+// Per-point kernels: one thread per quadrature point, PT_BLOCK threads per block; the two per-slip-system arrays
+// (1/g, w) of every thread are columns of a [2][NS][PT_BLOCK] shared-memory tile.
+#define PT_BLOCK 128
+typedef CpArr<PT_BLOCK> SArr;
+template <int NS>
+__device__ __forceinline__ void point_arrays(double* smem, CpPointState<SArr>& ps) {
+    ps.ginv.p = smem + threadIdx.x;
+    ps.w.p = smem + NS * PT_BLOCK + threadIdx.x;
+}
+template <int NS>
+static constexpr size_t point_smem() { return sizeof(double) * 2 * NS * PT_BLOCK; }
+
+// u_grad + state -> local Newton solve.  R is reloaded by the callers after the solve (keeps it out of the loop's registers).
+template <int NS, int POWN>
+__device__ __forceinline__ void solve_point(const StateView& st, const CpMaterial& mat, const CpSlip& slip, double dt,
+                                            int64_t p, int64_t np, const double* H, CpPointParams& pm, CpPointState<SArr>& ps) {
+    double A[9], R[9];
+    load9(st.Fp_inv, st.soa, p, np, A);
+    load9(st.rot, st.soa, p, np, R);
+    load_point_params(mat, st, p, pm);
+    cp_point_solve<NS, POWN>(slip, mat, pm, dt, H, A, gin(st.g, st.soa, p, NS, np), R, ps);
+}
+
 // -----------------------------------------------------------------------------------------------
 // K1: state update
 // -----------------------------------------------------------------------------------------------
-template <int NS>
-__global__ void __launch_bounds__(128)
+template <int NS, int POWN>
+__global__ void __launch_bounds__(PT_BLOCK, 3)
 k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
                StateView st, cpfem_state_out out, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt,
                int64_t np, long long* status) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ double smem[];
+    int64_t p = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;
     const bool valid = p < np;
     if (!valid) p = np - 1;
-    const int64_t c = p >> 3;
-    const int q = (int)(p & 7);
-    double H[9], A[9], R[9], g[NS];
-    {
-        double gN[8][3], JxW;
-        point_kinematics(cells, points, sol, c, q, H, gN, JxW, nullptr);
-    }
-    load_point_state<NS>(st, p, np, A, g, R);
+    CpPointState<SArr> ps;
+    point_arrays<NS>(smem, ps);
     CpPointParams pm;
-    load_point_params(mat, st, p, pm);
-    CpPointState<NS> ps;
-    cp_point_solve<NS>(slip, mat, pm, dt, H, A, g, R, ps);
-    double sl_old[NS], An[9], gn[NS], sn[NS];
-#pragma unroll
-    for (int a = 0; a < NS; ++a) sl_old[a] = st.slip[sidx(st.soa, p, a, NS, np)];
-    cp_point_state_update<NS>(slip, pm, ps, g, sl_old, R, An, gn, sn);
+    {
+        double H[9], gN[8][3], JxW;
+        point_kinematics(cells, points, sol, p >> 3, (int)(p & 7), H, gN, JxW);
+        solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
+    }
     if (valid) {
         const int so = (out.layout == CPFEM_LAYOUT_SOA);
+        double R[9], An[9];
+        load9(st.rot, st.soa, p, np, R);
+        cp_point_state_update<NS>(slip, pm, ps, gin(st.g, st.soa, p, NS, np), gin(st.slip, st.soa, p, NS, np), R, An,
+                                  gout(out.g, so, p, NS, np), gout(out.slip, so, p, NS, np));
+        const GOut Ao = gout(out.Fp_inv, so, p, 9, np);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) out.Fp_inv[sidx(so, p, i, 9, np)] = An[i];
-#pragma unroll
-        for (int a = 0; a < NS; ++a) out.g[sidx(so, p, a, NS, np)] = gn[a];
-#pragma unroll
-        for (int a = 0; a < NS; ++a) out.slip[sidx(so, p, a, NS, np)] = sn[a];
+        for (int i = 0; i < 9; ++i) Ao[i] = An[i];
     }
     warp_status(ps.info, valid, status);
 }
 
 // -----------------------------------------------------------------------------------------------
-// K2/K3: residual (+ tangent) assembly.  One warp = 4 cells.
-// shared memory per warp (doubles):  TA 4 x TA_CELL (tangent*JxW, point stride TA_PT), GN 4 x GN_CELL
-// (shape gradients [q][a][3]), PJ 4 x PJ_CELL (P*JxW [q][9]).  Strides are padded so that the four cells
-// of a warp fall into different banks when their 8 lanes broadcast-read the same address.
+// K2: residual only (compute_residual).  One warp = 4 cells; lane = quadrature point q of cell cl for the
+// constitutive solve, then lane = node a of cell cl for the element integration r[a,i] = sum_q P_ij dN_a/dX_j JxW
+// and the scatter-add into res (nnodes,3).
 // -----------------------------------------------------------------------------------------------
-#define TA_PT 82
-#define TA_CELL (8 * TA_PT + 2)     // 658
-#define GN_CELL (8 * 24 + 2)        // 194
+#define GN_CELL (8 * 24 + 2)        // 194: padded so that the four cells of a warp fall into different banks
 #define PJ_CELL (8 * 9 + 2)         // 74
 
-static size_t assemble_smem_per_warp(bool tangent) {
-    return sizeof(double) * (size_t)((tangent ? 4 * TA_CELL : 0) + 4 * GN_CELL + 4 * PJ_CELL);
-}
+template <int NS>
+static constexpr size_t residual_smem() { return point_smem<NS>() + sizeof(double) * (PT_BLOCK / 32) * 4 * (GN_CELL + PJ_CELL); }
 
-template <int NS, bool TANGENT>
-__global__ void __launch_bounds__(224, 1)
-k_assemble(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
+template <int NS, int POWN>
+__global__ void __launch_bounds__(PT_BLOCK, 3)
+k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
            StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t nc,
-           const int64_t* __restrict__ indptr, const uint8_t* __restrict__ rank, double* __restrict__ res,
-           double* __restrict__ csr_data, double* __restrict__ coo_V, long long* status, int warps_per_block) {
+           double* __restrict__ res, long long* status) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = (TANGENT ? 4 * TA_CELL : 0) + 4 * GN_CELL + 4 * PJ_CELL;
-    double* TA = smem + (size_t)warp * per_warp;
-    double* GN = TA + (TANGENT ? 4 * TA_CELL : 0);
+    double* GN = smem + 2 * NS * PT_BLOCK + (size_t)warp * 4 * (GN_CELL + PJ_CELL);
     double* PJ = GN + 4 * GN_CELL;
     const int cl = lane >> 3, q = lane & 7;
-    const int64_t nquads = (nc + 3) >> 2;
     const int64_t np = nc * 8;
-    for (int64_t quad = (int64_t)blockIdx.x * warps_per_block + warp; quad < nquads;
-         quad += (int64_t)gridDim.x * warps_per_block) {
-        int64_t c = quad * 4 + cl;
-        const bool valid = c < nc;
-        if (!valid) c = nc - 1;
-        const int64_t p = c * 8 + q;
-        int32_t nodes[8];
-        CpSolveInfo info;
-        // ---------------- phase 1: lane = quadrature point q of cell cl ----------------
+    int64_t p = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;
+    const bool valid = p < np;
+    if (!valid) p = np - 1;
+    const int64_t c = p >> 3;
+    CpPointState<SArr> ps;
+    point_arrays<NS>(smem, ps);
+    {
+        CpPointParams pm;
+        double JxW;
         {
-            double H[9], A[9], R[9], g[NS], gN[8][3], JxW;
-            point_kinematics(cells, points, sol, c, q, H, gN, JxW, nodes);
+            double H[9], gN[8][3];
+            point_kinematics(cells, points, sol, c, q, H, gN, JxW);
             double* gq = GN + cl * GN_CELL + q * 24;
 #pragma unroll
             for (int a = 0; a < 8; ++a)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) gq[a * 3 + i] = gN[a][i];
-            load_point_state<NS>(st, p, np, A, g, R);
-            CpPointParams pm;
-            load_point_params(mat, st, p, pm);
-            CpPointState<NS> ps;
-            cp_point_solve<NS>(slip, mat, pm, dt, H, A, g, R, ps);
-            info = ps.info;
-            double P[9];
-            CpStressAux<NS> ax;
-            cp_point_stress<NS>(ps, R, P, ax);
-            double* pj = PJ + cl * PJ_CELL + q * 9;
+            solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
+        }
+        double R[9], P[9];
+        load9(st.rot, st.soa, p, np, R);
+        CpStressAux ax;
+        cp_point_stress(ps, R, P, ax);
+        double* pj = PJ + cl * PJ_CELL + q * 9;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) pj[i] = P[i] * JxW;
-            if (TANGENT) cp_point_tangent<NS>(slip, pm, ps, ax, R, JxW, TA + cl * TA_CELL + q * TA_PT, 9);
+        for (int i = 0; i < 9; ++i) pj[i] = P[i] * JxW;
+    }
+    __syncwarp();
+    {
+        const int a = q;
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {
+            const double* pj = PJ + cl * PJ_CELL + qq * 9;
+            const double* ga = GN + cl * GN_CELL + qq * 24 + a * 3;
+            const double g0 = ga[0], g1 = ga[1], g2 = ga[2];
+            r0 += pj[0] * g0 + pj[1] * g1 + pj[2] * g2;
+            r1 += pj[3] * g0 + pj[4] * g1 + pj[5] * g2;
+            r2 += pj[6] * g0 + pj[7] * g1 + pj[8] * g2;
+        }
+        if (valid) {
+            const int64_t na = cells[c * 8 + a];
+            atomicAdd(&res[na * 3 + 0], r0);
+            atomicAdd(&res[na * 3 + 1], r1);
+            atomicAdd(&res[na * 3 + 2], r2);
+        }
+    }
+    warp_status(ps.info, valid, status);
+}
+
+// -----------------------------------------------------------------------------------------------
+// K3a: stress + consistent tangent at every point of a chunk of cells -> scratch (component-major, coalesced):
+//   PJ[9][npc]  = P_ij JxW          TA[81][npc] = dP_ij/dH_kl JxW        (npc = points in the chunk)
+// -----------------------------------------------------------------------------------------------
+template <int NS, int POWN>
+__global__ void __launch_bounds__(PT_BLOCK, 3)
+k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
+                StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np, int64_t p0,
+                int64_t npc, double* __restrict__ PJ, double* __restrict__ TA, long long* status) {
+    extern __shared__ double smem[];
+    const int64_t pl = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;      // point within the chunk
+    const bool valid = pl < npc;
+    const int64_t p = p0 + (valid ? pl : npc - 1);
+    CpPointState<SArr> ps;
+    point_arrays<NS>(smem, ps);
+    CpPointParams pm;
+    double JxW;
+    {
+        double H[9], gN[8][3];
+        point_kinematics(cells, points, sol, p >> 3, (int)(p & 7), H, gN, JxW);
+        solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
+    }
+    double R[9], P[9];
+    load9(st.rot, st.soa, p, np, R);
+    CpStressAux ax;
+    cp_point_stress(ps, R, P, ax);
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) PJ[i * npc + pl] = P[i] * JxW;
+        cp_point_tangent<NS>(slip, pm, ps, ax, R, JxW, TA + pl, 9 * npc, npc);
+    }
+    warp_status(ps.info, valid, status);
+}
+
+// -----------------------------------------------------------------------------------------------
+// K3b: element integration + scatter for a chunk.  One warp = 4 cells, lane = (cell cl, node a):
+//   stage the warp's 32 points of PJ / TA (coalesced rows of the scratch) and the shape gradients in shared memory,
+//   r[a,i]        = sum_q PJ_q[i,:] . dN_a[q,:]                          -> atomicAdd into res
+//   K_e[3a+i, :]  = sum_q sum_jl dN_a,j TA_q[ij,kl] dN_b,l  (24 columns) -> atomicAdd into the CSR slots of row 3 n_a + i
+//                                                                          (slot = indptr[row] + 3 rank(a,b) + k), optional COO V
+// -----------------------------------------------------------------------------------------------
+#define TA_PT 82
+#define TA_CELL (8 * TA_PT + 2)     // 658
+#define ELEM_WARP_DOUBLES (4 * TA_CELL + 4 * GN_CELL + 4 * PJ_CELL)
+
+__global__ void __launch_bounds__(224, 1)
+k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, int64_t c0, int64_t ncc,
+                  const double* __restrict__ PJg, const double* __restrict__ TAg, const int64_t* __restrict__ indptr,
+                  const uint8_t* __restrict__ rank, double* __restrict__ res, double* __restrict__ csr_data,
+                  double* __restrict__ coo_V, int warps_per_block) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* TA = smem + (size_t)warp * ELEM_WARP_DOUBLES;
+    double* GN = TA + 4 * TA_CELL;
+    double* PJ = GN + 4 * GN_CELL;
+    const int cl = lane >> 3, a = lane & 7;
+    const int64_t nquads = (ncc + 3) >> 2;
+    const int64_t npc = ncc * 8;
+    for (int64_t quad = (int64_t)blockIdx.x * warps_per_block + warp; quad < nquads;
+         quad += (int64_t)gridDim.x * warps_per_block) {
+        int64_t cc = quad * 4 + cl;                // cell within the chunk
+        const bool valid = cc < ncc;
+        if (!valid) cc = ncc - 1;
+        const int64_t c = c0 + cc;
+        // ---- stage: own point's shape gradients, the warp's 32 points of PJ and TA ----
+        {
+            double gN[8][3], JxW;
+            point_kinematics(cells, points, nullptr, c, a, nullptr, gN, JxW);
+            double* gq = GN + cl * GN_CELL + a * 24;
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) gq[b * 3 + i] = gN[b][i];
+            const int64_t pl = cc * 8 + a;          // clamped cells re-read the last cell: harmless
+            double* pj = PJ + cl * PJ_CELL + a * 9;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) pj[i] = PJg[i * npc + pl];
+            double* ta = TA + cl * TA_CELL + a * TA_PT;
+#pragma unroll 9
+            for (int i = 0; i < 81; ++i) ta[i] = TAg[i * npc + pl];
         }
         __syncwarp();
-        // ---------------- phase 2: lane = node a (= q) of cell cl ----------------
-        const int a = q;
-        const int32_t na = nodes[a];
-        {
-            // residual rows: r[a,i] = sum_q sum_j P_ij gN_a,j JxW
+        const int64_t na = cells[c * 8 + a];
+        if (res) {
             double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) {
@@ -527,63 +660,53 @@ k_assemble(const int32_t* __restrict__ cells, const double* __restrict__ points,
                 r1 += pj[3] * g0 + pj[4] * g1 + pj[5] * g2;
                 r2 += pj[6] * g0 + pj[7] * g1 + pj[8] * g2;
             }
-            if (valid && res) {
-                atomicAdd(&res[(int64_t)na * 3 + 0], r0);
-                atomicAdd(&res[(int64_t)na * 3 + 1], r1);
-                atomicAdd(&res[(int64_t)na * 3 + 2], r2);
+            if (valid) {
+                atomicAdd(&res[na * 3 + 0], r0);
+                atomicAdd(&res[na * 3 + 1], r1);
+                atomicAdd(&res[na * 3 + 2], r2);
             }
         }
-        if (TANGENT) {
-            double acc[3][24];
+        int rb[8];
+        if (csr_data) {
+            const uint2 rk = *reinterpret_cast<const uint2*>(rank + (c * 8 + a) * 8);
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 24; ++j) acc[i][j] = 0.0;
+            for (int b = 0; b < 4; ++b) { rb[b] = 3 * (int)((rk.x >> (8 * b)) & 0xffu); rb[4 + b] = 3 * (int)((rk.y >> (8 * b)) & 0xffu); }
+        }
 #pragma unroll 1
+        for (int i = 0; i < 3; ++i) {
+            double acc[24];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) acc[j] = 0.0;
+#pragma unroll 2
             for (int qq = 0; qq < 8; ++qq) {
-                const double* ta = TA + cl * TA_CELL + qq * TA_PT;
+                const double* ta = TA + cl * TA_CELL + qq * TA_PT + (3 * i) * 9;
                 const double* gq = GN + cl * GN_CELL + qq * 24;
                 const double ga0 = gq[a * 3], ga1 = gq[a * 3 + 1], ga2 = gq[a * 3 + 2];
+                double T[9];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    double T[9];
+                for (int kl = 0; kl < 9; ++kl) T[kl] = ga0 * ta[kl] + ga1 * ta[9 + kl] + ga2 * ta[18 + kl];
 #pragma unroll
-                    for (int kl = 0; kl < 9; ++kl)
-                        T[kl] = ga0 * ta[(3 * i) * 9 + kl] + ga1 * ta[(3 * i + 1) * 9 + kl] + ga2 * ta[(3 * i + 2) * 9 + kl];
+                for (int b = 0; b < 8; ++b) {
+                    const double gb0 = gq[b * 3], gb1 = gq[b * 3 + 1], gb2 = gq[b * 3 + 2];
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) {
-                        const double gb0 = gq[b * 3], gb1 = gq[b * 3 + 1], gb2 = gq[b * 3 + 2];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                            acc[i][3 * b + k] += T[3 * k] * gb0 + T[3 * k + 1] * gb1 + T[3 * k + 2] * gb2;
-                    }
+                    for (int k = 0; k < 3; ++k) acc[3 * b + k] += T[3 * k] * gb0 + T[3 * k + 1] * gb1 + T[3 * k + 2] * gb2;
                 }
             }
             if (valid) {
                 if (coo_V) {
-                    double* v = coo_V + c * 576 + (int64_t)(3 * a) * 24;
+                    double* v = coo_V + c * 576 + (int64_t)(3 * a + i) * 24;
 #pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int j = 0; j < 24; ++j) v[i * 24 + j] = acc[i][j];
+                    for (int j = 0; j < 24; ++j) v[j] = acc[j];
                 }
                 if (csr_data) {
-                    const uint8_t* rk = rank + (c * 8 + a) * 8;
-                    int rb[8];
+                    double* row = csr_data + indptr[na * 3 + i];
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) rb[b] = 3 * (int)rk[b];
+                    for (int b = 0; b < 8; ++b)
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        double* row = csr_data + indptr[(int64_t)na * 3 + i];
-#pragma unroll
-                        for (int b = 0; b < 8; ++b)
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) atomicAdd(&row[rb[b] + k], acc[i][3 * b + k]);
-                    }
+                        for (int k = 0; k < 3; ++k) atomicAdd(&row[rb[b] + k], acc[3 * b + k]);
                 }
             }
         }
-        warp_status(info, valid, status);
         __syncwarp();
     }
 }
@@ -591,33 +714,31 @@ k_assemble(const int32_t* __restrict__ cells, const double* __restrict__ points,
 // -----------------------------------------------------------------------------------------------
 // K5: average Cauchy stress per cell (models_copper.py:297-319)
 // -----------------------------------------------------------------------------------------------
-template <int NS>
-__global__ void __launch_bounds__(128)
+template <int NS, int POWN>
+__global__ void __launch_bounds__(PT_BLOCK, 3)
 k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
              StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np,
              double* __restrict__ sigma_cell, long long* status) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ double smem[];
+    int64_t p = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;
     const bool valid = p < np;
     if (!valid) p = np - 1;
     const int64_t c = p >> 3;
     const int q = (int)(p & 7);
-    double H[9], A[9], R[9], g[NS], JxW;
+    CpPointState<SArr> ps;
+    point_arrays<NS>(smem, ps);
+    CpPointParams pm;
+    double F[9], JxW;
     {
         double gN[8][3];
-        point_kinematics(cells, points, sol, c, q, H, gN, JxW, nullptr);
+        point_kinematics(cells, points, sol, c, q, F, gN, JxW);
+        solve_point<NS, POWN>(st, mat, slip, dt, p, np, F, pm, ps);
     }
-    load_point_state<NS>(st, p, np, A, g, R);
-    CpPointParams pm;
-    load_point_params(mat, st, p, pm);
-    CpPointState<NS> ps;
-    cp_point_solve<NS>(slip, mat, pm, dt, H, A, g, R, ps);
-    double P[9];
-    CpStressAux<NS> ax;
-    cp_point_stress<NS>(ps, R, P, ax);
+    double R[9], P[9], sg[9];
+    load9(st.rot, st.soa, p, np, R);
+    CpStressAux ax;
+    cp_point_stress(ps, R, P, ax);
     // sigma = P F^T / det F (:308-309)
-    double F[9], sg[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) F[i] = H[i];
     F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
     m3_mul_nt(P, F, sg);
     const double s = JxW / m3_det(F);
@@ -641,28 +762,31 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
 // -----------------------------------------------------------------------------------------------
 // tensor_map on explicit u_grads (and its jacfwd)
 // -----------------------------------------------------------------------------------------------
-template <int NS>
-__global__ void __launch_bounds__(128)
+template <int NS, int POWN>
+__global__ void __launch_bounds__(PT_BLOCK, 3)
 k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip,
              double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, long long* status) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ double smem[];
+    int64_t p = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;
     const bool valid = p < np;
     if (!valid) p = np - 1;
-    double H[9], A[9], R[9], g[NS];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) H[i] = u_grads[p * 9 + i];
-    load_point_state<NS>(st, p, np, A, g, R);
+    CpPointState<SArr> ps;
+    point_arrays<NS>(smem, ps);
     CpPointParams pm;
-    load_point_params(mat, st, p, pm);
-    CpPointState<NS> ps;
-    cp_point_solve<NS>(slip, mat, pm, dt, H, A, g, R, ps);
-    double P[9];
-    CpStressAux<NS> ax;
-    cp_point_stress<NS>(ps, R, P, ax);
+    {
+        double H[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] = u_grads[p * 9 + i];
+        solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
+    }
+    double R[9], P[9];
+    load9(st.rot, st.soa, p, np, R);
+    CpStressAux ax;
+    cp_point_stress(ps, R, P, ax);
     if (valid) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) Pout[p * 9 + i] = P[i];
-        if (Aout) cp_point_tangent<NS>(slip, pm, ps, ax, R, 1.0, Aout + p * 81, 9);
+        if (Aout) cp_point_tangent<NS>(slip, pm, ps, ax, R, 1.0, Aout + p * 81, 9, 1);
     }
     warp_status(ps.info, valid, status);
 }
@@ -747,6 +871,32 @@ static CpMaterial to_mat(const cpfem_material* m) {
     if (r.max_iter <= 0) r.max_iter = 200;
     return r;
 }
+// compile-time rate exponent n - 1 when the material is uniform and n - 1 is one of the instantiated integers, else 0
+static int rate_pown(const CpMaterial& m, const StateView& v) {
+    if (v.xm) return 0;
+    const double n1 = 1.0 / m.xm - 1.0;
+    if (n1 == 119.0) return 119;
+    if (n1 == 19.0) return 19;
+    if (n1 == 9.0) return 9;
+    return 0;
+}
+// instantiated (NS, POWN) pairs: FCC/BCC12 x {run-time, 9 (copper), 119 (304 steel)}, BCC24 x {run-time, 19 (DP steel)}
+#define CP_DISPATCH(ns, pown, CALL)                                             \
+    do {                                                                        \
+        if ((ns) == 12) {                                                       \
+            if ((pown) == 119) { CALL(12, 119); }                               \
+            else if ((pown) == 9) { CALL(12, 9); }                              \
+            else { CALL(12, 0); }                                               \
+        } else {                                                                \
+            if ((pown) == 19) { CALL(24, 19); }                                 \
+            else { CALL(24, 0); }                                               \
+        }                                                                       \
+    } while (0)
+
+template <typename K>
+static cudaError_t allow_smem(K kern, size_t bytes) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 
 extern "C" int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
                                   const cpfem_state* in, const cpfem_state_out* out, double dt, int64_t* status,
@@ -757,34 +907,15 @@ extern "C" int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* 
         return set_err(-1, "cpfem_update_state: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t np = plan->nc_active * 8;
-    const unsigned grid = (unsigned)((np + 127) / 128);
+    const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
     StateView v = make_view(in);
     CpMaterial m = to_mat(mat);
-    if (plan->ns == 12)
-        k_update_state<12><<<grid, 128, 0, stream>>>(plan->cells, plan->points, sol, v, *out, m, plan->slip, dt, np, (long long*)status);
-    else
-        k_update_state<24><<<grid, 128, 0, stream>>>(plan->cells, plan->points, sol, v, *out, m, plan->slip, dt, np, (long long*)status);
-    CU_TRY(cudaGetLastError());
-    return 0;
-}
-
-template <int NS, bool TANGENT>
-static int launch_assemble(const cpfem_plan* plan, const CpMaterial& m, const double* sol, const StateView& v, double dt,
-                           double* res, double* csr_data, double* coo_V, int64_t* status, cudaStream_t stream) {
-    const size_t per_warp = assemble_smem_per_warp(TANGENT);
-    int wpb = TANGENT ? 7 : 7;
-    const size_t smem = per_warp * wpb;
-    auto kern = k_assemble<NS, TANGENT>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int bps = 1;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem));
-    if (bps < 1) return set_err(-2, "cpfem assemble kernel does not fit on an SM");
-    const int64_t nquads = (plan->nc_active + 3) / 4;
-    int64_t grid = (int64_t)plan->sm_count * bps;
-    const int64_t need = (nquads + wpb - 1) / wpb;
-    if (grid > need) grid = need;
-    kern<<<(unsigned)grid, wpb * 32, smem, stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, plan->nc_active,
-                                                     plan->indptr, plan->rank, res, csr_data, coo_V, (long long*)status, wpb);
+#define CALL(NS, PW)                                                                                                   \
+    CU_TRY(allow_smem(k_update_state<NS, PW>, point_smem<NS>()));                                                      \
+    k_update_state<NS, PW><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, *out, m,   \
+                                                                         plan->slip, dt, np, (long long*)status)
+    CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
+#undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -798,8 +929,16 @@ extern "C" int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat,
     CU_TRY(cudaMemsetAsync(res, 0, plan->nn * 3 * sizeof(double), stream));
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
-    if (plan->ns == 12) return launch_assemble<12, false>(plan, m, sol, v, dt, res, nullptr, nullptr, status, stream);
-    return launch_assemble<24, false>(plan, m, sol, v, dt, res, nullptr, nullptr, status, stream);
+    const int64_t np = plan->nc_active * 8;
+    const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
+#define CALL(NS, PW)                                                                                                   \
+    CU_TRY(allow_smem(k_residual<NS, PW>, residual_smem<NS>()));                                                       \
+    k_residual<NS, PW><<<grid, PT_BLOCK, residual_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, \
+                                                                        dt, plan->nc_active, res, (long long*)status)
+    CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
+#undef CALL
+    CU_TRY(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
@@ -813,8 +952,32 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
     if (csr_data) CU_TRY(cudaMemsetAsync(csr_data, 0, plan->nnz * sizeof(double), stream));
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
-    if (plan->ns == 12) return launch_assemble<12, true>(plan, m, sol, v, dt, res, csr_data, coo_V, status, stream);
-    return launch_assemble<24, true>(plan, m, sol, v, dt, res, csr_data, coo_V, status, stream);
+    const int pown = rate_pown(m, v);
+    const int64_t np = plan->nc_active * 8;
+    const int wpb = 7;
+    const size_t esmem = sizeof(double) * ELEM_WARP_DOUBLES * wpb;
+    CU_TRY(allow_smem(k_element_tangent, esmem));
+    for (int64_t c0 = 0; c0 < plan->nc_active; c0 += plan->chunk_cells) {
+        const int64_t ncc = (plan->nc_active - c0 < plan->chunk_cells) ? plan->nc_active - c0 : plan->chunk_cells;
+        const int64_t npc = ncc * 8;
+        double* PJ = plan->scratch;
+        double* TA = plan->scratch + 9 * npc;
+        const unsigned grid = (unsigned)((npc + PT_BLOCK - 1) / PT_BLOCK);
+#define CALL(NS, PW)                                                                                                   \
+    CU_TRY(allow_smem(k_point_tangent<NS, PW>, point_smem<NS>()));                                                     \
+    k_point_tangent<NS, PW><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, \
+                                                                          dt, np, c0 * 8, npc, PJ, TA, (long long*)status)
+        CP_DISPATCH(plan->ns, pown, CALL);
+#undef CALL
+        CU_TRY(cudaGetLastError());
+        const int64_t nquads = (ncc + 3) / 4;
+        int64_t egrid = (nquads + wpb - 1) / wpb;
+        if (egrid > plan->sm_count) egrid = plan->sm_count;
+        k_element_tangent<<<(unsigned)egrid, wpb * 32, esmem, stream>>>(plan->cells, plan->points, c0, ncc, PJ, TA, plan->indptr,
+                                                                        plan->rank, res, csr_data, coo_V, wpb);
+        CU_TRY(cudaGetLastError());
+    }
+    return 0;
 }
 
 extern "C" int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
@@ -824,13 +987,15 @@ extern "C" int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* ma
     if (!sol || !sigma_cell) return set_err(-1, "cpfem_avg_stress: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t np = plan->nc_active * 8;
-    const unsigned grid = (unsigned)((np + 127) / 128);
+    const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
-    if (plan->ns == 12)
-        k_avg_stress<12><<<grid, 128, 0, stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, np, sigma_cell, (long long*)status);
-    else
-        k_avg_stress<24><<<grid, 128, 0, stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, np, sigma_cell, (long long*)status);
+#define CALL(NS, PW)                                                                                                   \
+    CU_TRY(allow_smem(k_avg_stress<NS, PW>, point_smem<NS>()));                                                        \
+    k_avg_stress<NS, PW><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, \
+                                                                       np, sigma_cell, (long long*)status)
+    CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
+#undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -843,13 +1008,15 @@ extern "C" int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_ma
     if (!u_grads || !P || np <= 0) return set_err(-1, "cpfem_point_stress_tangent: bad argument");
     if (st->layout != CPFEM_LAYOUT_AOS) return set_err(-1, "cpfem_point_stress_tangent: AoS state only");
     cudaStream_t stream = (cudaStream_t)stream_;
-    const unsigned grid = (unsigned)((np + 127) / 128);
+    const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
-    if (plan->ns == 12)
-        k_point_eval<12><<<grid, 128, 0, stream>>>(u_grads, v, m, plan->slip, dt, np, P, tangent, (long long*)status);
-    else
-        k_point_eval<24><<<grid, 128, 0, stream>>>(u_grads, v, m, plan->slip, dt, np, P, tangent, (long long*)status);
+#define CALL(NS, PW)                                                                                                   \
+    CU_TRY(allow_smem(k_point_eval<NS, PW>, point_smem<NS>()));                                                        \
+    k_point_eval<NS, PW><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(u_grads, v, m, plan->slip, dt, np, P, tangent,   \
+                                                                       (long long*)status)
+    CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
+#undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
 }

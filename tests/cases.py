@@ -13,6 +13,10 @@ MATERIALS = {
 }
 
 
+# compile-time rate exponent n - 1 the kernels instantiate for each set (0 = run-time path only)
+RATE_POWN = {'304steel': 119, 'copper': 9, 'tantalum': 0, 'dp_ferrite': 19}
+
+
 def rand_quat(rng, n):
     q = rng.normal(size=(n, 4))
     return q / np.linalg.norm(q, axis=1)[:, None]

@@ -5,18 +5,16 @@
 #include <string.h>
 #include "../../jax-cpfem_b200/csrc/cp_point.cuh"
 
-template <int NS>
+typedef CpArr<1> HArr;
+
+// POWN: 0 = run-time rate exponent (what the kernels use for per-point / non-integer exponents),
+//       9 / 19 / 119 = the compile-time integer chains the kernels instantiate for copper / DP steel / 304 steel.
+template <int NS, int POWN>
 static void run(const double* slip6, const CpMaterial* mat, double dt, int64_t np, const double* H, const double* A,
                 const double* g, const double* slip_old, const double* R, const double* pp /* np x 8 or null */,
                 double* P, double* tangent, double* A_new, double* g_new, double* slip_new, int32_t* iters) {
     CpSlip sl;
-    memset(&sl, 0, sizeof(sl));
-    for (int a = 0; a < NS; ++a) {
-        const double* row = slip6 + 6 * a;
-        double nn = sqrt(row[0] * row[0] + row[1] * row[1] + row[2] * row[2]);
-        double dn = sqrt(row[3] * row[3] + row[4] * row[4] + row[5] * row[5]);
-        for (int i = 0; i < 3; ++i) { sl.n[3 * a + i] = row[i] / nn; sl.d[3 * a + i] = row[3 + i] / dn; }
-    }
+    cp_slip_init(&sl, slip6, NS);
     for (int64_t p = 0; p < np; ++p) {
         CpPointParams pm;
         if (pp) {
@@ -27,21 +25,29 @@ static void run(const double* slip6, const CpMaterial* mat, double dt, int64_t n
             pm.C11 = mat->C11; pm.C12 = mat->C12; pm.C44 = mat->C44; pm.h = mat->h; pm.t_sat = mat->t_sat;
             pm.gss_a = mat->gss_a; pm.n_exp = 1.0 / mat->xm; pm.r = mat->r;
         }
-        CpPointState<NS> ps;
-        cp_point_solve<NS>(sl, *mat, pm, dt, H + 9 * p, A + 9 * p, g + NS * p, R + 9 * p, ps);
+        double ginv[NS], w[NS];
+        CpPointState<HArr> ps;
+        ps.ginv.p = ginv; ps.w.p = w;
+        cp_point_solve<NS, POWN>(sl, *mat, pm, dt, H + 9 * p, A + 9 * p, g + NS * p, R + 9 * p, ps);
         if (iters) { iters[3 * p] = ps.info.iters; iters[3 * p + 1] = ps.info.evals; iters[3 * p + 2] = ps.info.status; }
-        CpStressAux<NS> ax;
-        cp_point_stress<NS>(ps, R + 9 * p, P + 9 * p, ax);
-        if (tangent) cp_point_tangent<NS>(sl, pm, ps, ax, R + 9 * p, 1.0, tangent + 81 * p, 9);
+        CpStressAux ax;
+        cp_point_stress(ps, R + 9 * p, P + 9 * p, ax);
+        if (tangent) cp_point_tangent<NS>(sl, pm, ps, ax, R + 9 * p, 1.0, tangent + 81 * p, 9, 1);
+        // last: the state update overwrites ps.w
         if (A_new) cp_point_state_update<NS>(sl, pm, ps, g + NS * p, slip_old + NS * p, R + 9 * p, A_new + 9 * p, g_new + NS * p, slip_new + NS * p);
     }
 }
 
-extern "C" int hostcheck_points(int ns, const double* slip6, const CpMaterial* mat, double dt, int64_t np, const double* H,
+extern "C" int hostcheck_points(int ns, int pown, const double* slip6, const CpMaterial* mat, double dt, int64_t np, const double* H,
                                 const double* A, const double* g, const double* slip_old, const double* R, const double* pp,
                                 double* P, double* tangent, double* A_new, double* g_new, double* slip_new, int32_t* iters) {
-    if (ns == 12) run<12>(slip6, mat, dt, np, H, A, g, slip_old, R, pp, P, tangent, A_new, g_new, slip_new, iters);
-    else if (ns == 24) run<24>(slip6, mat, dt, np, H, A, g, slip_old, R, pp, P, tangent, A_new, g_new, slip_new, iters);
+#define RUN(NS, PW) run<NS, PW>(slip6, mat, dt, np, H, A, g, slip_old, R, pp, P, tangent, A_new, g_new, slip_new, iters)
+    if (ns == 12 && pown == 0) RUN(12, 0);
+    else if (ns == 12 && pown == 9) RUN(12, 9);
+    else if (ns == 12 && pown == 119) RUN(12, 119);
+    else if (ns == 24 && pown == 0) RUN(24, 0);
+    else if (ns == 24 && pown == 19) RUN(24, 19);
     else return -1;
+#undef RUN
     return 0;
 }

@@ -23,7 +23,7 @@ def load():
     return ctypes.CDLL(SO)
 
 
-def evaluate(lib, mat, dt, H, A, g, sl, R, pp=None, tangent=True):
+def evaluate(lib, mat, dt, H, A, g, sl, R, pp=None, tangent=True, pown=0):
     """mat: oracle Material. Returns P, T, A_new, g_new, slip_new, info(iters, evals, status)."""
     n = len(H)
     ns = g.shape[1]
@@ -35,7 +35,7 @@ def evaluate(lib, mat, dt, H, A, g, sl, R, pp=None, tangent=True):
     p_ = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
     if pp is not None:
         pp = np.ascontiguousarray(pp, dtype=np.float64)
-    rc = lib.hostcheck_points(ctypes.c_int(ns), p_(slip), ctypes.byref(m), ctypes.c_double(dt), ctypes.c_int64(n), p_(H), p_(A),
+    rc = lib.hostcheck_points(ctypes.c_int(ns), ctypes.c_int(pown), p_(slip), ctypes.byref(m), ctypes.c_double(dt), ctypes.c_int64(n), p_(H), p_(A),
                               p_(g), p_(sl), p_(R), p_(pp), p_(P), p_(T) if tangent else None, p_(An), p_(gn), p_(sn), p_(it))
     assert rc == 0
     return P.reshape(n, 3, 3), T.reshape(n, 3, 3, 3, 3), An.reshape(n, 3, 3), gn, sn, it

@@ -63,14 +63,16 @@ def test_point_algebra_vs_oracle(name, hostcheck):
         P_o = pb.first_PK_stress(H, dt, y).numpy()
         T_o = pb.tangent(H, dt, y).numpy()
         An_o, gn_o, sn_o = [x.numpy() for x in pb.update_int_vars(H, dt, y)]
-        P_h, T_h, An_h, gn_h, sn_h, info = hostcheck_build.evaluate(hostcheck, mat, dt, H, A, g, sl, R)
-        assert (info[:, 0] == it_o.numpy()).all() and (info[:, 1] == ev_o.numpy()).all() and (info[:, 2] == 0).all()
-        assert cases.relerr(P_h, P_o) < 1e-10
-        assert cases.relerr(T_h, T_o) < 1e-10
-        assert cases.relerr(An_h, An_o) < 1e-10 and cases.relerr(gn_h, gn_o) < 1e-10
-        # accumulated slip: compare on the physical scale ao*dt (values 1e-100 below it are amplified noise of
-        # the exponent-120 power law in both implementations)
-        assert np.abs(sn_h - sn_o).max() < 1e-10 * max(np.abs(sn_o).max(), mat.ao * dt)
+        # both code paths of the rate power: run-time exponent, and the compile-time chain the kernels pick for this set
+        for pown in {0, cases.RATE_POWN[name]}:
+            P_h, T_h, An_h, gn_h, sn_h, info = hostcheck_build.evaluate(hostcheck, mat, dt, H, A, g, sl, R, pown=pown)
+            assert (info[:, 0] == it_o.numpy()).all() and (info[:, 1] == ev_o.numpy()).all() and (info[:, 2] == 0).all()
+            assert cases.relerr(P_h, P_o) < 1e-10
+            assert cases.relerr(T_h, T_o) < 1e-10
+            assert cases.relerr(An_h, An_o) < 1e-10 and cases.relerr(gn_h, gn_o) < 1e-10
+            # accumulated slip: compare on the physical scale ao*dt (values 1e-100 below it are amplified noise of
+            # the exponent-120 power law in both implementations)
+            assert np.abs(sn_h - sn_o).max() < 1e-10 * max(np.abs(sn_o).max(), mat.ao * dt)
 
 
 def test_tangent_vs_central_differences():
