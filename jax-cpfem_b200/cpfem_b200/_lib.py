@@ -13,7 +13,8 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(os.path.dirname(_HERE), 'csrc')
 _INCLUDE = os.path.join(os.path.dirname(os.path.dirname(_HERE)), 'include')
-LIB_PATH = os.path.join(_HERE, 'libcpfem_b200.so')
+# CPFEM_B200_LIB: load another build of the same library (kernel-tuning experiments); still CUDA-only
+LIB_PATH = os.environ.get('CPFEM_B200_LIB') or os.path.join(_HERE, 'libcpfem_b200.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -80,17 +81,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out=None):
     """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    if not force and not needs_build():
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not needs_build():
         return LIB_PATH
-    cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-I', _INCLUDE, '-o', LIB_PATH] + sources()
+    cmd = ['nvcc'] + NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) + ['-I', _INCLUDE, '-o', out] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB_PATH
+    return out
 
 
 def lib():

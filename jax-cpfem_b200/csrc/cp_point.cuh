@@ -92,8 +92,15 @@ inline bool cp_slip_init(CpSlip* sl, const double* slip6, int ns) {
 }
 
 struct CpPointParams {   // per-point values actually used at one quadrature point
-    double C11, C12, C44, h, t_sat, gss_a, n_exp /* = 1/xm */, r;
+    double C11, C12, C44, n_exp /* = 1/xm */;     // needed inside the local Newton solve
+    double S11, S12, S44h;                        // cubic compliance: (C11+C12)/den, -C12/den, 1/(2 C44)
+    double h, t_sat, gss_a, r;                    // hardening law: only the state update reads them (set after the solve)
 };
+CP_HD void cp_params_elastic(CpPointParams& pm, double C11, double C12, double C44, double xm) {
+    pm.C11 = C11; pm.C12 = C12; pm.C44 = C44; pm.n_exp = 1.0 / xm;
+    const double iden = 1.0 / ((C11 - C12) * (C11 + 2.0 * C12));
+    pm.S11 = (C11 + C12) * iden; pm.S12 = -C12 * iden; pm.S44h = 0.5 / C44;
+}
 
 // Per-thread array of one double per slip system.  STRIDE = 1 on the host; on the device the kernels point it at
 // column threadIdx.x of a [NS][blockDim] shared-memory tile (conflict-free).
@@ -145,14 +152,36 @@ CP_HD void sym6_to_m3(const double* s, double* S) {
     S[5] = S[7] = s[3]; S[2] = S[6] = s[4]; S[1] = S[3] = s[5];
 }
 
-// x^N, N a compile-time integer >= 0: straight-line square-and-multiply (x^119 = 11 multiplications)
-template <int N>
-CP_HD double cp_ipow(double x) {
-    if (N == 0) return 1.0;
-    if (N == 1) return x;
-    const double h = cp_ipow<N / 2>(x);
-    return (N & 1) ? h * h * x : h * h;
-}
+// x_u^N for U values at once, N a compile-time integer >= 1.  The chains of the U values advance in lock step
+// (statement order = interleaved), so that consecutive DMULs are independent and the FP64 pipe latency is hidden
+// by instruction-level parallelism.  Square-and-multiply, except that a factor 7 or 17 of N is peeled off first
+// (119 = 7 x 17: 4 + 5 = 9 multiplications instead of 11).
+template <int N, int U>
+struct CpIpow {
+    static CP_HD void run(const double* x, double* out) {
+        if (N == 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) out[u] = x[u];
+        } else if (N > 17 && N % 17 == 0) {
+            double y[U];
+            CpIpow<17, U>::run(x, y);
+            CpIpow<(N % 17 == 0 ? N / 17 : 1), U>::run(y, out);
+        } else if (N > 7 && N % 7 == 0) {
+            double y[U];
+            CpIpow<7, U>::run(x, y);
+            CpIpow<(N % 7 == 0 ? N / 7 : 1), U>::run(y, out);
+        } else {
+            double h[U];
+            CpIpow<(N > 1 ? N / 2 : 1), U>::run(x, h);
+#pragma unroll
+            for (int u = 0; u < U; ++u) out[u] = h[u] * h[u];
+            if (N & 1) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) out[u] *= x[u];
+            }
+        }
+    }
+};
 
 // x^e for x >= 0, run-time e.  Integers take the square-and-multiply loop, half-integers add one sqrt
 // (copper's hardening exponent 2.5), everything else (tantalum: 44.2726) goes through pow().
@@ -175,8 +204,7 @@ CP_HD double cp_pow_pos(double x, double e) {
 template <int POWN, int U>
 CP_HD void cp_rate_pow(const double* ax /*U, >= 0*/, double n1, double* out) {
     if (POWN > 0) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) out[u] = cp_ipow<(POWN > 0 ? POWN : 1)>(ax[u]);
+        CpIpow<(POWN > 0 ? POWN : 1), U>::run(ax, out);
     } else {
         if (n1 == floor(n1) && n1 >= 0.0 && n1 < 2048.0) {
             int k = (int)n1;
@@ -278,8 +306,7 @@ CP_HD void cp_newton_matrix(const CpSlip& sl, const CpPointParams& pm, const dou
                             const Arr& w, double* N /*36*/, double* piv /*6*/) {
     double K[9];
     m3_mul_tn(Fe, G, K);
-    const double den = (pm.C11 - pm.C12) * (pm.C11 + 2.0 * pm.C12);
-    const double S11 = (pm.C11 + pm.C12) / den, S12 = -pm.C12 / den, S44q = 0.25 / pm.C44;
+    const double S11 = pm.S11, S12 = pm.S12, S44q = 0.5 * pm.S44h;
 #pragma unroll
     for (int i = 0; i < 36; ++i) N[i] = 0.0;
     N[0] = N[7] = N[14] = S11;
@@ -330,8 +357,7 @@ CP_HD void cp_lu_solve(const double* N, const double* piv, double* b /*6, in: rh
 
 // b = -C^-1 r (strain-like vector)
 CP_HD void cp_compliance_neg(const CpPointParams& pm, const double* r, double* b) {
-    const double den = (pm.C11 - pm.C12) * (pm.C11 + 2.0 * pm.C12);
-    const double S11 = (pm.C11 + pm.C12) / den, S12 = -pm.C12 / den, S44h = 0.5 / pm.C44;
+    const double S11 = pm.S11, S12 = pm.S12, S44h = pm.S44h;
     b[0] = -(S11 * r[0] + S12 * (r[1] + r[2]));
     b[1] = -(S11 * r[1] + S12 * (r[0] + r[2]));
     b[2] = -(S11 * r[2] + S12 * (r[0] + r[1]));
@@ -428,23 +454,30 @@ struct CpPointState {       // everything the output stages need, crystal frame
 };
 
 // Set-up + solve for one point.  H = u_grad (lab), A = Fp_inv_old (lab), g = slip resistances (any indexable),
-// R = rot_mat.  ps.ginv / ps.w must point at storage for NS doubles each.
+// R = rot_mat.  ps.ginv / ps.w must point at storage for NS doubles each.  ps.Ac is NOT set here: the output stages
+// need it, the Newton loop does not, so the callers fill it afterwards with cp_point_frame (the kernels reload A and
+// R from memory for that, which keeps 27 doubles out of the loop's registers).
 template <int NS, int POWN, class Arr, class GIn>
 CP_HD void cp_point_solve(const CpSlip& sl, const CpMaterial& mat, const CpPointParams& pm, double dt,
                           const double* H, const double* A, const GIn& g, const double* R, CpPointState<Arr>& ps) {
     {
-        double F[9], Fc[9];
+        double F[9], Fc[9], Ac[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) F[i] = H[i];
         F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
         cp_to_crystal(R, F, Fc);
-        cp_to_crystal(R, A, ps.Ac);
-        m3_mul(Fc, ps.Ac, ps.G);
+        cp_to_crystal(R, A, Ac);
+        m3_mul(Fc, Ac, ps.G);
     }
 #pragma unroll 4
     for (int a = 0; a < NS; ++a) ps.ginv[a] = 1.0 / g[a];
     ps.cdt = mat.ao * dt;
     cp_newton<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp, ps.info);
+}
+
+template <class Arr>
+CP_HD void cp_point_frame(const double* A, const double* R, CpPointState<Arr>& ps) {   // Ac = R^T Fp_inv_old R
+    cp_to_crystal(R, A, ps.Ac);
 }
 
 // New state (models_copper.py:164-169 via helper :172-192): Fp_inv_new (lab), g_new, slip_new.

@@ -329,18 +329,35 @@ __device__ __forceinline__ GOut gout(double* base, int soa, int64_t p, int ncomp
     return g;
 }
 
+__device__ __forceinline__ void load9(const double* base, int soa, int64_t p, int64_t np, double* out) {
+    const GIn a = gin(base, soa, p, 9, np);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out[i] = a[i];
+}
+
+// elastic constants + rate exponent: what the local Newton solve needs
 __device__ __forceinline__ void load_point_params(const CpMaterial& m, const StateView& st, int64_t p, CpPointParams& pm) {
+    double C11 = m.C11, C12 = m.C12, C44 = m.C44;
     if (st.C) {
         const double* C = st.C + p * 81;
-        pm.C11 = C[0]; pm.C12 = C[4]; pm.C44 = C[50];
-    } else {
-        pm.C11 = m.C11; pm.C12 = m.C12; pm.C44 = m.C44;
+        C11 = C[0]; C12 = C[4]; C44 = C[50];
     }
+    cp_params_elastic(pm, C11, C12, C44, st.xm ? st.xm[p] : m.xm);
+}
+// hardening law: loaded after the solve, only by the state update
+__device__ __forceinline__ void load_point_params_hard(const CpMaterial& m, const StateView& st, int64_t p, CpPointParams& pm) {
     pm.h = st.h ? st.h[p] : m.h;
     pm.t_sat = st.t_sat ? st.t_sat[p] : m.t_sat;
     pm.gss_a = st.gss_a ? st.gss_a[p] : m.gss_a;
     pm.r = st.r ? st.r[p] : m.r;
-    pm.n_exp = 1.0 / (st.xm ? st.xm[p] : m.xm);
+}
+// after the solve: reload A = Fp_inv_old and R, set ps.Ac (see cp_point_solve)
+template <class Arr>
+__device__ __forceinline__ void point_frame(const StateView& st, int64_t p, int64_t np, double* R, CpPointState<Arr>& ps) {
+    double A[9];
+    load9(st.Fp_inv, st.soa, p, np, A);
+    load9(st.rot, st.soa, p, np, R);
+    cp_point_frame(A, R, ps);
 }
 
 // hex8 physical shape-function gradients and JxW at Gauss point q (2x2x2, x slowest / z fastest),
@@ -410,11 +427,6 @@ __device__ __forceinline__ void point_kinematics(const int32_t* __restrict__ cel
     }
 }
 
-__device__ __forceinline__ void load9(const double* base, int soa, int64_t p, int64_t np, double* out) {
-    const GIn a = gin(base, soa, p, 9, np);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) out[i] = a[i];
-}
 
 __device__ __forceinline__ void warp_status(const CpSolveInfo& info, bool valid, long long* status) {
     if (!status) return;
@@ -441,6 +453,9 @@ __device__ __forceinline__ void warp_status(const CpSolveInfo& info, bool valid,
 // Per-point kernels: one thread per quadrature point, PT_BLOCK threads per block; the two per-slip-system arrays
 // (1/g, w) of every thread are columns of a [2][NS][PT_BLOCK] shared-memory tile.
 #define PT_BLOCK 128
+#ifndef PT_MIN_BLOCKS
+#define PT_MIN_BLOCKS 3      // 3 x 128 threads x 168 registers per SM
+#endif
 typedef CpArr<PT_BLOCK> SArr;
 template <int NS>
 __device__ __forceinline__ void point_arrays(double* smem, CpPointState<SArr>& ps) {
@@ -465,7 +480,7 @@ __device__ __forceinline__ void solve_point(const StateView& st, const CpMateria
 // K1: state update
 // -----------------------------------------------------------------------------------------------
 template <int NS, int POWN>
-__global__ void __launch_bounds__(PT_BLOCK, 3)
+__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
                StateView st, cpfem_state_out out, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt,
                int64_t np, long long* status) {
@@ -484,7 +499,8 @@ k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ poi
     if (valid) {
         const int so = (out.layout == CPFEM_LAYOUT_SOA);
         double R[9], An[9];
-        load9(st.rot, st.soa, p, np, R);
+        point_frame(st, p, np, R, ps);
+        load_point_params_hard(mat, st, p, pm);
         cp_point_state_update<NS>(slip, pm, ps, gin(st.g, st.soa, p, NS, np), gin(st.slip, st.soa, p, NS, np), R, An,
                                   gout(out.g, so, p, NS, np), gout(out.slip, so, p, NS, np));
         const GOut Ao = gout(out.Fp_inv, so, p, 9, np);
@@ -506,7 +522,7 @@ template <int NS>
 static constexpr size_t residual_smem() { return point_smem<NS>() + sizeof(double) * (PT_BLOCK / 32) * 4 * (GN_CELL + PJ_CELL); }
 
 template <int NS, int POWN>
-__global__ void __launch_bounds__(PT_BLOCK, 3)
+__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
            StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t nc,
            double* __restrict__ res, long long* status) {
@@ -536,7 +552,7 @@ k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points,
             solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
         }
         double R[9], P[9];
-        load9(st.rot, st.soa, p, np, R);
+        point_frame(st, p, np, R, ps);
         CpStressAux ax;
         cp_point_stress(ps, R, P, ax);
         double* pj = PJ + cl * PJ_CELL + q * 9;
@@ -571,7 +587,7 @@ k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points,
 //   PJ[9][npc]  = P_ij JxW          TA[81][npc] = dP_ij/dH_kl JxW        (npc = points in the chunk)
 // -----------------------------------------------------------------------------------------------
 template <int NS, int POWN>
-__global__ void __launch_bounds__(PT_BLOCK, 3)
+__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
                 StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np, int64_t p0,
                 int64_t npc, double* __restrict__ PJ, double* __restrict__ TA, long long* status) {
@@ -589,7 +605,7 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
         solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
     }
     double R[9], P[9];
-    load9(st.rot, st.soa, p, np, R);
+    point_frame(st, p, np, R, ps);
     CpStressAux ax;
     cp_point_stress(ps, R, P, ax);
     if (valid) {
@@ -715,7 +731,7 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
 // K5: average Cauchy stress per cell (models_copper.py:297-319)
 // -----------------------------------------------------------------------------------------------
 template <int NS, int POWN>
-__global__ void __launch_bounds__(PT_BLOCK, 3)
+__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
              StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np,
              double* __restrict__ sigma_cell, long long* status) {
@@ -735,7 +751,7 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
         solve_point<NS, POWN>(st, mat, slip, dt, p, np, F, pm, ps);
     }
     double R[9], P[9], sg[9];
-    load9(st.rot, st.soa, p, np, R);
+    point_frame(st, p, np, R, ps);
     CpStressAux ax;
     cp_point_stress(ps, R, P, ax);
     // sigma = P F^T / det F (:308-309)
@@ -763,7 +779,7 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
 // tensor_map on explicit u_grads (and its jacfwd)
 // -----------------------------------------------------------------------------------------------
 template <int NS, int POWN>
-__global__ void __launch_bounds__(PT_BLOCK, 3)
+__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip,
              double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, long long* status) {
     extern __shared__ double smem[];
@@ -780,7 +796,7 @@ k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, c
         solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
     }
     double R[9], P[9];
-    load9(st.rot, st.soa, p, np, R);
+    point_frame(st, p, np, R, ps);
     CpStressAux ax;
     cp_point_stress(ps, R, P, ax);
     if (valid) {

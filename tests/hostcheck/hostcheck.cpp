@@ -19,16 +19,17 @@ static void run(const double* slip6, const CpMaterial* mat, double dt, int64_t n
         CpPointParams pm;
         if (pp) {
             const double* q = pp + 8 * p;   // C11 C12 C44 h t_sat gss_a xm r
-            pm.C11 = q[0]; pm.C12 = q[1]; pm.C44 = q[2]; pm.h = q[3]; pm.t_sat = q[4]; pm.gss_a = q[5];
-            pm.n_exp = 1.0 / q[6]; pm.r = q[7];
+            cp_params_elastic(pm, q[0], q[1], q[2], q[6]);
+            pm.h = q[3]; pm.t_sat = q[4]; pm.gss_a = q[5]; pm.r = q[7];
         } else {
-            pm.C11 = mat->C11; pm.C12 = mat->C12; pm.C44 = mat->C44; pm.h = mat->h; pm.t_sat = mat->t_sat;
-            pm.gss_a = mat->gss_a; pm.n_exp = 1.0 / mat->xm; pm.r = mat->r;
+            cp_params_elastic(pm, mat->C11, mat->C12, mat->C44, mat->xm);
+            pm.h = mat->h; pm.t_sat = mat->t_sat; pm.gss_a = mat->gss_a; pm.r = mat->r;
         }
         double ginv[NS], w[NS];
         CpPointState<HArr> ps;
         ps.ginv.p = ginv; ps.w.p = w;
         cp_point_solve<NS, POWN>(sl, *mat, pm, dt, H + 9 * p, A + 9 * p, g + NS * p, R + 9 * p, ps);
+        cp_point_frame(A + 9 * p, R + 9 * p, ps);
         if (iters) { iters[3 * p] = ps.info.iters; iters[3 * p + 1] = ps.info.evals; iters[3 * p + 2] = ps.info.status; }
         CpStressAux ax;
         cp_point_stress(ps, R + 9 * p, P + 9 * p, ax);
