@@ -60,15 +60,25 @@ struct cpfem_plan {
     int64_t* indptr = nullptr;    // (3 nn + 1)
     int32_t* indices = nullptr;   // (nnz)
     uint8_t* rank = nullptr;      // (nc,8,8): rank of node b in the sorted neighbour list of node a
-    double* scratch = nullptr;    // (90, 8*chunk_cells): P JxW and dP/dH JxW of one chunk of cells, component-major
-    int64_t chunk_cells = 0;      // cells per assembly chunk
+    // assembly pipeline: the point kernel of chunk i+1 (FP64-bound, caller's stream) overlaps the element kernel of
+    // chunk i (load/store- and atomics-bound, plan-owned high-priority stream); two scratch buffers alternate
+    double* scratch[2] = {nullptr, nullptr};   // each (90, 8*chunk_cells): P JxW and dP/dH JxW, component-major
+    int64_t chunk_cells = 0;                   // cells per assembly chunk
+    cudaStream_t elem_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_point[2] = {nullptr, nullptr}, ev_elem[2] = {nullptr, nullptr};
     CpSlip slip;
     int device = 0;
     int sm_count = 148;
 };
 
 #define MAX_VALENCE 16
+// two-stream overlap of the point and element kernels: measured on B200 (r1c), no gain (38.1 vs 37.3 ms at 128^3) - off
+#ifndef CPFEM_OVERLAP
+#define CPFEM_OVERLAP 0
+#endif
+#ifndef CPFEM_CHUNK_CELLS
 #define CPFEM_CHUNK_CELLS (1 << 19)   // 4 Mi points per assembly chunk: 3.0 GB of scratch
+#endif
 
 __global__ void k_count_valence(const int32_t* __restrict__ cells, int64_t n, int64_t nn, int64_t* cnt, int* err) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,7 +175,13 @@ static cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc((void**)p, n *
 extern "C" int cpfem_plan_destroy(cpfem_plan* p) {
     if (!p) return 0;
     cudaFree(p->cells); cudaFree(p->points); cudaFree(p->indptr); cudaFree(p->indices); cudaFree(p->rank);
-    cudaFree(p->scratch);
+    cudaFree(p->scratch[0]); cudaFree(p->scratch[1]);
+    if (p->elem_stream) cudaStreamDestroy(p->elem_stream);
+    if (p->ev_start) cudaEventDestroy(p->ev_start);
+    for (int i = 0; i < 2; ++i) {
+        if (p->ev_point[i]) cudaEventDestroy(p->ev_point[i]);
+        if (p->ev_elem[i]) cudaEventDestroy(p->ev_elem[i]);
+    }
     delete p;
     return 0;
 }
@@ -237,8 +253,24 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
         PLAN_TRY(dev_alloc(&p->indptr, 3 * nnodes + 1));
         PLAN_TRY(dev_alloc(&p->indices, p->nnz));
         PLAN_TRY(dev_alloc(&p->rank, nc * 64));
-        p->chunk_cells = nc < CPFEM_CHUNK_CELLS ? nc : CPFEM_CHUNK_CELLS;
-        PLAN_TRY(dev_alloc(&p->scratch, (size_t)90 * 8 * p->chunk_cells));
+        // chunking: CPFEM_CHUNK_CELLS per chunk for big meshes, four chunks for mid-size ones (so that the two
+        // kernels of the assembly overlap), one chunk for tiny ones; always a multiple of 16 cells (one 128-thread block)
+        if (nc >= 4 * CPFEM_CHUNK_CELLS) p->chunk_cells = CPFEM_CHUNK_CELLS;
+        else if (nc >= 4096 && CPFEM_OVERLAP) p->chunk_cells = (((nc + 3) / 4) + 15) / 16 * 16;
+        else p->chunk_cells = nc < CPFEM_CHUNK_CELLS ? nc : CPFEM_CHUNK_CELLS;
+        {
+            const bool two = p->chunk_cells < nc;
+            PLAN_TRY(dev_alloc(&p->scratch[0], (size_t)90 * 8 * p->chunk_cells));
+            if (two && CPFEM_OVERLAP) PLAN_TRY(dev_alloc(&p->scratch[1], (size_t)90 * 8 * p->chunk_cells));
+            int lo = 0, hi = 0;
+            PLAN_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            PLAN_TRY(cudaStreamCreateWithPriority(&p->elem_stream, cudaStreamNonBlocking, hi));
+            PLAN_TRY(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+            for (int i = 0; i < 2; ++i) {
+                PLAN_TRY(cudaEventCreateWithFlags(&p->ev_point[i], cudaEventDisableTiming));
+                PLAN_TRY(cudaEventCreateWithFlags(&p->ev_elem[i], cudaEventDisableTiming));
+            }
+        }
         k_fill_csr<<<blocks(nnodes + 1), T, 0, stream>>>(nbr_ptr, nbr, nnodes, p->indptr, p->indices);
         k_rank_map<<<blocks(nc * 8), T, 0, stream>>>(p->cells, nc, nbr_ptr, nbr, p->rank);
         // max valence (for info only)
@@ -623,31 +655,52 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
 //   K_e[3a+i, :]  = sum_q sum_jl dN_a,j TA_q[ij,kl] dN_b,l  (24 columns) -> atomicAdd into the CSR slots of row 3 n_a + i
 //                                                                          (slot = indptr[row] + 3 rank(a,b) + k), optional COO V
 // -----------------------------------------------------------------------------------------------
-#define TA_PT 82
-#define TA_CELL (8 * TA_PT + 2)     // 658
-#define ELEM_WARP_DOUBLES (4 * TA_CELL + 4 * GN_CELL + 4 * PJ_CELL)
+// The tangent is consumed in three slices (one per row i of P): 27 doubles per point are staged at a time, which keeps
+// the shared-memory footprint at 15.6 kB per warp (12 warps per SM) instead of 29.6 kB.
+#define TS_PT 27                     // odd point stride: the 32 staging stores of a warp are conflict-free
+#define TS_CELL (8 * TS_PT + 2)      // 218: the four cells of a warp fall into different banks for the broadcast reads
+#define KE_ROW 25                    // odd row stride of the K_e row tile: conflict-free stores
+// per warp: tangent slice, shape gradients, P JxW, one K_e row (24 doubles) per lane, and per lane the CSR row start
+// (int64) + the 8 column-block offsets (int32) of its row for the coalesced scatter
+#define ELEM_WARP_DOUBLES (4 * TS_CELL + 4 * GN_CELL + 4 * PJ_CELL + 32 * KE_ROW + 32 + 32 * 4)
+#define ELEM_WARPS 4
+#ifndef ELEM_PREFETCH
+#define ELEM_PREFETCH 0
+#endif
+#ifndef ELEM_MIN_BLOCKS
+#define ELEM_MIN_BLOCKS 3
+#endif
 
-__global__ void __launch_bounds__(224, 1)
+__global__ void __launch_bounds__(ELEM_WARPS * 32, ELEM_MIN_BLOCKS)
 k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, int64_t c0, int64_t ncc,
                   const double* __restrict__ PJg, const double* __restrict__ TAg, const int64_t* __restrict__ indptr,
                   const uint8_t* __restrict__ rank, double* __restrict__ res, double* __restrict__ csr_data,
-                  double* __restrict__ coo_V, int warps_per_block) {
+                  double* __restrict__ coo_V) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* TA = smem + (size_t)warp * ELEM_WARP_DOUBLES;
-    double* GN = TA + 4 * TA_CELL;
+    double* TS = smem + (size_t)warp * ELEM_WARP_DOUBLES;
+    double* GN = TS + 4 * TS_CELL;
     double* PJ = GN + 4 * GN_CELL;
+    double* KE = PJ + 4 * PJ_CELL;                                   // [32 lanes][KE_ROW]
+    long long* ROWP = reinterpret_cast<long long*>(KE + 32 * KE_ROW); // [32] CSR slot of the row start (or -1)
+    int* RB = reinterpret_cast<int*>(ROWP + 32);                      // [32][8] column-block offsets
     const int cl = lane >> 3, a = lane & 7;
     const int64_t nquads = (ncc + 3) >> 2;
     const int64_t npc = ncc * 8;
-    for (int64_t quad = (int64_t)blockIdx.x * warps_per_block + warp; quad < nquads;
-         quad += (int64_t)gridDim.x * warps_per_block) {
+    for (int64_t quad = (int64_t)blockIdx.x * ELEM_WARPS + warp; quad < nquads; quad += (int64_t)gridDim.x * ELEM_WARPS) {
         int64_t cc = quad * 4 + cl;                // cell within the chunk
         const bool valid = cc < ncc;
         if (!valid) cc = ncc - 1;
         const int64_t c = c0 + cc;
-        // ---- stage: own point's shape gradients, the warp's 32 points of PJ and TA ----
+        const int64_t pl = cc * 8 + a;             // this lane's point of the chunk (clamped cells re-read the last cell)
+        double* ts = TS + cl * TS_CELL + a * TS_PT;
+        // ---- stage: slice 0 of the tangent and P JxW of this lane's point, its shape gradients ----
         {
+            double t[27], pj9[9];
+#pragma unroll
+            for (int i = 0; i < 27; ++i) t[i] = TAg[i * npc + pl];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) pj9[i] = PJg[i * npc + pl];
             double gN[8][3], JxW;
             point_kinematics(cells, points, nullptr, c, a, nullptr, gN, JxW);
             double* gq = GN + cl * GN_CELL + a * 24;
@@ -655,13 +708,11 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
             for (int b = 0; b < 8; ++b)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) gq[b * 3 + i] = gN[b][i];
-            const int64_t pl = cc * 8 + a;          // clamped cells re-read the last cell: harmless
             double* pj = PJ + cl * PJ_CELL + a * 9;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) pj[i] = PJg[i * npc + pl];
-            double* ta = TA + cl * TA_CELL + a * TA_PT;
-#pragma unroll 9
-            for (int i = 0; i < 81; ++i) ta[i] = TAg[i * npc + pl];
+            for (int i = 0; i < 9; ++i) pj[i] = pj9[i];
+#pragma unroll
+            for (int i = 0; i < 27; ++i) ts[i] = t[i];
         }
         __syncwarp();
         const int64_t na = cells[c * 8 + a];
@@ -682,20 +733,30 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
                 atomicAdd(&res[na * 3 + 2], r2);
             }
         }
-        int rb[8];
         if (csr_data) {
             const uint2 rk = *reinterpret_cast<const uint2*>(rank + (c * 8 + a) * 8);
 #pragma unroll
-            for (int b = 0; b < 4; ++b) { rb[b] = 3 * (int)((rk.x >> (8 * b)) & 0xffu); rb[4 + b] = 3 * (int)((rk.y >> (8 * b)) & 0xffu); }
+            for (int b = 0; b < 4; ++b) {
+                RB[lane * 8 + b] = 3 * (int)((rk.x >> (8 * b)) & 0xffu);
+                RB[lane * 8 + 4 + b] = 3 * (int)((rk.y >> (8 * b)) & 0xffu);
+            }
         }
 #pragma unroll 1
         for (int i = 0; i < 3; ++i) {
+            // prefetch the next slice into registers while this one is consumed
+#if ELEM_PREFETCH
+            double t[27];
+            if (i < 2) {
+#pragma unroll
+                for (int k = 0; k < 27; ++k) t[k] = TAg[((i + 1) * 27 + k) * npc + pl];
+            }
+#endif
             double acc[24];
 #pragma unroll
             for (int j = 0; j < 24; ++j) acc[j] = 0.0;
 #pragma unroll 2
             for (int qq = 0; qq < 8; ++qq) {
-                const double* ta = TA + cl * TA_CELL + qq * TA_PT + (3 * i) * 9;
+                const double* ta = TS + cl * TS_CELL + qq * TS_PT;
                 const double* gq = GN + cl * GN_CELL + qq * 24;
                 const double ga0 = gq[a * 3], ga1 = gq[a * 3 + 1], ga2 = gq[a * 3 + 2];
                 double T[9];
@@ -708,22 +769,46 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
                     for (int k = 0; k < 3; ++k) acc[3 * b + k] += T[3 * k] * gb0 + T[3 * k + 1] * gb1 + T[3 * k + 2] * gb2;
                 }
             }
+            __syncwarp();                           // every lane is done reading slice i
+#if ELEM_PREFETCH
+            if (i < 2) {
+#pragma unroll
+                for (int k = 0; k < 27; ++k) ts[k] = t[k];
+            }
+#else
+            if (i < 2) {
+                double t[27];
+#pragma unroll
+                for (int k = 0; k < 27; ++k) t[k] = TAg[((i + 1) * 27 + k) * npc + pl];
+#pragma unroll
+                for (int k = 0; k < 27; ++k) ts[k] = t[k];
+            }
+#endif
             if (valid) {
                 if (coo_V) {
                     double* v = coo_V + c * 576 + (int64_t)(3 * a + i) * 24;
 #pragma unroll
                     for (int j = 0; j < 24; ++j) v[j] = acc[j];
                 }
-                if (csr_data) {
-                    double* row = csr_data + indptr[na * 3 + i];
+            }
+            if (csr_data) {
+                // coalesced scatter: every lane parks its row in shared memory, then one warp instruction adds one row:
+                // lanes 0..23 hit the 8 x 24-byte pieces of that CSR row (x-neighbour pairs are contiguous), i.e. a
+                // handful of sectors per instruction instead of 32
+                double* ke = KE + lane * KE_ROW;
 #pragma unroll
-                    for (int b = 0; b < 8; ++b)
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) atomicAdd(&row[rb[b] + k], acc[3 * b + k]);
+                for (int j = 0; j < 24; ++j) ke[j] = acc[j];
+                ROWP[lane] = valid ? (long long)indptr[na * 3 + i] : -1LL;
+                __syncwarp();
+                const int jb = (lane < 24) ? lane / 3 : 0, jk = (lane < 24) ? lane - 3 * (lane / 3) : 0;
+#pragma unroll 4
+                for (int t = 0; t < 32; ++t) {
+                    const long long base = ROWP[t];
+                    if (lane < 24 && base >= 0) atomicAdd(csr_data + base + RB[t * 8 + jb] + jk, KE[t * KE_ROW + lane]);
                 }
             }
+            __syncwarp();                           // slice i+1 is visible, KE / ROWP free again
         }
-        __syncwarp();
     }
 }
 
@@ -970,14 +1055,25 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
     CpMaterial m = to_mat(mat);
     const int pown = rate_pown(m, v);
     const int64_t np = plan->nc_active * 8;
-    const int wpb = 7;
-    const size_t esmem = sizeof(double) * ELEM_WARP_DOUBLES * wpb;
+    const size_t esmem = sizeof(double) * ELEM_WARP_DOUBLES * ELEM_WARPS;
     CU_TRY(allow_smem(k_element_tangent, esmem));
-    for (int64_t c0 = 0; c0 < plan->nc_active; c0 += plan->chunk_cells) {
+    int ebps = 1;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ebps, k_element_tangent, ELEM_WARPS * 32, esmem));
+    if (ebps < 1) return set_err(-2, "cpfem_newton_update: element kernel does not fit on an SM");
+    const bool piped = plan->scratch[1] != nullptr && CPFEM_OVERLAP;
+    cudaStream_t estream = piped ? plan->elem_stream : stream;
+    if (piped) {
+        CU_TRY(cudaEventRecord(plan->ev_start, stream));              // res / csr_data are zeroed
+        CU_TRY(cudaStreamWaitEvent(estream, plan->ev_start, 0));
+    }
+    int64_t ichunk = 0;
+    for (int64_t c0 = 0; c0 < plan->nc_active; c0 += plan->chunk_cells, ++ichunk) {
         const int64_t ncc = (plan->nc_active - c0 < plan->chunk_cells) ? plan->nc_active - c0 : plan->chunk_cells;
         const int64_t npc = ncc * 8;
-        double* PJ = plan->scratch;
-        double* TA = plan->scratch + 9 * npc;
+        const int buf = piped ? (int)(ichunk & 1) : 0;
+        double* PJ = plan->scratch[buf];
+        double* TA = plan->scratch[buf] + 9 * npc;
+        if (piped && ichunk >= 2) CU_TRY(cudaStreamWaitEvent(stream, plan->ev_elem[buf], 0));   // buffer free again
         const unsigned grid = (unsigned)((npc + PT_BLOCK - 1) / PT_BLOCK);
 #define CALL(NS, PW)                                                                                                   \
     CU_TRY(allow_smem(k_point_tangent<NS, PW>, point_smem<NS>()));                                                     \
@@ -986,12 +1082,21 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
         CP_DISPATCH(plan->ns, pown, CALL);
 #undef CALL
         CU_TRY(cudaGetLastError());
+        if (piped) {
+            CU_TRY(cudaEventRecord(plan->ev_point[buf], stream));
+            CU_TRY(cudaStreamWaitEvent(estream, plan->ev_point[buf], 0));
+        }
         const int64_t nquads = (ncc + 3) / 4;
-        int64_t egrid = (nquads + wpb - 1) / wpb;
-        if (egrid > plan->sm_count) egrid = plan->sm_count;
-        k_element_tangent<<<(unsigned)egrid, wpb * 32, esmem, stream>>>(plan->cells, plan->points, c0, ncc, PJ, TA, plan->indptr,
-                                                                        plan->rank, res, csr_data, coo_V, wpb);
+        int64_t egrid = (nquads + ELEM_WARPS - 1) / ELEM_WARPS;
+        if (egrid > (int64_t)plan->sm_count * ebps) egrid = (int64_t)plan->sm_count * ebps;
+        k_element_tangent<<<(unsigned)egrid, ELEM_WARPS * 32, esmem, estream>>>(plan->cells, plan->points, c0, ncc, PJ, TA, plan->indptr,
+                                                                                plan->rank, res, csr_data, coo_V);
         CU_TRY(cudaGetLastError());
+        if (piped) CU_TRY(cudaEventRecord(plan->ev_elem[buf], estream));
+    }
+    if (piped) {                                                      // join: the caller's stream owns the results
+        CU_TRY(cudaStreamWaitEvent(stream, plan->ev_elem[0], 0));
+        if (ichunk >= 2) CU_TRY(cudaStreamWaitEvent(stream, plan->ev_elem[1], 0));
     }
     return 0;
 }
