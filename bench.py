@@ -28,13 +28,18 @@ sys.path.insert(0, os.path.join(ROOT, 'jax-cpfem_b200'))
 import numpy as np
 import torch
 
-# ---- algorithmic work model (DESIGN.md "Work model"; flops with FMA = 2, integer pow(x,119) = 13 flops) ----------
-F_RES = 840.0            # one residual evaluation, 12 slip systems
-F_ITER = 2620.0          # one local Newton iteration = Newton matrix + 6x6 LU/solve + one residual evaluation
-F_UPDATE_FIXED = 2400.0  # kinematics + frame change + first residual + hardening/state update
-F_ASSEMBLY_FIXED = 17600.0  # kinematics + frame change + first residual + stress + tangent (11 k) + element K_e share (4.9 k)
-B_UPDATE = 610.0         # bytes/point: state in 336 + state out 264 + mesh/sol share 10
-B_ASSEMBLY = 740.0       # bytes/point: state in 240 + mesh/sol 10 + CSR memset 244 + CSR write 244 (+ residual)
+# ---- work model (DESIGN.md "Work model") ------------------------------------------------------------------------
+# algorithmic flops per point, SURVEY.md section 8(d) / Appendix G (hand-derived 9x9 formulation, FMA = 2 flops):
+F_UPDATE_FIXED = 1600.0     # set-up: Schmid rotation, B = F A M, hardening
+F_ITER = 5000.0             # one local Newton iteration incl. one line-search residual evaluation
+F_ASSEMBLY_FIXED = 16600.0  # set-up + consistent tangent (10 k) + element K_e share (5 k)
+# executed by this implementation (6x6 symmetric crystal-frame form), 2 x FP64 instructions from the ncu source page:
+X_UPDATE_FIXED = 3000.0     # kinematics, frame change, first residual, state update
+X_ITER = 3200.0             # Newton matrix (12 x 61) + LU + solve (1.0 k instr) + 1.7 residual evaluations x 0.36 k, x 2
+X_ASSEMBLY_FIXED = 17000.0  # + stress, 9-direction tangent (4.6 k instr), element K_e (2.4 k instr)
+B_UPDATE = 610.0            # bytes/point: state in 336 + state out 264 + mesh/sol share 10
+B_ASSEMBLY = 2180.0         # bytes/point: state 240 + mesh/sol 10 + CSR memset 244 + CSR RMW 244 + scratch 2 x 720
+TRAFFIC_UPDATE_B_PER_POINT = 600.0   # ncu dram__bytes_read + write per point, k_update_state at 64^3 (profiles/r1)
 
 MESH_N = 200
 D_EPS, DT, PRE_STEPS = 2e-4, 2e-3, 10
@@ -295,53 +300,55 @@ def main():
     res_norm = float(torch.sqrt(norm_buf)[0])
 
     # ---- e2e: host (pinned) buffers through the public API ---------------------------------------------------
+    # update pass: Plan.update_state_host streams the host-resident state through the device (H2D of sol + state, update,
+    # D2H of the new state, chunk-pipelined on three streams).  Assembly: H2D of sol + state, newton_update, D2H of the
+    # residual (the CSR stays on the device for the device linear solver).
     e2e = None
     if not args.no_e2e:
-        hin = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (sol, state[0], state[1], state[2], state[3])]
-        for h, t in zip(hin, (sol, state[0], state[1], state[2], state[3])):
+        if layout != api.LAYOUT_AOS:
+            raise SystemExit('e2e uses the reference (AoS) layout')
+        hsol = torch.empty(sol.shape, dtype=sol.dtype, pin_memory=True)
+        hsol.copy_(sol)
+        hstate = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in state]
+        for h, t in zip(hstate, state):
             h.copy_(t)
-        hout = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (out[0], out[1], out[2], res)]
+        hnew = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in out]
+        hres = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
         dsol = torch.empty_like(sol)
-        dstate = [torch.empty_like(t) for t in state]
-        h2d = sum(h.numel() * 8 for h in hin)
-        d2h_state = sum(h.numel() * 8 for h in hout[:3])
-        d2h_res = hout[3].numel() * 8
+        h2d_upd = hsol.numel() * 8 + sum(h.numel() * 8 for h in hstate)
+        d2h_upd = sum(h.numel() * 8 for h in hnew)
         Ke = max(1, min(K, 3))
-        te = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(Ke + 1)]
+        te = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(Ke + 1)]
         barrier()
         for k in range(Ke + 1):                      # first pass is warm-up
             te[k][0].record()
-            dsol.copy_(hin[0], non_blocking=True)
-            for d, h in zip(dstate, hin[1:]):
-                d.copy_(h, non_blocking=True)
+            plan.update_state_host(mat, hsol, hstate, DT, out=hnew)            # synchronises before returning
             te[k][1].record()
-            plan.update_state(mat, dsol, dstate, DT, out=out, layout=layout)
-            te[k][2].record()
-            for h, d in zip(hout[:3], out):
-                h.copy_(d, non_blocking=True)
-            te[k][3].record()
-            plan.newton_update(mat, dsol, dstate, DT, res=res, csr_data=csr, layout=layout)
+            dsol.copy_(hsol, non_blocking=True)
+            dst = [state[0], state[1], state[3]]
+            for d, h in zip(dst, (hstate[0], hstate[1], hstate[3])):           # the assembly does not read the slips
+                d.copy_(h, non_blocking=True)
+            plan.newton_update(mat, dsol, state, DT, res=res, csr_data=csr, layout=layout)
             if ex is not None:
                 ex.exchange(res, csr)
-            hout[3].copy_(res, non_blocking=True)
-            te[k][4].record()
+            hres.copy_(res, non_blocking=True)
+            te[k][2].record()
         barrier()
-        t_h2d = sum(e[0].elapsed_time(e[1]) for e in te[1:])
-        t_k = sum(e[1].elapsed_time(e[2]) for e in te[1:])
-        t_d2h = sum(e[2].elapsed_time(e[3]) for e in te[1:])
-        t_a = sum(e[3].elapsed_time(e[4]) for e in te[1:])
-        tt = torch.tensor([t_h2d + t_k + t_d2h, t_h2d + t_a], dtype=torch.float64, device=dev)
+        t_u = sum(e[0].elapsed_time(e[1]) for e in te[1:])
+        t_a = sum(e[1].elapsed_time(e[2]) for e in te[1:])
+        tt = torch.tensor([t_u, t_a], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tb = torch.tensor([h2d, d2h_state + d2h_res], dtype=torch.float64, device=dev)
+        tb = torch.tensor([h2d_upd, d2h_upd], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tb)
         e2e = {'value': npts_global * Ke / (tt[0].item() * 1e-3), 'unit': 'quad-point updates/s',
                'h2d_bytes_per_step': int(tb[0].item()), 'd2h_bytes_per_step': int(tb[1].item()),
-               'assembly_ms': tt[1].item() / Ke, 'steps': Ke,
-               'what': 'update_int_vars_gp with pinned-host sol+state in, new state out; assembly_ms = H2D of sol+state + '
-                       'newton_update + D2H of the residual (CSR stays on the device for the device linear solver)'}
-        del hin, hout, dsol, dstate
+               'ms_per_step': tt[0].item() / Ke, 'assembly_ms': tt[1].item() / Ke, 'steps': Ke,
+               'what': 'Plan.update_state_host: pinned-host sol + state (Fp_inv, g, slip, rot) in, new state out, chunk-'
+                       'pipelined H2D / update / D2H; assembly_ms = H2D of sol + Fp_inv, g, rot, newton_update, D2H of the '
+                       'residual (the CSR stays on the device for the device linear solver)'}
+        del hsol, hstate, hnew, hres, dsol
 
     if rank != 0:
         if world > 1:
@@ -349,7 +356,10 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline (update kernel = the metric's kernel; assembly kernel reported beside it) ---------------------
+    # ---- roofline (update kernel = the metric's kernel; assembly reported beside it) --------------------------------
+    # achieved = ALGORITHMIC flops of SURVEY 8(d) (hand-derived 9x9 form: 1.6 k + k 5.0 k per point, +15 k for the assembly)
+    # x points / CUDA-event duration; `executed` = the leaner 6x6 crystal-frame form this kernel actually runs
+    # (FP64 instructions counted on the ncu source page, profiles/r1) - DESIGN.md "Work model".
     peaks = _peaks()
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     hbm_src = 'measured (MEASURED_PEAKS.json, burst copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
@@ -359,20 +369,32 @@ def main():
     pts_rank = npts_global / world
     f_upd = F_UPDATE_FIXED + F_ITER * k_mean_u
     f_asm = F_ASSEMBLY_FIXED + F_ITER * k_mean_a
-    roof = {'bound': 'fp64', 'kernel': 'k_update_state<12>', 'achieved': pts_rank * f_upd / upd_s / 1e12, 'peak': fp64_peak,
-            'unit': 'TFLOP/s', 'frac': pts_rank * f_upd / upd_s / 1e12 / fp64_peak, 'traffic': None,
-            'peak_source': 'DFMA microbenchmark (cpfem_dfma_peak_kernel) measured in this run; B200 has no published '
-                           'measured FP64 figure in MEASURED_PEAKS.json',
-            'flops_per_point': f_upd, 'mean_local_newton_iters': k_mean_u,
+    x_upd = X_UPDATE_FIXED + X_ITER * k_mean_u
+    x_asm = X_ASSEMBLY_FIXED + X_ITER * k_mean_a
+    tf = lambda f, t: pts_rank * f / t / 1e12
+    roof = {'bound': 'fp64', 'kernel': 'k_update_state<12,119>', 'achieved': tf(f_upd, upd_s), 'peak': fp64_peak,
+            'unit': 'TFLOP/s', 'frac': tf(f_upd, upd_s) / fp64_peak,
+            'traffic': TRAFFIC_UPDATE_B_PER_POINT * pts_rank,
+            'traffic_source': 'ncu --set full at 64^3 (profiles/r1): dram read+write = 600 B/point, scaled to this launch; '
+                              'algorithmic bytes 610 B/point',
+            'peak_source': 'DFMA microbenchmark (cpfem_dfma_peak_kernel) measured in this run = 148 SMs x 64 DFMA/clk x SM clock; '
+                           'MEASURED_PEAKS.json has no FP64 entry',
+            'flops_per_point': f_upd, 'flops_model': 'SURVEY 8(d): 1.6 k + k x 5.0 k, k = mean local Newton iterations (measured)',
+            'mean_local_newton_iters': k_mean_u,
+            'executed': {'flops_per_point': x_upd, 'achieved': tf(x_upd, upd_s), 'frac': tf(x_upd, upd_s) / fp64_peak,
+                         'model': '2 x FP64 instructions/point of the 6x6 crystal-frame form: 3.0 k + k x 3.2 k '
+                                  '(ncu source page, profiles/r1); ncu sm__pipe_fp64_cycles_active = 79 % at 64^3'},
             'hbm': {'achieved': pts_rank * B_UPDATE / upd_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': pts_rank * B_UPDATE / upd_s / 1e9 / hbm_peak, 'bytes_per_point': B_UPDATE, 'peak_source': hbm_src},
-            'note': 'arithmetic intensity ~%.0f flop/B >> B200 balance (~5.7): the FP64 pipe is the bound; duration '
-                    'includes the interface exchange for the assembly figures' % (f_upd / B_UPDATE)}
-    roof_asm = {'bound': 'fp64', 'kernel': 'k_point_tangent<12,119> + k_element_tangent', 'achieved': pts_rank * f_asm / asm_s / 1e12, 'peak': fp64_peak,
-                'unit': 'TFLOP/s', 'frac': pts_rank * f_asm / asm_s / 1e12 / fp64_peak, 'traffic': None,
+            'note': 'arithmetic intensity ~%.0f flop/B >> B200 balance (~5.5): the FP64 pipe is the bound, not HBM or tensor '
+                    'cores (3x3 / 6x6 / 12-wide algebra per point)' % (f_upd / B_UPDATE)}
+    roof_asm = {'bound': 'fp64', 'kernel': 'k_point_tangent<12,119> + k_element_tangent', 'achieved': tf(f_asm, asm_s),
+                'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': tf(f_asm, asm_s) / fp64_peak, 'traffic': None,
                 'flops_per_point': f_asm, 'mean_local_newton_iters': k_mean_a,
+                'executed': {'flops_per_point': x_asm, 'achieved': tf(x_asm, asm_s), 'frac': tf(x_asm, asm_s) / fp64_peak},
                 'hbm': {'achieved': pts_rank * B_ASSEMBLY / asm_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                        'frac': pts_rank * B_ASSEMBLY / asm_s / 1e9 / hbm_peak, 'bytes_per_point': B_ASSEMBLY}}
+                        'frac': pts_rank * B_ASSEMBLY / asm_s / 1e9 / hbm_peak, 'bytes_per_point': B_ASSEMBLY},
+                'note': 'duration includes the CSR memset, both kernels and (multi-GPU) the interface exchange'}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -104,6 +104,13 @@ int cpfem_plan_info(const cpfem_plan* plan, int64_t* out);
 int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* in,
                        const cpfem_state_out* out, double dt, int64_t* status, void* stream);
 
+/* Same for the cells [cell0, cell0 + ncells) only: the state arrays of `in` / `out` hold just those ncells*8 points
+ * (chunk-local, any layout).  Lets a host-resident state stream through the device chunk by chunk (H2D copy of chunk
+ * k+1 and D2H copy of chunk k-1 overlap the update of chunk k). */
+int cpfem_update_state_cells(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* in,
+                             const cpfem_state_out* out, double dt, int64_t cell0, int64_t ncells, int64_t* status,
+                             void* stream);
+
 /* compute_residual: res (nnodes,3) is OVERWRITTEN (zeroed inside, then accumulated). */
 int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* st,
                    double dt, double* res, int64_t* status, void* stream);

@@ -48,6 +48,8 @@ SIGNATURES = {
     'cpfem_plan_info': (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
     'cpfem_update_state': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State),
                                           ctypes.POINTER(StateOut), c_dbl, c_vp, c_vp]),
+    'cpfem_update_state_cells': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State),
+                                                ctypes.POINTER(StateOut), c_dbl, c_i64, c_i64, c_vp, c_vp]),
     'cpfem_residual': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State), c_dbl, c_vp, c_vp, c_vp]),
     'cpfem_newton_update': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State), c_dbl,
                                            c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -129,6 +129,83 @@ class Plan:
                                                 float(dt), _ptr(status), _stream()), 'cpfem_update_state')
         return out
 
+    def update_state_cells(self, mat: Material, sol, params, dt, cell0, ncells, out, status=None, layout=LAYOUT_AOS):
+        """cpfem_update_state_cells: `params` / `out` hold only the points of cells [cell0, cell0+ncells)."""
+        st, ts = self._state(params, layout)
+        so = StateOut(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), layout)
+        check(_lib.lib().cpfem_update_state_cells(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st), ctypes.byref(so),
+                                                  float(dt), int(cell0), int(ncells), _ptr(status), _stream()),
+              'cpfem_update_state_cells')
+        return out
+
+    def update_state_host(self, mat: Material, sol, params, dt, out=None, status=None, chunk_cells=None):
+        """update_int_vars_gp for a HOST-resident state (reference layout, torch CPU tensors; pinned memory makes the
+        copies asynchronous): the state streams through the device in chunks of `chunk_cells` cells on three streams,
+        so that the H2D copy of chunk k+1, the update of chunk k and the D2H copy of chunk k-1 overlap (PCIe is full
+        duplex).  `out` = [Fp_inv_new, g_new, slip_new] host tensors (allocated pinned when None).  Returns `out` after
+        synchronising; the per-point material arrays of the DP-steel form (params[4:]) are streamed with the state."""
+        hs = [p if isinstance(p, torch.Tensor) else torch.as_tensor(onp.ascontiguousarray(p, dtype=onp.float64)) for p in params]
+        nc = self.nc_active
+        if any(h.is_cuda or h.dtype != torch.float64 or not h.is_contiguous() or h.shape[0] != nc for h in hs):
+            raise ValueError('update_state_host: params must be contiguous float64 CPU tensors with leading dimension nc')
+        if out is None:
+            out = [torch.empty(h.shape, dtype=torch.float64, pin_memory=True) for h in hs[:3]]
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream()
+            s_in, s_out = self._host_streams()
+            sol_d = _dev_f64(sol if isinstance(sol, torch.Tensor) else onp.asarray(sol), self.device)
+            if chunk_cells is None:                     # at least 8 chunks in flight, at most 2 Mi points each
+                chunk_cells = max(1, min(1 << 18, -(-nc // 8)))
+            cc = int(min(chunk_cells, nc))
+            nbuf = 2
+            key = (cc, tuple(tuple(h.shape[1:]) for h in hs))
+            if getattr(self, '_host_key', None) != key:
+                self._host_in = [[torch.empty((cc,) + tuple(h.shape[1:]), dtype=torch.float64, device=self.device) for h in hs]
+                                 for _ in range(nbuf)]
+                self._host_out = [[torch.empty((cc,) + tuple(h.shape[1:]), dtype=torch.float64, device=self.device) for h in hs[:3]]
+                                  for _ in range(nbuf)]
+                self._host_key = key
+            ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+            ev_cmp = [torch.cuda.Event() for _ in range(nbuf)]
+            ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+            start = torch.cuda.Event()
+            start.record(cur)
+            s_in.wait_event(start)
+            s_out.wait_event(start)
+            k = 0
+            for c0 in range(0, nc, cc):
+                n = min(cc, nc - c0)
+                b = k % nbuf
+                din = [t[:n] for t in self._host_in[b]]
+                dout = [t[:n] for t in self._host_out[b]]
+                with torch.cuda.stream(s_in):
+                    if k >= nbuf:
+                        s_in.wait_event(ev_cmp[b])            # the update that read this input buffer is done
+                    for d, h in zip(din, hs):
+                        d.copy_(h[c0:c0 + n], non_blocking=True)
+                    ev_in[b].record(s_in)
+                cur.wait_event(ev_in[b])
+                if k >= nbuf:
+                    cur.wait_event(ev_out[b])                 # the D2H copy that read this output buffer is done
+                self.update_state_cells(mat, sol_d, din, dt, c0, n, dout, status=status)
+                ev_cmp[b].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[b])
+                    for h, d in zip(out, dout):
+                        h[c0:c0 + n].copy_(d, non_blocking=True)
+                    ev_out[b].record(s_out)
+                k += 1
+            for b in range(min(k, nbuf)):
+                cur.wait_event(ev_out[b])
+            cur.synchronize()
+        return out
+
+    def _host_streams(self):
+        if getattr(self, '_s_in', None) is None:
+            self._s_in = torch.cuda.Stream(device=self.device)
+            self._s_out = torch.cuda.Stream(device=self.device)
+        return self._s_in, self._s_out
+
     def residual(self, mat: Material, sol, params, dt, res=None, status=None, layout=LAYOUT_AOS):
         with torch.cuda.device(self.device):
             st, ts = self._state(params, layout)

@@ -291,6 +291,12 @@ class CrystalPlasticityBase(Problem):
 
     # ---- models_copper.py:273-282 --------------------------------------------------------------
     def update_int_vars_gp(self, sol, params):
+        if all(isinstance(v, torch.Tensor) and not v.is_cuda for v in params):
+            # host-resident state (torch CPU tensors, ideally pinned): stream it through the device, return host tensors
+            st = self.plan.new_status()
+            new = self.plan.update_state_host(self.material, sol, list(params), self.dt, status=st)
+            self.last_status = st
+            return [new[0], new[1], new[2]] + list(params[3:])
         params = [api._dev_f64(v, self.device) for v in params]
         st = self.plan.new_status()
         new = self.plan.update_state(self.material, sol, params, self.dt, status=st)

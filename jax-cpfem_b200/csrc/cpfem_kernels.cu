@@ -515,7 +515,8 @@ template <int NS, int POWN>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
                StateView st, cpfem_state_out out, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt,
-               int64_t np, long long* status) {
+               int64_t np, int64_t cell0, long long* status) {
+    // the state arrays hold the np points of cells [cell0, cell0 + np/8); p indexes them, the mesh is indexed by cell0 + p/8
     extern __shared__ double smem[];
     int64_t p = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;
     const bool valid = p < np;
@@ -525,7 +526,7 @@ k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ poi
     CpPointParams pm;
     {
         double H[9], gN[8][3], JxW;
-        point_kinematics(cells, points, sol, p >> 3, (int)(p & 7), H, gN, JxW);
+        point_kinematics(cells, points, sol, cell0 + (p >> 3), (int)(p & 7), H, gN, JxW);
         solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
     }
     if (valid) {
@@ -999,26 +1000,34 @@ static cudaError_t allow_smem(K kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-extern "C" int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
-                                  const cpfem_state* in, const cpfem_state_out* out, double dt, int64_t* status,
-                                  void* stream_) {
+extern "C" int cpfem_update_state_cells(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                                        const cpfem_state* in, const cpfem_state_out* out, double dt, int64_t cell0,
+                                        int64_t ncells, int64_t* status, void* stream_) {
     int rc = check_common(plan, mat, in, "cpfem_update_state");
     if (rc) return rc;
     if (!sol || !out || !out->Fp_inv || !out->g || !out->slip || !in->slip)
         return set_err(-1, "cpfem_update_state: null argument");
+    if (cell0 < 0 || ncells < 1 || cell0 + ncells > plan->nc_active) return set_err(-1, "cpfem_update_state: cell range out of bounds");
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int64_t np = plan->nc_active * 8;
+    const int64_t np = ncells * 8;
     const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
     StateView v = make_view(in);
     CpMaterial m = to_mat(mat);
 #define CALL(NS, PW)                                                                                                   \
     CU_TRY(allow_smem(k_update_state<NS, PW>, point_smem<NS>()));                                                      \
     k_update_state<NS, PW><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, *out, m,   \
-                                                                         plan->slip, dt, np, (long long*)status)
+                                                                         plan->slip, dt, np, cell0, (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
+}
+
+extern "C" int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                                  const cpfem_state* in, const cpfem_state_out* out, double dt, int64_t* status,
+                                  void* stream_) {
+    if (!plan) return set_err(-1, "cpfem_update_state: null argument");
+    return cpfem_update_state_cells(plan, mat, sol, in, out, dt, 0, plan->nc_active, status, stream_);
 }
 
 extern "C" int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,

@@ -129,6 +129,23 @@ def test_soa_layout_and_transposes():
     assert (r_a - r_b).abs().max().item() < 1e-13 * r_a.abs().max().item() + 1e-12
 
 
+def test_host_streaming_state_update():
+    """Plan.update_state_host (chunk-pipelined H2D / update / D2H of a host-resident state, cpfem_update_state_cells)
+    gives the same bits as the device-resident call, for chunk sizes that do and do not divide the mesh."""
+    from cpfem_b200 import Plan
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('304steel', N=4, steps=6)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    m = _mat(mat)
+    ref = [t.cpu() for t in plan.update_state(m, sol, params, dt)]
+    host = [torch.as_tensor(np.ascontiguousarray(p)).pin_memory() for p in params]
+    for cc in (64, 24, 7, 1000):
+        st = plan.new_status()
+        new = plan.update_state_host(m, torch.as_tensor(sol), host, dt, status=st, chunk_cells=cc)
+        for a, b in zip(new, ref):
+            assert not a.is_cuda and torch.equal(a, b)
+        assert int(st[0]) == 0 and int(st[3]) > 0
+
+
 def test_csr_pattern_ragged_and_unstructured():
     """Pattern vs scipy on meshes that are not boxes: an L-shaped cell subset with a permuted node numbering."""
     from cpfem_b200 import Plan
