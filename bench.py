@@ -188,6 +188,8 @@ def main():
     if args.impl == 'reference':
         return run_reference(args)
 
+    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':      # keeps NCCL's version banner off stdout (one JSON line only)
+        os.environ['NCCL_DEBUG'] = 'WARN'
     import torch.distributed as dist
     import cpfem_b200
     from cpfem_b200 import Plan, api, make_material, synthetic, slip_systems

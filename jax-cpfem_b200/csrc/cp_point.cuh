@@ -44,6 +44,9 @@
 #endif
 
 #define CP_MAX_NS 24
+#ifndef CP_TRACE_X
+#define CP_TRACE_X(a, ax)      // test hook (tests only): observe |tau/g| of every residual evaluation
+#endif
 
 // Uniform material description.  Per-point overrides (DP steel) come through CpPointParams.
 struct CpMaterial {
@@ -61,15 +64,27 @@ struct CpMaterial {
 
 // One slip system in the crystal frame, from the normalised normal n and direction d of the slip table
 // (models_copper.py:62-69).  24 doubles = 192 bytes.
-struct CpSlipSys {
+struct
+#ifdef __CUDACC__
+    __align__(16)
+#endif
+    CpSlipSys {
     double Et[6];   // strain-like Voigt of sym(d n^T): d0n0, d1n1, d2n2, (d1n2+d2n1)/2, (d0n2+d2n0)/2, (d0n1+d1n0)/2
     double M[9];    // d n^T, row-major
-    double d[3];
+    double pad0;
+    double d[3];    // 16-byte aligned together with n: the six doubles load as three pairs
     double n[3];
-    double pad[3];
+    double pad[2];
 };
 struct CpSlip {
     CpSlipSys sys[CP_MAX_NS];
+};
+// The device keeps two copies of the table: the kernel parameter (constant bank: free operands for loops whose
+// index is uniform and known at compile time) and a shared-memory copy (for the data-dependent indices of the
+// active-set loops).  CpSlipRef carries both; on the host they are the same table.
+struct CpSlipRef {
+    const CpSlip* u;    // uniform / compile-time indices
+    const CpSlip* d;    // data-dependent indices
 };
 
 // rows of `slip6`: normal(3) direction(3), un-normalised, as in data/csv/input_slip_sys*.txt.  Returns false on a zero vector.
@@ -94,10 +109,19 @@ inline bool cp_slip_init(CpSlip* sl, const double* slip6, int ns) {
 struct CpPointParams {   // per-point values actually used at one quadrature point
     double C11, C12, C44, n_exp /* = 1/xm */;     // needed inside the local Newton solve
     double S11, S12, S44h;                        // cubic compliance: (C11+C12)/den, -C12/den, 1/(2 C44)
+    double x_lo;                                  // slip systems with |tau/g| < x_lo are inactive (see cp_x_lo)
     double h, t_sat, gss_a, r;                    // hardening law: only the state update reads them (set after the solve)
 };
-CP_HD void cp_params_elastic(CpPointParams& pm, double C11, double C12, double C44, double xm) {
+// Activity threshold of the power law: a system with |tau/g| < x_lo has |tau/g|^(n-1) < 1e-20, i.e. a slip increment
+// below 1e-24 and a Newton-matrix contribution below 1e-19 of the elastic compliance for every parameter set of the
+// reference - no effect on any double-precision result, so such systems are skipped (their dgamma and w are set to 0).
+// With rate exponent 120 fewer than 5 of the 12 FCC systems are active in an average residual evaluation.
+CP_HD double cp_x_lo(double n_exp) {
+    return (n_exp > 1.0) ? exp(-46.051701859880914 / (n_exp - 1.0)) : 0.0;     // 1e-20 ^ (1/(n-1))
+}
+CP_HD void cp_params_elastic(CpPointParams& pm, double C11, double C12, double C44, double xm, double x_lo = -1.0) {
     pm.C11 = C11; pm.C12 = C12; pm.C44 = C44; pm.n_exp = 1.0 / xm;
+    pm.x_lo = (x_lo >= 0.0) ? x_lo : cp_x_lo(pm.n_exp);
     const double iden = 1.0 / ((C11 - C12) * (C11 + 2.0 * C12));
     pm.S11 = (C11 + C12) * iden; pm.S12 = -C12 * iden; pm.S44h = 0.5 / C44;
 }
@@ -227,6 +251,29 @@ CP_HD void cp_rate_pow(const double* ax /*U, >= 0*/, double n1, double* out) {
     }
 }
 
+// union of a per-lane bit mask over the lanes of the warp that are executing together (host: one lane)
+CP_HD unsigned cp_warp_or(unsigned m) {
+#ifdef __CUDA_ARCH__
+    return __reduce_or_sync(__activemask(), m);
+#else
+    return m;
+#endif
+}
+CP_HD int cp_ffs0(unsigned m) {          // index of the lowest set bit (m != 0)
+#ifdef __CUDA_ARCH__
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+CP_HD int cp_popc(unsigned m) {
+#ifdef __CUDA_ARCH__
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One residual evaluation at s (crystal frame).  Also leaves what the next Newton matrix needs (w, Fe).
 //   tau_a  = d_a . S n_a = etilde_a . (D s)            (models_copper.py:173)
@@ -237,37 +284,65 @@ CP_HD void cp_rate_pow(const double* ax /*U, >= 0*/, double n1, double* out) {
 // returns ||r||_F over the 9 entries (:212, np.linalg.norm of the 9-vector).
 // `s_is_zero`: the caller knows s == 0 and n > 1, where every tau, dg and w vanishes (first evaluation of every solve).
 // ---------------------------------------------------------------------------------------------------
+// Two passes over the slip systems: (1) x_a = tau_a / g_a for all of them (parked in w[a]) and the set of ACTIVE
+// systems |x_a| >= x_lo, united over the warp so that control flow stays uniform; (2) the power law, w and the Lp
+// accumulation for the active ones only, U at a time (U independent multiplication chains in flight).  A lane whose
+// own |x_a| is below x_lo gets dgamma_a = w_a = 0 even when the system is processed because another lane of the warp
+// needs it, so every point's result depends on its own data only (bitwise, whatever the warp composition).
+// `mact` returns the warp's active set (what the Newton matrix and the tangent loop over), `mask` the set that was
+// processed (mact padded to a multiple of U); w[a] outside `mask` is meaningless until cp_newton zeroes it at the end.
 template <int NS, int POWN, class Arr>
-CP_HD double cp_residual(const CpSlip& sl, const CpPointParams& pm, double cdt, const double* G, const Arr& ginv,
-                         const Arr& w, const double* s, bool s_is_zero, double* r, double* Fe, double* Lp) {
+CP_HD double cp_residual(const CpSlipRef& sl, const CpPointParams& pm, double cdt, const double* G, const Arr& ginv,
+                         const Arr& w, const double* s, bool s_is_zero, double* r, double* Fe, double* Lp, unsigned& mask,
+                         unsigned& mact) {
     constexpr int U = 4;
     static_assert(NS % U == 0, "slip systems are processed four at a time");
 #pragma unroll
     for (int i = 0; i < 9; ++i) Lp[i] = 0.0;
-    if (s_is_zero) {
-#pragma unroll 1
-        for (int a = 0; a < NS; ++a) w[a] = 0.0;
-    } else {
+    mask = 0u;
+    mact = 0u;
+    if (!s_is_zero) {
         const double n1 = pm.n_exp - 1.0;
         const double cn = cdt * pm.n_exp;
         const double s3 = s[3] + s[3], s4 = s[4] + s[4], s5 = s[5] + s[5];
-#pragma unroll 1
-        for (int a0 = 0; a0 < NS; a0 += U) {
-            double x[U], ax[U], pw[U], gi[U];
+        unsigned act = 0u;
+#pragma unroll
+        for (int a = 0; a < NS; ++a) {
+            const CpSlipSys& y = sl.u->sys[a];
+            const double tau = y.Et[0] * s[0] + y.Et[1] * s[1] + y.Et[2] * s[2] + y.Et[3] * s3 + y.Et[4] * s4 + y.Et[5] * s5;
+            const double x = tau * ginv[a];
+            w[a] = x;
+            CP_TRACE_X(a, fabs(x));
+            act |= (fabs(x) >= pm.x_lo ? 1u : 0u) << a;
+        }
+        unsigned m = cp_warp_or(act);
+        mact = m;
+        // pad the set to a multiple of U with inactive systems (they are evaluated honestly: tiny values)
+        {
+            const int k = (U - (cp_popc(m) & (U - 1))) & (U - 1);
+            for (int i = 0; i < k; ++i) {
+                const unsigned z = ~m & ((NS == 32) ? 0xffffffffu : ((1u << NS) - 1u));
+                m |= z & (0u - z);
+            }
+        }
+        mask = m;
+        while (m) {
+            int a[U];
+            double x[U], ax[U], pw[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const CpSlipSys& y = sl.sys[a0 + u];
-                const double tau = y.Et[0] * s[0] + y.Et[1] * s[1] + y.Et[2] * s[2] + y.Et[3] * s3 + y.Et[4] * s4 + y.Et[5] * s5;
-                gi[u] = ginv[a0 + u];
-                x[u] = tau * gi[u];
+                a[u] = cp_ffs0(m);
+                m &= m - 1u;
+                x[u] = w[a[u]];
                 ax[u] = fabs(x[u]);
             }
             cp_rate_pow<POWN, U>(ax, n1, pw);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const CpSlipSys& y = sl.sys[a0 + u];
+                const CpSlipSys& y = sl.d->sys[a[u]];
+                if (!(ax[u] >= pm.x_lo)) pw[u] = 0.0;
                 const double dg = (cdt * pw[u]) * x[u];
-                w[a0 + u] = (cn * pw[u]) * gi[u];
+                w[a[u]] = (cn * pw[u]) * ginv[a[u]];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) Lp[i] += dg * y.M[i];
             }
@@ -302,8 +377,8 @@ CP_HD double cp_residual(const CpSlip& sl, const CpPointParams& pm, double cdt, 
 // After the call N holds L (unit lower) and U; piv[i] = 1/U_ii.
 // ---------------------------------------------------------------------------------------------------
 template <int NS, class Arr>
-CP_HD void cp_newton_matrix(const CpSlip& sl, const CpPointParams& pm, const double* G, const double* Fe,
-                            const Arr& w, double* N /*36*/, double* piv /*6*/) {
+CP_HD void cp_newton_matrix(const CpSlipRef& sl, const CpPointParams& pm, const double* G, const double* Fe,
+                            const Arr& w, unsigned mask, double* N /*36*/, double* piv /*6*/) {
     double K[9];
     m3_mul_tn(Fe, G, K);
     const double S11 = pm.S11, S12 = pm.S12, S44q = 0.5 * pm.S44h;
@@ -312,20 +387,35 @@ CP_HD void cp_newton_matrix(const CpSlip& sl, const CpPointParams& pm, const dou
     N[0] = N[7] = N[14] = S11;
     N[1] = N[2] = N[6] = N[8] = N[12] = N[13] = S12;
     N[21] = N[28] = N[35] = S44q;
-#pragma unroll 2
-    for (int a = 0; a < NS; ++a) {
-        const CpSlipSys& y = sl.sys[a];
-        const double k0 = K[0] * y.d[0] + K[1] * y.d[1] + K[2] * y.d[2];
-        const double k1 = K[3] * y.d[0] + K[4] * y.d[1] + K[5] * y.d[2];
-        const double k2 = K[6] * y.d[0] + K[7] * y.d[1] + K[8] * y.d[2];
-        const double wa = w[a], wh = 0.5 * wa;
-        double e[6];
-        e[0] = wa * (k0 * y.n[0]); e[1] = wa * (k1 * y.n[1]); e[2] = wa * (k2 * y.n[2]);
-        e[3] = wh * (k1 * y.n[2] + k2 * y.n[1]); e[4] = wh * (k0 * y.n[2] + k2 * y.n[0]); e[5] = wh * (k0 * y.n[1] + k1 * y.n[0]);
+    // only the warp's active systems contribute (w = 0 for all others); two per trip for instruction-level parallelism
+    for (unsigned m = mask; m;) {
+        int a2[2];
+        double w2[2];
+        a2[0] = cp_ffs0(m);
+        m &= m - 1u;
+        w2[0] = w[a2[0]];
+        a2[1] = a2[0];
+        w2[1] = 0.0;
+        if (m) {
+            a2[1] = cp_ffs0(m);
+            m &= m - 1u;
+            w2[1] = w[a2[1]];
+        }
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
+        for (int u = 0; u < 2; ++u) {
+            const CpSlipSys& y = sl.d->sys[a2[u]];
+            const double k0 = K[0] * y.d[0] + K[1] * y.d[1] + K[2] * y.d[2];
+            const double k1 = K[3] * y.d[0] + K[4] * y.d[1] + K[5] * y.d[2];
+            const double k2 = K[6] * y.d[0] + K[7] * y.d[1] + K[8] * y.d[2];
+            const double wa = w2[u], wh = 0.5 * wa;
+            double e[6];
+            e[0] = wa * (k0 * y.n[0]); e[1] = wa * (k1 * y.n[1]); e[2] = wa * (k2 * y.n[2]);
+            e[3] = wh * (k1 * y.n[2] + k2 * y.n[1]); e[4] = wh * (k0 * y.n[2] + k2 * y.n[0]); e[5] = wh * (k0 * y.n[1] + k1 * y.n[0]);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) N[6 * i + j] += e[i] * y.Et[j];
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) N[6 * i + j] += e[i] * y.Et[j];
+        }
     }
     // in-place LU (Doolittle), no pivoting
 #pragma unroll
@@ -382,9 +472,9 @@ struct CpSolveInfo {
 // returned s (bitwise: y + relax*inc and y + 2*(relax/2)*inc are the same number).
 // ---------------------------------------------------------------------------------------------------
 template <int NS, int POWN, class Arr>
-CP_HD void cp_newton(const CpSlip& sl, const CpPointParams& pm, double cdt, double tol, int max_sub, int max_iter,
+CP_HD void cp_newton(const CpSlipRef& sl, const CpPointParams& pm, double cdt, double tol, int max_sub, int max_iter,
                      const double* G, const Arr& ginv, const Arr& w, double* s, double* Fe, double* Lp,
-                     CpSolveInfo& info) {
+                     unsigned& mask, unsigned& mact, CpSolveInfo& info) {
     double r[6], st[6], inc[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) { s[i] = 0.0; st[i] = 0.0; inc[i] = 0.0; }
@@ -394,7 +484,7 @@ CP_HD void cp_newton(const CpSlip& sl, const CpPointParams& pm, double cdt, doub
     bool first = true;
     info.iters = 0; info.evals = 0; info.status = 0;
     for (;;) {
-        const double crtn = cp_residual<NS, POWN>(sl, pm, cdt, G, ginv, w, st, first && zero_ok, r, Fe, Lp);
+        const double crtn = cp_residual<NS, POWN>(sl, pm, cdt, G, ginv, w, st, first && zero_ok, r, Fe, Lp, mask, mact);
         ++info.evals;
         if (!first) {
             relax *= 0.5;
@@ -416,7 +506,7 @@ CP_HD void cp_newton(const CpSlip& sl, const CpPointParams& pm, double cdt, doub
             for (int i = 0; i < 6; ++i) inc[i] = -r[i];
         } else {
             double N[36], piv[6];
-            cp_newton_matrix<NS>(sl, pm, G, Fe, w, N, piv);
+            cp_newton_matrix<NS>(sl, pm, G, Fe, w, mact, N, piv);
             cp_compliance_neg(pm, r, inc);
             cp_lu_solve(N, piv, inc);
             inc[3] *= 0.5; inc[4] *= 0.5; inc[5] *= 0.5;          // inc = D^-1 z
@@ -428,6 +518,10 @@ CP_HD void cp_newton(const CpSlip& sl, const CpPointParams& pm, double cdt, doub
         for (int i = 0; i < 6; ++i) st[i] = s[i] + inc[i];
     }
     if (!(rn == rn)) info.status |= 2;
+    // systems outside the last processed set: w = 0 (the output stages read w of every system)
+#pragma unroll 4
+    for (int a = 0; a < NS; ++a)
+        if (!((mask >> a) & 1u)) w[a] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -449,6 +543,7 @@ struct CpPointState {       // everything the output stages need, crystal frame
     double G[9], Ac[9];
     double s[6], Fe[9], Lp[9];
     Arr ginv, w;            // per-slip-system arrays (1/g_old, d dgamma / d tau at the solution)
+    unsigned mask, mact;    // slip systems processed by / active in the last residual evaluation (w = 0 for all others)
     double cdt;
     CpSolveInfo info;
 };
@@ -458,7 +553,7 @@ struct CpPointState {       // everything the output stages need, crystal frame
 // need it, the Newton loop does not, so the callers fill it afterwards with cp_point_frame (the kernels reload A and
 // R from memory for that, which keeps 27 doubles out of the loop's registers).
 template <int NS, int POWN, class Arr, class GIn>
-CP_HD void cp_point_solve(const CpSlip& sl, const CpMaterial& mat, const CpPointParams& pm, double dt,
+CP_HD void cp_point_solve(const CpSlipRef& sl, const CpMaterial& mat, const CpPointParams& pm, double dt,
                           const double* H, const double* A, const GIn& g, const double* R, CpPointState<Arr>& ps) {
     {
         double F[9], Fc[9], Ac[9];
@@ -472,7 +567,8 @@ CP_HD void cp_point_solve(const CpSlip& sl, const CpMaterial& mat, const CpPoint
 #pragma unroll 4
     for (int a = 0; a < NS; ++a) ps.ginv[a] = 1.0 / g[a];
     ps.cdt = mat.ao * dt;
-    cp_newton<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp, ps.info);
+    cp_newton<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp,
+                        ps.mask, ps.mact, ps.info);
 }
 
 template <class Arr>
@@ -484,7 +580,7 @@ CP_HD void cp_point_frame(const double* A, const double* R, CpPointState<Arr>& p
 // g / slip_old are read and g_new / slip_new written through indexable accessors (global memory in the kernels);
 // ps.w is overwritten with the hardening terms t_a.
 template <int NS, class Arr, class GIn, class GOut>
-CP_HD void cp_point_state_update(const CpSlip& sl, const CpPointParams& pm, const CpPointState<Arr>& ps,
+CP_HD void cp_point_state_update(const CpSlipRef& sl, const CpPointParams& pm, const CpPointState<Arr>& ps,
                                  const GIn& g, const GIn& slip_old, const double* R,
                                  double* A_new_lab, const GOut& g_new, const GOut& slip_new) {
     {
@@ -500,7 +596,7 @@ CP_HD void cp_point_state_update(const CpSlip& sl, const CpPointParams& pm, cons
     double tsum = 0.0;
 #pragma unroll 2
     for (int a = 0; a < NS; ++a) {
-        const CpSlipSys& y = sl.sys[a];
+        const CpSlipSys& y = sl.u->sys[a];
         // dgamma_a recomputed from w_a: dg = w tau / n
         const double tau = y.Et[0] * ps.s[0] + y.Et[1] * ps.s[1] + y.Et[2] * ps.s[2] + y.Et[3] * s3 + y.Et[4] * s4 + y.Et[5] * s5;
         const double dg = ps.w[a] * tau * inv_n;
@@ -557,10 +653,10 @@ CP_HD void cp_point_stress(const CpPointState<Arr>& ps, const double* R, double*
 // `scale` multiplies the whole tangent (JxW for the element integration).
 // ---------------------------------------------------------------------------------------------------
 template <int NS, class Arr, typename OutT>
-CP_HD void cp_point_tangent(const CpSlip& sl, const CpPointParams& pm, const CpPointState<Arr>& ps,
+CP_HD void cp_point_tangent(const CpSlipRef& sl, const CpPointParams& pm, const CpPointState<Arr>& ps,
                             const CpStressAux& ax, const double* R, double scale, OutT out, long ld, long ls) {
     double N[36], piv[6];
-    cp_newton_matrix<NS>(sl, pm, ps.G, ps.Fe, ps.w, N, piv);
+    cp_newton_matrix<NS>(sl, pm, ps.G, ps.Fe, ps.w, ps.mact, N, piv);
     // constant pieces
     double S[9], Z[9], T1[9] /* S A_new^T */, T2[9] /* Fe S */, Y[9] /* (I-Lp)^-1 */, tmp[9], dY;
     sym6_to_m3(ps.s, S);
@@ -596,9 +692,9 @@ CP_HD void cp_point_tangent(const CpSlip& sl, const CpPointParams& pm, const CpP
         double dLp[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) dLp[i] = 0.0;
-#pragma unroll 4
-        for (int a = 0; a < NS; ++a) {
-            const CpSlipSys& y = sl.sys[a];
+        for (unsigned m = ps.mact; m; m &= m - 1u) {
+            const int a = cp_ffs0(m);
+            const CpSlipSys& y = sl.d->sys[a];
             const double dtau = y.Et[0] * z[0] + y.Et[1] * z[1] + y.Et[2] * z[2] + y.Et[3] * z[3] + y.Et[4] * z[4] + y.Et[5] * z[5];
             const double dgm = ps.w[a] * dtau;
 #pragma unroll

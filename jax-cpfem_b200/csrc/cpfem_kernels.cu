@@ -485,6 +485,19 @@ __device__ __forceinline__ void warp_status(const CpSolveInfo& info, bool valid,
 // Per-point kernels: one thread per quadrature point, PT_BLOCK threads per block; the two per-slip-system arrays
 // (1/g, w) of every thread are columns of a [2][NS][PT_BLOCK] shared-memory tile.
 #define PT_BLOCK 128
+// The slip-system records are read with data-dependent indices (only the active systems are processed), which the
+// constant bank serves slowly (LDC); every per-point kernel therefore starts by copying the table of its kernel
+// parameter into shared memory (4.6 kB) and reads it from there (LDS, same address in every lane = broadcast).
+__device__ __forceinline__ CpSlipRef stage_slip(const CpSlip& param, CpSlip& sh, int ns) {
+    const double* src = reinterpret_cast<const double*>(&param);
+    double* dst = reinterpret_cast<double*>(&sh);
+    for (int i = threadIdx.x; i < ns * 24; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    CpSlipRef r;
+    r.u = &param;
+    r.d = &sh;
+    return r;
+}
 #ifndef PT_MIN_BLOCKS
 #define PT_MIN_BLOCKS 3      // 3 x 128 threads x 168 registers per SM
 #endif
@@ -499,7 +512,7 @@ static constexpr size_t point_smem() { return sizeof(double) * 2 * NS * PT_BLOCK
 
 // u_grad + state -> local Newton solve.  R is reloaded by the callers after the solve (keeps it out of the loop's registers).
 template <int NS, int POWN>
-__device__ __forceinline__ void solve_point(const StateView& st, const CpMaterial& mat, const CpSlip& slip, double dt,
+__device__ __forceinline__ void solve_point(const StateView& st, const CpMaterial& mat, const CpSlipRef& slip, double dt,
                                             int64_t p, int64_t np, const double* H, CpPointParams& pm, CpPointState<SArr>& ps) {
     double A[9], R[9];
     load9(st.Fp_inv, st.soa, p, np, A);
@@ -518,6 +531,8 @@ k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ poi
                int64_t np, int64_t cell0, long long* status) {
     // the state arrays hold the np points of cells [cell0, cell0 + np/8); p indexes them, the mesh is indexed by cell0 + p/8
     extern __shared__ double smem[];
+    __shared__ CpSlip s_slip;
+    const CpSlipRef slp = stage_slip(slip, s_slip, NS);
     int64_t p = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;
     const bool valid = p < np;
     if (!valid) p = np - 1;
@@ -527,14 +542,14 @@ k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ poi
     {
         double H[9], gN[8][3], JxW;
         point_kinematics(cells, points, sol, cell0 + (p >> 3), (int)(p & 7), H, gN, JxW);
-        solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
+        solve_point<NS, POWN>(st, mat, slp, dt, p, np, H, pm, ps);
     }
     if (valid) {
         const int so = (out.layout == CPFEM_LAYOUT_SOA);
         double R[9], An[9];
         point_frame(st, p, np, R, ps);
         load_point_params_hard(mat, st, p, pm);
-        cp_point_state_update<NS>(slip, pm, ps, gin(st.g, st.soa, p, NS, np), gin(st.slip, st.soa, p, NS, np), R, An,
+        cp_point_state_update<NS>(slp, pm, ps, gin(st.g, st.soa, p, NS, np), gin(st.slip, st.soa, p, NS, np), R, An,
                                   gout(out.g, so, p, NS, np), gout(out.slip, so, p, NS, np));
         const GOut Ao = gout(out.Fp_inv, so, p, 9, np);
 #pragma unroll
@@ -560,6 +575,8 @@ k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points,
            StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t nc,
            double* __restrict__ res, long long* status) {
     extern __shared__ double smem[];
+    __shared__ CpSlip s_slip;
+    const CpSlipRef slp = stage_slip(slip, s_slip, NS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* GN = smem + 2 * NS * PT_BLOCK + (size_t)warp * 4 * (GN_CELL + PJ_CELL);
     double* PJ = GN + 4 * GN_CELL;
@@ -582,7 +599,7 @@ k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points,
             for (int a = 0; a < 8; ++a)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) gq[a * 3 + i] = gN[a][i];
-            solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
+            solve_point<NS, POWN>(st, mat, slp, dt, p, np, H, pm, ps);
         }
         double R[9], P[9];
         point_frame(st, p, np, R, ps);
@@ -625,6 +642,8 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
                 StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np, int64_t p0,
                 int64_t npc, double* __restrict__ PJ, double* __restrict__ TA, long long* status) {
     extern __shared__ double smem[];
+    __shared__ CpSlip s_slip;
+    const CpSlipRef slp = stage_slip(slip, s_slip, NS);
     const int64_t pl = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;      // point within the chunk
     const bool valid = pl < npc;
     const int64_t p = p0 + (valid ? pl : npc - 1);
@@ -635,7 +654,7 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
     {
         double H[9], gN[8][3];
         point_kinematics(cells, points, sol, p >> 3, (int)(p & 7), H, gN, JxW);
-        solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
+        solve_point<NS, POWN>(st, mat, slp, dt, p, np, H, pm, ps);
     }
     double R[9], P[9];
     point_frame(st, p, np, R, ps);
@@ -644,7 +663,7 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
     if (valid) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) PJ[i * npc + pl] = P[i] * JxW;
-        cp_point_tangent<NS>(slip, pm, ps, ax, R, JxW, TA + pl, 9 * npc, npc);
+        cp_point_tangent<NS>(slp, pm, ps, ax, R, JxW, TA + pl, 9 * npc, npc);
     }
     warp_status(ps.info, valid, status);
 }
@@ -822,6 +841,8 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
              StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np,
              double* __restrict__ sigma_cell, long long* status) {
     extern __shared__ double smem[];
+    __shared__ CpSlip s_slip;
+    const CpSlipRef slp = stage_slip(slip, s_slip, NS);
     int64_t p = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;
     const bool valid = p < np;
     if (!valid) p = np - 1;
@@ -834,7 +855,7 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
     {
         double gN[8][3];
         point_kinematics(cells, points, sol, c, q, F, gN, JxW);
-        solve_point<NS, POWN>(st, mat, slip, dt, p, np, F, pm, ps);
+        solve_point<NS, POWN>(st, mat, slp, dt, p, np, F, pm, ps);
     }
     double R[9], P[9], sg[9];
     point_frame(st, p, np, R, ps);
@@ -869,6 +890,8 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip,
              double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, long long* status) {
     extern __shared__ double smem[];
+    __shared__ CpSlip s_slip;
+    const CpSlipRef slp = stage_slip(slip, s_slip, NS);
     int64_t p = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;
     const bool valid = p < np;
     if (!valid) p = np - 1;
@@ -879,7 +902,7 @@ k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, c
         double H[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) H[i] = u_grads[p * 9 + i];
-        solve_point<NS, POWN>(st, mat, slip, dt, p, np, H, pm, ps);
+        solve_point<NS, POWN>(st, mat, slp, dt, p, np, H, pm, ps);
     }
     double R[9], P[9];
     point_frame(st, p, np, R, ps);
@@ -888,7 +911,7 @@ k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, c
     if (valid) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) Pout[p * 9 + i] = P[i];
-        if (Aout) cp_point_tangent<NS>(slip, pm, ps, ax, R, 1.0, Aout + p * 81, 9, 1);
+        if (Aout) cp_point_tangent<NS>(slp, pm, ps, ax, R, 1.0, Aout + p * 81, 9, 1);
     }
     warp_status(ps.info, valid, status);
 }

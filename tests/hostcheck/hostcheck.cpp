@@ -13,8 +13,9 @@ template <int NS, int POWN>
 static void run(const double* slip6, const CpMaterial* mat, double dt, int64_t np, const double* H, const double* A,
                 const double* g, const double* slip_old, const double* R, const double* pp /* np x 8 or null */,
                 double* P, double* tangent, double* A_new, double* g_new, double* slip_new, int32_t* iters) {
-    CpSlip sl;
-    cp_slip_init(&sl, slip6, NS);
+    CpSlip table;
+    cp_slip_init(&table, slip6, NS);
+    const CpSlipRef sl = {&table, &table};
     for (int64_t p = 0; p < np; ++p) {
         CpPointParams pm;
         if (pp) {
