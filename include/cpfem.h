@@ -16,6 +16,7 @@
  *   cpfem_newton_update                  Problem.newton_update -> res, V        (solver.py:392,281)
  *                                        + get_A's CSR data                     (solver.py:281)
  *   cpfem_avg_stress                     CrystalPlasticity.compute_avg_stress   (models_copper.py:297-319)
+ *   cpfem_update_state_avg_stress        the two calls above fused (driver order singlecrystal_copper.py:205,227)
  *   cpfem_point_stress_tangent           get_tensor_map()'s tensor_map under vmap, and its jacfwd
  *                                        (models_copper.py:135-137,155-162,251-265)
  *   cpfem_apply_dirichlet                apply_bc_vec + zeroRows                (solver.py:119-133,290-293)
@@ -110,6 +111,14 @@ int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* mat, const 
 int cpfem_update_state_cells(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* in,
                              const cpfem_state_out* out, double dt, int64_t cell0, int64_t ncells, int64_t* status,
                              void* stream);
+
+/* update_int_vars_gp fused with compute_avg_stress (models_copper.py:273-282 + 297-319): the reference drivers call
+ * compute_avg_stress(sol, params) and then update_int_vars_gp(sol, params) with the same arguments
+ * (singlecrystal_copper.py:205,227), i.e. the same converged local solve twice; this entry point does it once and
+ * writes both the new state and sigma_cell (nc, 9). */
+int cpfem_update_state_avg_stress(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                                  const cpfem_state* in, const cpfem_state_out* out, double dt, double* sigma_cell,
+                                  int64_t* status, void* stream);
 
 /* compute_residual: res (nnodes,3) is OVERWRITTEN (zeroed inside, then accumulated). */
 int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* st,

@@ -50,6 +50,8 @@ SIGNATURES = {
                                           ctypes.POINTER(StateOut), c_dbl, c_vp, c_vp]),
     'cpfem_update_state_cells': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State),
                                                 ctypes.POINTER(StateOut), c_dbl, c_i64, c_i64, c_vp, c_vp]),
+    'cpfem_update_state_avg_stress': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State),
+                                                     ctypes.POINTER(StateOut), c_dbl, c_vp, c_vp, c_vp]),
     'cpfem_residual': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State), c_dbl, c_vp, c_vp, c_vp]),
     'cpfem_newton_update': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State), c_dbl,
                                            c_vp, c_vp, c_vp, c_vp, c_vp]),

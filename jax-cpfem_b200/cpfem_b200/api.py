@@ -129,6 +129,22 @@ class Plan:
                                                 float(dt), _ptr(status), _stream()), 'cpfem_update_state')
         return out
 
+    def update_state_avg_stress(self, mat: Material, sol, params, dt, out=None, sigma=None, status=None, layout=LAYOUT_AOS):
+        """cpfem_update_state_avg_stress: update_int_vars_gp and compute_avg_stress from ONE local solve per point.
+        Returns ((Fp_inv_new, g_new, slip_new), sigma_cell (nc, 3, 3))."""
+        with torch.cuda.device(self.device):
+            st, ts = self._state(params, layout)
+            sol = _dev_f64(sol, self.device)
+            if out is None:
+                out = [torch.empty_like(ts[0]), torch.empty_like(ts[1]), torch.empty_like(ts[2])]
+            if sigma is None:
+                sigma = torch.empty(self.nc_active, 3, 3, dtype=torch.float64, device=self.device)
+            so = StateOut(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), layout)
+            check(_lib.lib().cpfem_update_state_avg_stress(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st),
+                                                           ctypes.byref(so), float(dt), _ptr(sigma), _ptr(status), _stream()),
+                  'cpfem_update_state_avg_stress')
+        return out, sigma
+
     def update_state_cells(self, mat: Material, sol, params, dt, cell0, ncells, out, status=None, layout=LAYOUT_AOS):
         """cpfem_update_state_cells: `params` / `out` hold only the points of cells [cell0, cell0+ncells)."""
         st, ts = self._state(params, layout)

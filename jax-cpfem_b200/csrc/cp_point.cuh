@@ -617,108 +617,172 @@ CP_HD void cp_point_state_update(const CpSlipRef& sl, const CpPointParams& pm, c
     }
 }
 
-// First Piola-Kirchhoff stress (lab): P = Fe S A_new^T / det A_new  (== det F sigma F^-T, :160-161).
-// Also returns the crystal-frame pieces the tangent needs.
+// First Piola-Kirchhoff stress (lab): P = Fe S A_new^T / det A_new  (== det F sigma F^-T, :160-161), computed as
+// P = (R Fe) S (R A_new)^T / det A_new so that the two mixed-frame matrices the tangent needs come for free.
 struct CpStressAux {
-    double Anc[9];     // A_new crystal
+    double RFe[9];     // R Fe     (lab row, crystal column)
+    double RAn[9];     // R A_new  (lab row, crystal column)
     double idet;       // 1/det(A_new)
-    double Pc[9];      // P crystal
 };
 
 template <class Arr>
 CP_HD void cp_point_stress(const CpPointState<Arr>& ps, const double* R, double* P_lab, CpStressAux& ax) {
-    double ImL[9], S[9];
+    {
+        double ImL[9], Anc[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) ImL[i] = -ps.Lp[i];
-    ImL[0] += 1.0; ImL[4] += 1.0; ImL[8] += 1.0;
-    m3_mul(ps.Ac, ImL, ax.Anc);
-    ax.idet = 1.0 / m3_det(ax.Anc);
+        for (int i = 0; i < 9; ++i) ImL[i] = -ps.Lp[i];
+        ImL[0] += 1.0; ImL[4] += 1.0; ImL[8] += 1.0;
+        m3_mul(ps.Ac, ImL, Anc);
+        ax.idet = 1.0 / m3_det(Anc);
+        m3_mul(R, Anc, ax.RAn);
+    }
+    m3_mul(R, ps.Fe, ax.RFe);
+    double S[9], T[9];
     sym6_to_m3(ps.s, S);
-    double T[9], T2[9];
-    m3_mul(ps.Fe, S, T);
-    m3_mul_nt(T, ax.Anc, T2);
+    m3_mul(ax.RFe, S, T);
+    m3_mul_nt(T, ax.RAn, P_lab);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) ax.Pc[i] = T2[i] * ax.idet;
-    cp_to_lab(R, ax.Pc, P_lab);
+    for (int i = 0; i < 9; ++i) P_lab[i] *= ax.idet;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Consistent tangent dP_ij/dH_kl in the lab frame, out[(3i+j)*ld + (3k+l)*ls].
-//   ds/dF   = -J^-1 dr/dF   (f_jvp, models_copper.py:251-259),  dr/dF[dF] = -C : sym(Fe^T dF A_new)
-//   dP      = dF Z + [ dFe S A_new^T + Fe dS A_new^T + Fe S dA_new^T ] / det - P tr(A_new^-1 dA_new)
-//   with dLp = sum_a w_a (p_a . ds) d_a n_a^T,  dA_new = -Ac dLp,  dFe = -G dLp,
-//        tr(A_new^-1 dA_new) = -tr((I-Lp)^-1 dLp),  Z = A_new S A_new^T / det.
-// The loop runs over LAB directions dF = e_k e_l^T, i.e. crystal dF_c = (R^T e_k)(R^T e_l)^T, and rotates each
-// dP_c column back with R, which is cheaper than rotating the rank-4 tensor.
-// `scale` multiplies the whole tangent (JxW for the element integration).
+// Consistent tangent dP_ij/dH_kl in the lab frame (times `scale`: JxW for the element integration).  Reproduces jacfwd through the local solve (f_jvp, models_copper.py:251-259):
+//   ds/dF = -J^-1 dr/dF,  dr/dF[dF] = -C : sym(Fe^T dF A_new)   =>   z = D ds = N^-1 b,  b = voigt(sym(u_k v_l^T)),
+//   u_k = row k of R Fe, v_l = row l of R A_new   (direction dF = e_k e_l^T in the lab frame),
+//   dP = dF Z + [ dFe S A_new^T + Fe dS A_new^T + Fe S dA_new^T ] / det - P tr(A_new^-1 dA_new),
+//   dLp = sum_a w_a (etilde_a . z) d_a n_a^T,  dA_new = -Ac dLp,  dFe = -G dLp,  Z = A_new S A_new^T / det.
+// Everything after z is linear in z, so   dP_ij(kl) = delta_ik Zlab_lj + W_ij . z(kl)   with the 9 x 6 matrix
+//   W_ij,m = [ (R Fe) E_m (R A_new)^T ]_ij / det + sum_a w_a etilde_a[m] Q_a,ij        (E_m: unit dS of z_m)
+//   Q_a    = -[ (RFe Y d_a)(RAn S n_a)^T + (RFe S n_a)(RAn Y d_a)^T ] / det + P (n_a . Y d_a),   Y = (I - Lp)^-1
+// (G = Fe Y, Ac = A_new Y; every slip system enters through four 3-vectors because M_a = d_a n_a^T has rank one), and
+//   W_ij . N^-1 b(kl) = (N^-T W_ij) . b(kl) = [ (R Fe) X_ij (R A_new)^T ]_kl,   X_ij = symmetric 3x3 of y = N^-T W_ij,
+// i.e. nine transposed 6x6 solves and nine pairs of 3x3 products replace the nine solve + push-forward passes of the
+// direct form.  The work is done one row i of P at a time (18 accumulators), and the LU factors of N are parked in
+// `park` (CP_TANGENT_PARK doubles: shared memory in the kernels) while the slip loop runs, so the routine needs no
+// local-memory spills.
 // ---------------------------------------------------------------------------------------------------
-template <int NS, class Arr, typename OutT>
-CP_HD void cp_point_tangent(const CpSlipRef& sl, const CpPointParams& pm, const CpPointState<Arr>& ps,
-                            const CpStressAux& ax, const double* R, double scale, OutT out, long ld, long ls) {
+#define CP_TANGENT_PARK 42
+CP_HD double cp_sel3(int i, double a0, double a1, double a2) { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
+// Step 1 (call right after the local solve, before the stress: G and the matrix die before R Fe, R A_new, P are born):
+// Newton matrix at the converged state, LU-factorised, parked.
+template <int NS, class Arr, class Park>
+CP_HD void cp_point_tangent_factor(const CpSlipRef& sl, const CpPointParams& pm, const CpPointState<Arr>& ps, const Park& park) {
     double N[36], piv[6];
     cp_newton_matrix<NS>(sl, pm, ps.G, ps.Fe, ps.w, ps.mact, N, piv);
-    // constant pieces
-    double S[9], Z[9], T1[9] /* S A_new^T */, T2[9] /* Fe S */, Y[9] /* (I-Lp)^-1 */, tmp[9], dY;
-    sym6_to_m3(ps.s, S);
-    m3_mul_nt(S, ax.Anc, T1);
-    m3_mul(ax.Anc, T1, Z);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Z[i] *= ax.idet;
-    m3_mul(ps.Fe, S, T2);
+    for (int i = 0; i < 36; ++i) park[i] = N[i];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) tmp[i] = -ps.Lp[i];
-    tmp[0] += 1.0; tmp[4] += 1.0; tmp[8] += 1.0;
-    m3_inv(tmp, Y, &dY);
-    // U_k = Fe^T R^T e_k  -> rows of (R Fe) ; V_l = A_new^T-contracted: row l of (R A_new)
-    double RFe[9], RAn[9], RZ[9];
-    m3_mul(R, ps.Fe, RFe);      // RFe[k][:] = sum_c R[k][c] Fe[c][:]   (= Fe^T r_k as a row)
-    m3_mul(R, ax.Anc, RAn);     // RAn[l][:] = sum_c R[l][c] A_new[c][:]
-    m3_mul(R, Z, RZ);           // RZ[l][:]  = sum_c R[l][c] Z[c][:]
+    for (int i = 0; i < 6; ++i) park[36 + i] = piv[i];
+}
+// Step 2 (after cp_point_stress): the tangent itself.
+// `store(ij, kl, v)` receives dP_ij/dH_kl * scale (the kernels pass a streaming global store, the host check an array).
+template <int NS, class Arr, class Park, class Store>
+CP_HD void cp_point_tangent(const CpSlipRef& sl, const CpPointState<Arr>& ps, const CpStressAux& ax, const double* P_lab,
+                            double scale, const Park& park, const Store& store) {
+    double Y[9], Zl[9];
+    {
+        double tmp[9], dY;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) tmp[i] = -ps.Lp[i];
+        tmp[0] += 1.0; tmp[4] += 1.0; tmp[8] += 1.0;
+        m3_inv(tmp, Y, &dY);
+        double S[9], T[9];
+        sym6_to_m3(ps.s, S);
+        m3_mul_nt(S, ax.RAn, T);
+        m3_mul(ax.RAn, T, Zl);              // R Z R^T = (R A_new) S (R A_new)^T / det
+        const double zs = ax.idet * scale;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Zl[i] *= zs;
+    }
+    const double* s = ps.s;
+    const double idet = ax.idet;
 #pragma unroll 1
-    for (int kl = 0; kl < 9; ++kl) {
-        const int k = kl / 3, l = kl - 3 * k;
-        const double* u = &RFe[3 * k];     // Fe^T r_k
-        const double* v = &RAn[3 * l];     // (r_l^T A_new)
-        // z = N^-1 voigt(sym(u v^T))
-        double z[6];
-        z[0] = u[0] * v[0]; z[1] = u[1] * v[1]; z[2] = u[2] * v[2];
-        z[3] = 0.5 * (u[1] * v[2] + u[2] * v[1]); z[4] = 0.5 * (u[0] * v[2] + u[2] * v[0]); z[5] = 0.5 * (u[0] * v[1] + u[1] * v[0]);
-        cp_lu_solve(N, piv, z);
-        // ds = D^-1 z ; dS full
-        double dS[9];
-        dS[0] = z[0]; dS[4] = z[1]; dS[8] = z[2];
-        dS[5] = dS[7] = 0.5 * z[3]; dS[2] = dS[6] = 0.5 * z[4]; dS[1] = dS[3] = 0.5 * z[5];
-        // dLp = sum_a w_a (etilde_a . z) d_a n_a^T      (p_a . ds == etilde_a . z)
-        double dLp[9];
+    for (int i = 0; i < 3; ++i) {
+        double W[3][6];
+        // row i of R Fe and of P, picked with selects (a dynamic index would push the arrays into local memory)
+        const double ui0 = cp_sel3(i, ax.RFe[0], ax.RFe[3], ax.RFe[6]), ui1 = cp_sel3(i, ax.RFe[1], ax.RFe[4], ax.RFe[7]),
+                     ui2 = cp_sel3(i, ax.RFe[2], ax.RFe[5], ax.RFe[8]);
+        const double Pi[3] = {cp_sel3(i, P_lab[0], P_lab[3], P_lab[6]), cp_sel3(i, P_lab[1], P_lab[4], P_lab[7]),
+                              cp_sel3(i, P_lab[2], P_lab[5], P_lab[8])};
+        {   // elastic part: [ RFe E_m RAn^T ]_ij / det
+            const double f0 = idet * ui0, f1 = idet * ui1, f2 = idet * ui2;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) dLp[i] = 0.0;
-        for (unsigned m = ps.mact; m; m &= m - 1u) {
+            for (int j = 0; j < 3; ++j) {
+                const double v0 = ax.RAn[3 * j], v1 = ax.RAn[3 * j + 1], v2 = ax.RAn[3 * j + 2];
+                W[j][0] = f0 * v0; W[j][1] = f1 * v1; W[j][2] = f2 * v2;
+                W[j][3] = 0.5 * (f1 * v2 + f2 * v1); W[j][4] = 0.5 * (f0 * v2 + f2 * v0); W[j][5] = 0.5 * (f0 * v1 + f1 * v0);
+            }
+        }
+        for (unsigned m = ps.mact; m; m &= m - 1u) {        // slip part: sum_a w_a etilde_a[m] Q_a,ij
             const int a = cp_ffs0(m);
             const CpSlipSys& y = sl.d->sys[a];
-            const double dtau = y.Et[0] * z[0] + y.Et[1] * z[1] + y.Et[2] * z[2] + y.Et[3] * z[3] + y.Et[4] * z[4] + y.Et[5] * z[5];
-            const double dgm = ps.w[a] * dtau;
+            const double d0 = y.d[0], d1 = y.d[1], d2 = y.d[2], n0 = y.n[0], n1 = y.n[1], n2 = y.n[2];
+            const double yd0 = Y[0] * d0 + Y[1] * d1 + Y[2] * d2, yd1 = Y[3] * d0 + Y[4] * d1 + Y[5] * d2,
+                         yd2 = Y[6] * d0 + Y[7] * d1 + Y[8] * d2;
+            const double sn0 = s[0] * n0 + s[5] * n1 + s[4] * n2, sn1 = s[5] * n0 + s[1] * n1 + s[3] * n2,
+                         sn2 = s[4] * n0 + s[3] * n1 + s[2] * n2;
+            const double c = n0 * yd0 + n1 * yd1 + n2 * yd2;
+            const double gd = -idet * (ui0 * yd0 + ui1 * yd1 + ui2 * yd2);
+            const double t2 = -idet * (ui0 * sn0 + ui1 * sn1 + ui2 * sn2);
+            double q[3];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) dLp[i] += dgm * y.M[i];
+            for (int j = 0; j < 3; ++j) {
+                const double v0 = ax.RAn[3 * j], v1 = ax.RAn[3 * j + 1], v2 = ax.RAn[3 * j + 2];
+                q[j] = gd * (v0 * sn0 + v1 * sn1 + v2 * sn2) + t2 * (v0 * yd0 + v1 * yd1 + v2 * yd2) + Pi[j] * c;
+            }
+            const double wa = ps.w[a];
+#pragma unroll
+            for (int mm = 0; mm < 6; ++mm) {
+                const double cf = wa * y.Et[mm];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) W[j][mm] += cf * q[j];
+            }
         }
-        // dPc = r_k (r_l^T Z)  +  [ -(G dLp) T1 + Fe dS A_new^T - T2 (Ac dLp)^T ] idet + Pc tr(Y dLp)
-        double GdL[9], AdL[9], M1[9], M2[9], M3[9], dPc[9];
-        m3_mul(ps.G, dLp, GdL);
-        m3_mul(GdL, T1, M1);
-        m3_mul(ps.Fe, dS, tmp);
-        m3_mul_nt(tmp, ax.Anc, M2);
-        m3_mul(ps.Ac, dLp, AdL);
-        m3_mul_nt(T2, AdL, M3);
-        const double tr = Y[0] * dLp[0] + Y[1] * dLp[3] + Y[2] * dLp[6] + Y[3] * dLp[1] + Y[4] * dLp[4] + Y[5] * dLp[7] +
-                          Y[6] * dLp[2] + Y[7] * dLp[5] + Y[8] * dLp[8];
+        // y_j = N^-T W_j for the three j at once (N = L U parked; every entry is read once per row i):
+        //   U^T t = w (forward substitution),  L^T y = t (backward, unit diagonal)
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int r = 0; r < 6; ++r) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
-                dPc[3 * i + j] = R[3 * k + i] * RZ[3 * l + j] + (M2[3 * i + j] - M1[3 * i + j] - M3[3 * i + j]) * ax.idet +
-                                 ax.Pc[3 * i + j] * tr;
-        double dP[9];
-        cp_to_lab(R, dPc, dP);
+            for (int k = 0; k < r; ++k) {
+                const double u = park[6 * k + r];
 #pragma unroll
-        for (int ij = 0; ij < 9; ++ij) out[ij * ld + kl * ls] = dP[ij] * scale;
+                for (int j = 0; j < 3; ++j) W[j][r] -= u * W[j][k];
+            }
+            const double ip = park[36 + r];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) W[j][r] *= ip;
+        }
+#pragma unroll
+        for (int r = 4; r >= 0; --r) {
+#pragma unroll
+            for (int k = r + 1; k < 6; ++k) {
+                const double l = park[6 * k + r];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) W[j][r] -= l * W[j][k];
+            }
+        }
+        // dP_ij(kl) = scale [ RFe X_ij RAn^T ]_kl + delta_ik scale Zlab_lj,  X = sym3(y): shear entries carry the 1/2 of b
+        const double hs = 0.5 * scale;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double x00 = W[j][0] * scale, x11 = W[j][1] * scale, x22 = W[j][2] * scale;
+            const double x12 = W[j][3] * hs, x02 = W[j][4] * hs, x01 = W[j][5] * hs;
+            double T[9];                 // T[p][l] = sum_q X[p][q] RAn[l][q]
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                const double v0 = ax.RAn[3 * l], v1 = ax.RAn[3 * l + 1], v2 = ax.RAn[3 * l + 2];
+                T[l] = x00 * v0 + x01 * v1 + x02 * v2;
+                T[3 + l] = x01 * v0 + x11 * v1 + x12 * v2;
+                T[6 + l] = x02 * v0 + x12 * v1 + x22 * v2;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    double v = ax.RFe[3 * k] * T[l] + ax.RFe[3 * k + 1] * T[3 + l] + ax.RFe[3 * k + 2] * T[6 + l];
+                    if (k == i) v += Zl[3 * l + j];
+                    store(3 * i + j, 3 * k + l, v);
+                }
+        }
     }
 }

@@ -80,6 +80,10 @@ struct cpfem_plan {
 #define CPFEM_CHUNK_CELLS (1 << 19)   // 4 Mi points per assembly chunk: 3.0 GB of scratch
 #endif
 
+// Row pitch (in doubles) of the component-major assembly scratch: the points of a chunk rounded up to a 256-byte row,
+// plus an odd number of rows' worth of padding so that the 90 component rows do not sit a power of two apart.
+static inline int64_t scratch_pitch(int64_t chunk_cells) { return ((chunk_cells * 8 + 31) / 32) * 32 + 73 * 32; }
+
 __global__ void k_count_valence(const int32_t* __restrict__ cells, int64_t n, int64_t nn, int64_t* cnt, int* err) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -260,8 +264,8 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
         else p->chunk_cells = nc < CPFEM_CHUNK_CELLS ? nc : CPFEM_CHUNK_CELLS;
         {
             const bool two = p->chunk_cells < nc;
-            PLAN_TRY(dev_alloc(&p->scratch[0], (size_t)90 * 8 * p->chunk_cells));
-            if (two && CPFEM_OVERLAP) PLAN_TRY(dev_alloc(&p->scratch[1], (size_t)90 * 8 * p->chunk_cells));
+            PLAN_TRY(dev_alloc(&p->scratch[0], (size_t)90 * scratch_pitch(p->chunk_cells)));
+            if (two && CPFEM_OVERLAP) PLAN_TRY(dev_alloc(&p->scratch[1], (size_t)90 * scratch_pitch(p->chunk_cells)));
             int lo = 0, hi = 0;
             PLAN_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
             PLAN_TRY(cudaStreamCreateWithPriority(&p->elem_stream, cudaStreamNonBlocking, hi));
@@ -502,13 +506,19 @@ __device__ __forceinline__ CpSlipRef stage_slip(const CpSlip& param, CpSlip& sh,
 #define PT_MIN_BLOCKS 3      // 3 x 128 threads x 168 registers per SM
 #endif
 typedef CpArr<PT_BLOCK> SArr;
+// layout: [w: NS][1/g: NS][tangent kernels only: CP_TANGENT_PARK - NS more rows] x PT_BLOCK columns.  1/g is dead once the
+// local solve has returned, so the tangent parks the LU factors of its Newton matrix in the 1/g rows + the extra rows.
 template <int NS>
 __device__ __forceinline__ void point_arrays(double* smem, CpPointState<SArr>& ps) {
-    ps.ginv.p = smem + threadIdx.x;
-    ps.w.p = smem + NS * PT_BLOCK + threadIdx.x;
+    ps.w.p = smem + threadIdx.x;
+    ps.ginv.p = smem + NS * PT_BLOCK + threadIdx.x;
 }
 template <int NS>
 static constexpr size_t point_smem() { return sizeof(double) * 2 * NS * PT_BLOCK; }
+template <int NS>
+static constexpr size_t update_smem() { return sizeof(double) * (2 * NS + 10) * PT_BLOCK; }   // + u_grad, JxW rows (fused avg stress)
+template <int NS>
+static constexpr size_t tangent_smem() { return sizeof(double) * (NS + (NS > CP_TANGENT_PARK ? NS : CP_TANGENT_PARK)) * PT_BLOCK; }
 
 // u_grad + state -> local Newton solve.  R is reloaded by the callers after the solve (keeps it out of the loop's registers).
 template <int NS, int POWN>
@@ -528,7 +538,7 @@ template <int NS, int POWN>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
                StateView st, cpfem_state_out out, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt,
-               int64_t np, int64_t cell0, long long* status) {
+               int64_t np, int64_t cell0, double* __restrict__ sigma_cell, long long* status) {
     // the state arrays hold the np points of cells [cell0, cell0 + np/8); p indexes them, the mesh is indexed by cell0 + p/8
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
@@ -539,15 +549,50 @@ k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ poi
     CpPointState<SArr> ps;
     point_arrays<NS>(smem, ps);
     CpPointParams pm;
+    // fused compute_avg_stress (sigma_cell != nullptr): u_grad and JxW of the point wait in 10 more shared-memory rows
+    double* hs = smem + 2 * NS * PT_BLOCK + threadIdx.x;
     {
         double H[9], gN[8][3], JxW;
         point_kinematics(cells, points, sol, cell0 + (p >> 3), (int)(p & 7), H, gN, JxW);
+        if (sigma_cell) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) hs[i * PT_BLOCK] = H[i];
+            hs[9 * PT_BLOCK] = JxW;
+        }
         solve_point<NS, POWN>(st, mat, slp, dt, p, np, H, pm, ps);
+    }
+    double R[9];
+    point_frame(st, p, np, R, ps);
+    if (sigma_cell) {
+        // models_copper.py:297-319 on the converged solve of this pass: sigma = P F^T / det F, JxW-weighted cell mean
+        double P[9], F[9], sg[9];
+        {
+            CpStressAux ax;
+            cp_point_stress(ps, R, P, ax);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) F[i] = hs[i * PT_BLOCK];
+        F[0] += 1.0; F[4] += 1.0; F[8] += 1.0;
+        double wsum = hs[9 * PT_BLOCK];
+        m3_mul_nt(P, F, sg);
+        const double sc = wsum / m3_det(F);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sg[i] *= sc;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sg[i] += __shfl_xor_sync(0xffffffffu, sg[i], o);
+            wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        }
+        if (valid && (p & 7) == 0) {
+            const double iw = 1.0 / wsum;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sigma_cell[(p >> 3) * 9 + i] = sg[i] * iw;
+        }
     }
     if (valid) {
         const int so = (out.layout == CPFEM_LAYOUT_SOA);
-        double R[9], An[9];
-        point_frame(st, p, np, R, ps);
+        double An[9];
         load_point_params_hard(mat, st, p, pm);
         cp_point_state_update<NS>(slp, pm, ps, gin(st.g, st.soa, p, NS, np), gin(st.slip, st.soa, p, NS, np), R, An,
                                   gout(out.g, so, p, NS, np), gout(out.slip, so, p, NS, np));
@@ -640,7 +685,7 @@ template <int NS, int POWN>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
                 StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np, int64_t p0,
-                int64_t npc, double* __restrict__ PJ, double* __restrict__ TA, long long* status) {
+                int64_t npc, int64_t pitch, double* __restrict__ PJ, double* __restrict__ TA, long long* status) {
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
     const CpSlipRef slp = stage_slip(slip, s_slip, NS);
@@ -656,14 +701,16 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
         point_kinematics(cells, points, sol, p >> 3, (int)(p & 7), H, gN, JxW);
         solve_point<NS, POWN>(st, mat, slp, dt, p, np, H, pm, ps);
     }
+    cp_point_tangent_factor<NS>(slp, pm, ps, ps.ginv);
     double R[9], P[9];
     point_frame(st, p, np, R, ps);
     CpStressAux ax;
     cp_point_stress(ps, R, P, ax);
     if (valid) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) PJ[i * npc + pl] = P[i] * JxW;
-        cp_point_tangent<NS>(slp, pm, ps, ax, R, JxW, TA + pl, 9 * npc, npc);
+        for (int i = 0; i < 9; ++i) __stcs(PJ + i * pitch + pl, P[i] * JxW);
+        double* ta = TA + pl;
+        cp_point_tangent<NS>(slp, ps, ax, P, JxW, ps.ginv, [ta, pitch](int ij, int kl, double v) { __stcs(ta + (int64_t)(9 * ij + kl) * pitch, v); });
     }
     warp_status(ps.info, valid, status);
 }
@@ -693,7 +740,7 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
 
 __global__ void __launch_bounds__(ELEM_WARPS * 32, ELEM_MIN_BLOCKS)
 k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, int64_t c0, int64_t ncc,
-                  const double* __restrict__ PJg, const double* __restrict__ TAg, const int64_t* __restrict__ indptr,
+                  int64_t pitch, const double* __restrict__ PJg, const double* __restrict__ TAg, const int64_t* __restrict__ indptr,
                   const uint8_t* __restrict__ rank, double* __restrict__ res, double* __restrict__ csr_data,
                   double* __restrict__ coo_V) {
     extern __shared__ double smem[];
@@ -706,7 +753,6 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
     int* RB = reinterpret_cast<int*>(ROWP + 32);                      // [32][8] column-block offsets
     const int cl = lane >> 3, a = lane & 7;
     const int64_t nquads = (ncc + 3) >> 2;
-    const int64_t npc = ncc * 8;
     for (int64_t quad = (int64_t)blockIdx.x * ELEM_WARPS + warp; quad < nquads; quad += (int64_t)gridDim.x * ELEM_WARPS) {
         int64_t cc = quad * 4 + cl;                // cell within the chunk
         const bool valid = cc < ncc;
@@ -718,9 +764,9 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
         {
             double t[27], pj9[9];
 #pragma unroll
-            for (int i = 0; i < 27; ++i) t[i] = TAg[i * npc + pl];
+            for (int i = 0; i < 27; ++i) t[i] = __ldcs(TAg + i * pitch + pl);
 #pragma unroll
-            for (int i = 0; i < 9; ++i) pj9[i] = PJg[i * npc + pl];
+            for (int i = 0; i < 9; ++i) pj9[i] = __ldcs(PJg + i * pitch + pl);
             double gN[8][3], JxW;
             point_kinematics(cells, points, nullptr, c, a, nullptr, gN, JxW);
             double* gq = GN + cl * GN_CELL + a * 24;
@@ -768,7 +814,7 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
             double t[27];
             if (i < 2) {
 #pragma unroll
-                for (int k = 0; k < 27; ++k) t[k] = TAg[((i + 1) * 27 + k) * npc + pl];
+                for (int k = 0; k < 27; ++k) t[k] = __ldcs(TAg + ((i + 1) * 27 + k) * pitch + pl);
             }
 #endif
             double acc[24];
@@ -799,7 +845,7 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
             if (i < 2) {
                 double t[27];
 #pragma unroll
-                for (int k = 0; k < 27; ++k) t[k] = TAg[((i + 1) * 27 + k) * npc + pl];
+                for (int k = 0; k < 27; ++k) t[k] = __ldcs(TAg + ((i + 1) * 27 + k) * pitch + pl);
 #pragma unroll
                 for (int k = 0; k < 27; ++k) ts[k] = t[k];
             }
@@ -904,6 +950,7 @@ k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, c
         for (int i = 0; i < 9; ++i) H[i] = u_grads[p * 9 + i];
         solve_point<NS, POWN>(st, mat, slp, dt, p, np, H, pm, ps);
     }
+    if (Aout) cp_point_tangent_factor<NS>(slp, pm, ps, ps.ginv);
     double R[9], P[9];
     point_frame(st, p, np, R, ps);
     CpStressAux ax;
@@ -911,7 +958,10 @@ k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, c
     if (valid) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) Pout[p * 9 + i] = P[i];
-        if (Aout) cp_point_tangent<NS>(slp, pm, ps, ax, R, 1.0, Aout + p * 81, 9, 1);
+        if (Aout) {
+            double* ao = Aout + p * 81;
+            cp_point_tangent<NS>(slp, ps, ax, P, 1.0, ps.ginv, [ao](int ij, int kl, double v) { ao[9 * ij + kl] = v; });
+        }
     }
     warp_status(ps.info, valid, status);
 }
@@ -1023,9 +1073,9 @@ static cudaError_t allow_smem(K kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-extern "C" int cpfem_update_state_cells(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
-                                        const cpfem_state* in, const cpfem_state_out* out, double dt, int64_t cell0,
-                                        int64_t ncells, int64_t* status, void* stream_) {
+static int update_state_impl(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                             const cpfem_state* in, const cpfem_state_out* out, double dt, int64_t cell0,
+                             int64_t ncells, double* sigma_cell, int64_t* status, void* stream_) {
     int rc = check_common(plan, mat, in, "cpfem_update_state");
     if (rc) return rc;
     if (!sol || !out || !out->Fp_inv || !out->g || !out->slip || !in->slip)
@@ -1037,13 +1087,27 @@ extern "C" int cpfem_update_state_cells(const cpfem_plan* plan, const cpfem_mate
     StateView v = make_view(in);
     CpMaterial m = to_mat(mat);
 #define CALL(NS, PW)                                                                                                   \
-    CU_TRY(allow_smem(k_update_state<NS, PW>, point_smem<NS>()));                                                      \
-    k_update_state<NS, PW><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, *out, m,   \
-                                                                         plan->slip, dt, np, cell0, (long long*)status)
+    CU_TRY(allow_smem(k_update_state<NS, PW>, update_smem<NS>()));                                                     \
+    k_update_state<NS, PW><<<grid, PT_BLOCK, update_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, *out, m,  \
+                                                                          plan->slip, dt, np, cell0, sigma_cell,       \
+                                                                          (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
+}
+
+extern "C" int cpfem_update_state_cells(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                                        const cpfem_state* in, const cpfem_state_out* out, double dt, int64_t cell0,
+                                        int64_t ncells, int64_t* status, void* stream_) {
+    return update_state_impl(plan, mat, sol, in, out, dt, cell0, ncells, nullptr, status, stream_);
+}
+
+extern "C" int cpfem_update_state_avg_stress(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
+                                             const cpfem_state* in, const cpfem_state_out* out, double dt,
+                                             double* sigma_cell, int64_t* status, void* stream_) {
+    if (!plan || !sigma_cell) return set_err(-1, "cpfem_update_state_avg_stress: null argument");
+    return update_state_impl(plan, mat, sol, in, out, dt, 0, plan->nc_active, sigma_cell, status, stream_);
 }
 
 extern "C" int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
@@ -1103,14 +1167,15 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
         const int64_t ncc = (plan->nc_active - c0 < plan->chunk_cells) ? plan->nc_active - c0 : plan->chunk_cells;
         const int64_t npc = ncc * 8;
         const int buf = piped ? (int)(ichunk & 1) : 0;
+        const int64_t pitch = scratch_pitch(plan->chunk_cells);
         double* PJ = plan->scratch[buf];
-        double* TA = plan->scratch[buf] + 9 * npc;
+        double* TA = plan->scratch[buf] + 9 * pitch;
         if (piped && ichunk >= 2) CU_TRY(cudaStreamWaitEvent(stream, plan->ev_elem[buf], 0));   // buffer free again
         const unsigned grid = (unsigned)((npc + PT_BLOCK - 1) / PT_BLOCK);
 #define CALL(NS, PW)                                                                                                   \
-    CU_TRY(allow_smem(k_point_tangent<NS, PW>, point_smem<NS>()));                                                     \
-    k_point_tangent<NS, PW><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, \
-                                                                          dt, np, c0 * 8, npc, PJ, TA, (long long*)status)
+    CU_TRY(allow_smem(k_point_tangent<NS, PW>, tangent_smem<NS>()));                                                   \
+    k_point_tangent<NS, PW><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, \
+                                                                          dt, np, c0 * 8, npc, pitch, PJ, TA, (long long*)status)
         CP_DISPATCH(plan->ns, pown, CALL);
 #undef CALL
         CU_TRY(cudaGetLastError());
@@ -1121,7 +1186,7 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
         const int64_t nquads = (ncc + 3) / 4;
         int64_t egrid = (nquads + ELEM_WARPS - 1) / ELEM_WARPS;
         if (egrid > (int64_t)plan->sm_count * ebps) egrid = (int64_t)plan->sm_count * ebps;
-        k_element_tangent<<<(unsigned)egrid, ELEM_WARPS * 32, esmem, estream>>>(plan->cells, plan->points, c0, ncc, PJ, TA, plan->indptr,
+        k_element_tangent<<<(unsigned)egrid, ELEM_WARPS * 32, esmem, estream>>>(plan->cells, plan->points, c0, ncc, pitch, PJ, TA, plan->indptr,
                                                                                 plan->rank, res, csr_data, coo_V);
         CU_TRY(cudaGetLastError());
         if (piped) CU_TRY(cudaEventRecord(plan->ev_elem[buf], estream));
@@ -1165,8 +1230,8 @@ extern "C" int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_ma
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
 #define CALL(NS, PW)                                                                                                   \
-    CU_TRY(allow_smem(k_point_eval<NS, PW>, point_smem<NS>()));                                                        \
-    k_point_eval<NS, PW><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(u_grads, v, m, plan->slip, dt, np, P, tangent,   \
+    CU_TRY(allow_smem(k_point_eval<NS, PW>, tangent_smem<NS>()));                                                      \
+    k_point_eval<NS, PW><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(u_grads, v, m, plan->slip, dt, np, P, tangent,   \
                                                                        (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
 #undef CALL

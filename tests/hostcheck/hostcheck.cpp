@@ -32,9 +32,15 @@ static void run(const double* slip6, const CpMaterial* mat, double dt, int64_t n
         cp_point_solve<NS, POWN>(sl, *mat, pm, dt, H + 9 * p, A + 9 * p, g + NS * p, R + 9 * p, ps);
         cp_point_frame(A + 9 * p, R + 9 * p, ps);
         if (iters) { iters[3 * p] = ps.info.iters; iters[3 * p + 1] = ps.info.evals; iters[3 * p + 2] = ps.info.status; }
+        double parkbuf[CP_TANGENT_PARK];
+        HArr park; park.p = parkbuf;
+        if (tangent) cp_point_tangent_factor<NS>(sl, pm, ps, park);
         CpStressAux ax;
         cp_point_stress(ps, R + 9 * p, P + 9 * p, ax);
-        if (tangent) cp_point_tangent<NS>(sl, pm, ps, ax, R + 9 * p, 1.0, tangent + 81 * p, 9, 1);
+        if (tangent) {
+            double* T = tangent + 81 * p;
+            cp_point_tangent<NS>(sl, ps, ax, P + 9 * p, 1.0, park, [T](int ij, int kl, double v) { T[9 * ij + kl] = v; });
+        }
         // last: the state update overwrites ps.w
         if (A_new) cp_point_state_update<NS>(sl, pm, ps, g + NS * p, slip_old + NS * p, R + 9 * p, A_new + 9 * p, g_new + NS * p, slip_new + NS * p);
     }

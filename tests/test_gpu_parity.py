@@ -234,6 +234,49 @@ def test_problem_mirror_driver_loop():
     assert int(problem.last_status[2]) > 3
 
 
+def test_fused_update_avg_stress():
+    """cpfem_update_state_avg_stress (F3: one local solve for compute_avg_stress + update_int_vars_gp) vs the two separate
+    entry points (bitwise state, sigma to rounding) and vs the oracle; the Problem mirror pairs the two driver calls
+    through it and drops the pairing as soon as an argument changes."""
+    import torch
+    from cpfem_b200 import Plan
+    from cpfem_b200.generate_mesh import Mesh
+    from cpfem_b200.models_304steel import CrystalPlasticity
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('304steel', N=3, steps=6)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    m = _mat(mat)
+    st = plan.new_status()
+    new_f, sg_f = plan.update_state_avg_stress(m, sol, params, dt, status=st)
+    new_s = plan.update_state(m, sol, params, dt)
+    sg_s = plan.avg_stress(m, sol, params, dt)
+    for a, b in zip(new_f, new_s):
+        assert torch.equal(a, b)
+    assert cases.relerr(sg_f.cpu().numpy(), sg_s.cpu().numpy()) < 1e-14
+    assert cases.relerr(sg_f.cpu().numpy(), fe.compute_avg_stress(sol, params, dt)) < TOL
+    new_o = fe.update_int_vars_gp(sol, params, dt)
+    for k in range(2):
+        assert cases.relerr(new_f[k].cpu().numpy(), new_o[k]) < TOL
+    assert int(st[0]) == 0 and int(st[1]) == 0
+    # Problem mirror: compute_avg_stress then update_int_vars_gp on the same device tensors -> one kernel launch
+    problem = CrystalPlasticity(Mesh(fe.points, fe.cells), vec=3, dim=3, ele_type='HEX8', dirichlet_bc_info=None,
+                                additional_info=(quat, ori))
+    problem.dt = dt
+    dsol = torch.as_tensor(sol, device='cuda')
+    dpar = [torch.as_tensor(np.ascontiguousarray(v), device='cuda') for v in params]
+    sg = problem.compute_avg_stress(dsol, dpar)
+    assert problem._fuse_cache is not None
+    new = problem.update_int_vars_gp(dsol, dpar)
+    assert problem._fuse_cache is None                      # handed over
+    assert torch.equal(sg, sg_f) and all(torch.equal(a, b) for a, b in zip(new[:3], new_f))
+    assert new[3] is dpar[3]                                # rot_mats passed through (models_copper.py:282)
+    # a changed argument (in-place edit bumps the version counter) must not be served from the pairing
+    sg = problem.compute_avg_stress(dsol, dpar)
+    dsol.mul_(1.01)
+    new2 = problem.update_int_vars_gp(dsol, dpar)
+    ref2 = plan.update_state(m, dsol, dpar, dt)
+    assert all(torch.equal(a, b) for a, b in zip(new2[:3], ref2)) and not torch.equal(new2[0], new_f[0])
+
+
 def test_full_size_properties():
     """Size-independent properties on a mesh the oracle cannot follow (64^3, 2.1 M points): the residual of a rigid
     translation of the converged field is unchanged, the tangent annihilates rigid translations, CSR row sums of the
