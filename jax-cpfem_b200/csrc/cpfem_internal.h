@@ -1,0 +1,47 @@
+// cpfem_internal.h - shared by the translation units of libcpfem_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/cpfem.h"
+#include "cp_point.cuh"
+
+// -----------------------------------------------------------------------------------------------
+// error plumbing
+// -----------------------------------------------------------------------------------------------
+int cpfem_set_err(int code, const char* what, cudaError_t e = cudaSuccess);
+static inline int set_err(int code, const char* what, cudaError_t e = cudaSuccess) { return cpfem_set_err(code, what, e); }
+#define CU_TRY(x)                                                  \
+    do {                                                           \
+        cudaError_t _e = (x);                                      \
+        if (_e != cudaSuccess) return set_err(-2, #x, _e);         \
+    } while (0)
+
+// -----------------------------------------------------------------------------------------------
+// plan
+// -----------------------------------------------------------------------------------------------
+struct cpfem_plan {
+    int64_t nc = 0, nn = 0, nnz = 0;
+    int64_t nc_active = 0;        // kernels loop over the first nc_active cells (owned cells of a partition)
+    int32_t ns = 0;
+    int32_t max_valence = 0;
+    int32_t* cells = nullptr;     // (nc,8)
+    double* points = nullptr;     // (nn,3)
+    int64_t* indptr = nullptr;    // (3 nn + 1)
+    int32_t* indices = nullptr;   // (nnz)
+    uint8_t* rank = nullptr;      // (nc,8,8): rank of node b in the sorted neighbour list of node a
+    // node-level adjacency behind the pattern (kept for the node-block SpMV of the device solver): the rows 3n..3n+2
+    // own the 9 m(n) entries starting at 9 nbr_ptr[n], laid out [i][j][k] over the sorted neighbours nbr[nbr_ptr[n] + j]
+    int64_t* nbr_ptr = nullptr;   // (nn + 1)
+    int32_t* nbr = nullptr;       // (nnz / 9)
+    // assembly pipeline: the point kernel of chunk i+1 (FP64-bound, caller's stream) overlaps the element kernel of
+    // chunk i (load/store- and atomics-bound, plan-owned high-priority stream); two scratch buffers alternate
+    double* scratch[2] = {nullptr, nullptr};   // each (90, pitch): P JxW and dP/dH JxW, component-major
+    int64_t chunk_cells = 0;                   // cells per assembly chunk
+    cudaStream_t elem_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_point[2] = {nullptr, nullptr}, ev_elem[2] = {nullptr, nullptr};
+    CpSlip slip;
+    int device = 0;
+    int sm_count = 148;
+};

@@ -21,16 +21,15 @@
 #include <string>
 #include <new>
 
-#include "../../include/cpfem.h"
-#include "cp_point.cuh"
+#include "cpfem_internal.h"
 
 static_assert(sizeof(cpfem_material) == sizeof(CpMaterial), "material struct mismatch");
 
 // -----------------------------------------------------------------------------------------------
-// error plumbing
+// error plumbing (declarations + the plan struct: cpfem_internal.h)
 // -----------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
-static int set_err(int code, const char* what, cudaError_t e = cudaSuccess) {
+int cpfem_set_err(int code, const char* what, cudaError_t e) {
     g_last_error = what;
     if (e != cudaSuccess) {
         g_last_error += ": ";
@@ -38,38 +37,9 @@ static int set_err(int code, const char* what, cudaError_t e = cudaSuccess) {
     }
     return code;
 }
-#define CU_TRY(x)                                                  \
-    do {                                                           \
-        cudaError_t _e = (x);                                      \
-        if (_e != cudaSuccess) return set_err(-2, #x, _e);         \
-    } while (0)
 
 extern "C" const char* cpfem_last_error(void) { return g_last_error.c_str(); }
-extern "C" int cpfem_version(void) { return 100; }
-
-// -----------------------------------------------------------------------------------------------
-// plan
-// -----------------------------------------------------------------------------------------------
-struct cpfem_plan {
-    int64_t nc = 0, nn = 0, nnz = 0;
-    int64_t nc_active = 0;        // kernels loop over the first nc_active cells (owned cells of a partition)
-    int32_t ns = 0;
-    int32_t max_valence = 0;
-    int32_t* cells = nullptr;     // (nc,8)
-    double* points = nullptr;     // (nn,3)
-    int64_t* indptr = nullptr;    // (3 nn + 1)
-    int32_t* indices = nullptr;   // (nnz)
-    uint8_t* rank = nullptr;      // (nc,8,8): rank of node b in the sorted neighbour list of node a
-    // assembly pipeline: the point kernel of chunk i+1 (FP64-bound, caller's stream) overlaps the element kernel of
-    // chunk i (load/store- and atomics-bound, plan-owned high-priority stream); two scratch buffers alternate
-    double* scratch[2] = {nullptr, nullptr};   // each (90, 8*chunk_cells): P JxW and dP/dH JxW, component-major
-    int64_t chunk_cells = 0;                   // cells per assembly chunk
-    cudaStream_t elem_stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_point[2] = {nullptr, nullptr}, ev_elem[2] = {nullptr, nullptr};
-    CpSlip slip;
-    int device = 0;
-    int sm_count = 148;
-};
+extern "C" int cpfem_version(void) { return 101; }
 
 #define MAX_VALENCE 16
 // two-stream overlap of the point and element kernels: measured on B200 (r1c), no gain (38.1 vs 37.3 ms at 128^3) - off
@@ -179,6 +149,7 @@ static cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc((void**)p, n *
 extern "C" int cpfem_plan_destroy(cpfem_plan* p) {
     if (!p) return 0;
     cudaFree(p->cells); cudaFree(p->points); cudaFree(p->indptr); cudaFree(p->indices); cudaFree(p->rank);
+    cudaFree(p->nbr_ptr); cudaFree(p->nbr);
     cudaFree(p->scratch[0]); cudaFree(p->scratch[1]);
     if (p->elem_stream) cudaStreamDestroy(p->elem_stream);
     if (p->ev_start) cudaEventDestroy(p->ev_start);
@@ -205,7 +176,7 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
     // slip table: normalise (models_copper.py:62-66) and build the per-system constant records
     if (!cp_slip_init(&p->slip, slip, ns)) { delete p; return set_err(-1, "cpfem_plan_create: zero slip vector"); }
     int64_t *cnt = nullptr, *n2c_ptr = nullptr, *nneigh = nullptr, *nbr_ptr = nullptr;
-    int32_t *n2c = nullptr, *nbr = nullptr;
+    int32_t *n2c = nullptr, *nbr = nullptr;     // nbr_ptr / nbr move into the plan on success
     unsigned long long* cursor = nullptr;
     int* derr = nullptr;
     void* tmp = nullptr;
@@ -291,6 +262,8 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
         p->max_valence = (int32_t)maxv;
     }
     PLAN_TRY(cudaGetLastError());
+    p->nbr_ptr = nbr_ptr; p->nbr = nbr;
+    nbr_ptr = nullptr; nbr = nullptr;
 done:
     cudaFree(cnt); cudaFree(n2c_ptr); cudaFree(nneigh); cudaFree(nbr_ptr); cudaFree(cursor); cudaFree(n2c);
     cudaFree(nbr); cudaFree(derr); cudaFree(tmp);
@@ -717,88 +690,120 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
 
 // -----------------------------------------------------------------------------------------------
 // K3b: element integration + scatter for a chunk.  One warp = 4 cells, lane = (cell cl, node a):
-//   stage the warp's 32 points of PJ / TA (coalesced rows of the scratch) and the shape gradients in shared memory,
 //   r[a,i]        = sum_q PJ_q[i,:] . dN_a[q,:]                          -> atomicAdd into res
 //   K_e[3a+i, :]  = sum_q sum_jl dN_a,j TA_q[ij,kl] dN_b,l  (24 columns) -> atomicAdd into the CSR slots of row 3 n_a + i
 //                                                                          (slot = indptr[row] + 3 rank(a,b) + k), optional COO V
+// The tangent is consumed in three slices (one per row i of P, 27 components x 32 points = 6.9 kB).  A slice is staged
+// by the bulk-copy engine (cp.async.bulk, 27 rows of 256 contiguous bytes of the component-major scratch, completion
+// on a per-warp mbarrier) into one of two buffers, so that the copy of slice i+1 - and of the next quad's first slice -
+// runs under the arithmetic of slice i and no LDG/STS instruction or register is spent on staging.  The staged layout is
+// the scratch's own ([component][point]): a lane reads the SAME component of two consecutive quadrature points with one
+// 128-bit load (the 8 lanes of a cell share the address: 64 bytes per wavefront), which halves the shared-memory
+// wavefronts per FMA with respect to a point-major tile; the lane's own gradients (8 points x 3) live in registers.
 // -----------------------------------------------------------------------------------------------
-// The tangent is consumed in three slices (one per row i of P): 27 doubles per point are staged at a time, which keeps
-// the shared-memory footprint at 15.6 kB per warp (12 warps per SM) instead of 29.6 kB.
-#define TS_PT 27                     // odd point stride: the 32 staging stores of a warp are conflict-free
-#define TS_CELL (8 * TS_PT + 2)      // 218: the four cells of a warp fall into different banks for the broadcast reads
-#define KE_ROW 25                    // odd row stride of the K_e row tile: conflict-free stores
-// per warp: tangent slice, shape gradients, P JxW, one K_e row (24 doubles) per lane, and per lane the CSR row start
-// (int64) + the 8 column-block offsets (int32) of its row for the coalesced scatter
-#define ELEM_WARP_DOUBLES (4 * TS_CELL + 4 * GN_CELL + 4 * PJ_CELL + 32 * KE_ROW + 32 + 32 * 4)
-#define ELEM_WARPS 4
-#ifndef ELEM_PREFETCH
-#define ELEM_PREFETCH 0
-#endif
-#ifndef ELEM_MIN_BLOCKS
-#define ELEM_MIN_BLOCKS 3
+#define KE_ROW 25                        // odd row stride of the K_e row tile: conflict-free stores
+#define EL_TS (27 * 32)                  // one tangent slice [27 components][32 points]
+#define EL_GN (4 * GN_CELL)              // shape gradients [cell][q][b][3]
+#define EL_KE (32 * KE_ROW)              // K_e row tile [32 lanes][KE_ROW]; at quad start the same space holds the transposed
+                                         // gradients GA[cell][a][q][3] (768 doubles) until every lane has its own in registers
+#define EL_MISC (32 + 32 * 4 + 2)        // ROWP int64[32], RB int[32][8], two mbarriers
+#define ELEM_WARP_DOUBLES (2 * EL_TS + EL_GN + EL_KE + EL_MISC)     // 3466 doubles = 27.7 kB per warp
+#ifndef ELEM_WARPS
+#define ELEM_WARPS 8                     // 222 kB and 256 x 255 registers per block: one block fills an SM (measured on B200 at
+                                         // 64^3: 6 / 7 / 8 warps -> 1.46 / 1.27 / 1.14 ms; the previous LDG+STS-staged kernel: 1.19 ms)
 #endif
 
-__global__ void __launch_bounds__(ELEM_WARPS * 32, ELEM_MIN_BLOCKS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "EL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra EL_DONE;\n"
+        "bra EL_WAIT;\n"
+        "EL_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// warp-collective: rows [0, nrows) of `src` (row pitch `pitch` doubles, 32 doubles each) -> dst, completion on `bar`
+__device__ __forceinline__ void el_fill(uint32_t dst, uint32_t bar, const double* src, int64_t pitch, int nrows, int lane) {
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)nrows * 256u);
+    __syncwarp();
+    if (lane < nrows) bulk_g2s(dst + (uint32_t)lane * 256u, src + (int64_t)lane * pitch, 256u, bar);
+}
+
+__global__ void __launch_bounds__(ELEM_WARPS * 32, 1)
 k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, int64_t c0, int64_t ncc,
-                  int64_t pitch, const double* __restrict__ PJg, const double* __restrict__ TAg, const int64_t* __restrict__ indptr,
-                  const uint8_t* __restrict__ rank, double* __restrict__ res, double* __restrict__ csr_data,
-                  double* __restrict__ coo_V) {
-    extern __shared__ double smem[];
+                  int64_t pitch, const double* __restrict__ PJg, const double* __restrict__ TAg,
+                  const int64_t* __restrict__ indptr, const uint8_t* __restrict__ rank, double* __restrict__ res,
+                  double* __restrict__ csr_data, double* __restrict__ coo_V) {
+    extern __shared__ __align__(128) double smem_el[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* TS = smem + (size_t)warp * ELEM_WARP_DOUBLES;
-    double* GN = TS + 4 * TS_CELL;
-    double* PJ = GN + 4 * GN_CELL;
-    double* KE = PJ + 4 * PJ_CELL;                                   // [32 lanes][KE_ROW]
-    long long* ROWP = reinterpret_cast<long long*>(KE + 32 * KE_ROW); // [32] CSR slot of the row start (or -1)
+    double* TS = smem_el + (size_t)warp * ELEM_WARP_DOUBLES;          // [2][27][32]
+    double* GN = TS + 2 * EL_TS;
+    double* KE = GN + EL_GN;                                          // [32 lanes][KE_ROW]  (alias: GA)
+    long long* ROWP = reinterpret_cast<long long*>(KE + EL_KE);       // [32] CSR slot of the row start (or -1)
     int* RB = reinterpret_cast<int*>(ROWP + 32);                      // [32][8] column-block offsets
+    unsigned long long* BAR = reinterpret_cast<unsigned long long*>(RB + 32 * 8);
+    const uint32_t ts_a[2] = {smem_u32(TS), smem_u32(TS + EL_TS)};
+    const uint32_t bar_a[2] = {smem_u32(BAR), smem_u32(BAR + 1)};
+    if (lane == 0) {
+        mbar_init(bar_a[0], 1);
+        mbar_init(bar_a[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     const int cl = lane >> 3, a = lane & 7;
     const int64_t nquads = (ncc + 3) >> 2;
-    for (int64_t quad = (int64_t)blockIdx.x * ELEM_WARPS + warp; quad < nquads; quad += (int64_t)gridDim.x * ELEM_WARPS) {
+    const int64_t stride = (int64_t)gridDim.x * ELEM_WARPS;
+    int64_t quad = (int64_t)blockIdx.x * ELEM_WARPS + warp;
+    if (quad < nquads) {                     // prologue: slice 0 -> buffer 0, P JxW -> buffer 1
+        el_fill(ts_a[0], bar_a[0], TAg + quad * 32, pitch, 27, lane);
+        el_fill(ts_a[1], bar_a[1], PJg + quad * 32, pitch, 9, lane);
+    }
+    for (; quad < nquads; quad += stride) {
+        const int64_t next = quad + stride;
         int64_t cc = quad * 4 + cl;                // cell within the chunk
         const bool valid = cc < ncc;
         if (!valid) cc = ncc - 1;
         const int64_t c = c0 + cc;
-        const int64_t pl = cc * 8 + a;             // this lane's point of the chunk (clamped cells re-read the last cell)
-        double* ts = TS + cl * TS_CELL + a * TS_PT;
-        // ---- stage: slice 0 of the tangent and P JxW of this lane's point, its shape gradients ----
+        // ---- shape gradients of this lane's point (cell cl, q = a): GN[cl][q][b][:] and the transposed copy GA[cl][b][q][:] ----
+        double ga[8][3];
         {
-            double t[27], pj9[9];
-#pragma unroll
-            for (int i = 0; i < 27; ++i) t[i] = __ldcs(TAg + i * pitch + pl);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) pj9[i] = __ldcs(PJg + i * pitch + pl);
             double gN[8][3], JxW;
             point_kinematics(cells, points, nullptr, c, a, nullptr, gN, JxW);
             double* gq = GN + cl * GN_CELL + a * 24;
+            double* gt = KE + cl * 192 + a * 3;
 #pragma unroll
             for (int b = 0; b < 8; ++b)
 #pragma unroll
-                for (int i = 0; i < 3; ++i) gq[b * 3 + i] = gN[b][i];
-            double* pj = PJ + cl * PJ_CELL + a * 9;
+                for (int i = 0; i < 3; ++i) {
+                    gq[b * 3 + i] = gN[b][i];
+                    gt[b * 24 + i] = gN[b][i];
+                }
+            __syncwarp();
+            const double2* g2 = reinterpret_cast<const double2*>(KE + cl * 192 + a * 24);    // own node a, all 8 points
 #pragma unroll
-            for (int i = 0; i < 9; ++i) pj[i] = pj9[i];
-#pragma unroll
-            for (int i = 0; i < 27; ++i) ts[i] = t[i];
+            for (int t = 0; t < 12; ++t) {
+                const double2 v = g2[t];
+                ga[(2 * t) / 3][(2 * t) % 3] = v.x;
+                ga[(2 * t + 1) / 3][(2 * t + 1) % 3] = v.y;
+            }
+            __syncwarp();                           // GA is dead: the space is the K_e row tile from here on
         }
-        __syncwarp();
         const int64_t na = cells[c * 8 + a];
-        if (res) {
-            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-#pragma unroll
-            for (int qq = 0; qq < 8; ++qq) {
-                const double* pj = PJ + cl * PJ_CELL + qq * 9;
-                const double* ga = GN + cl * GN_CELL + qq * 24 + a * 3;
-                const double g0 = ga[0], g1 = ga[1], g2 = ga[2];
-                r0 += pj[0] * g0 + pj[1] * g1 + pj[2] * g2;
-                r1 += pj[3] * g0 + pj[4] * g1 + pj[5] * g2;
-                r2 += pj[6] * g0 + pj[7] * g1 + pj[8] * g2;
-            }
-            if (valid) {
-                atomicAdd(&res[na * 3 + 0], r0);
-                atomicAdd(&res[na * 3 + 1], r1);
-                atomicAdd(&res[na * 3 + 2], r2);
-            }
-        }
         if (csr_data) {
             const uint2 rk = *reinterpret_cast<const uint2*>(rank + (c * 8 + a) * 8);
 #pragma unroll
@@ -807,55 +812,74 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
                 RB[lane * 8 + 4 + b] = 3 * (int)((rk.y >> (8 * b)) & 0xffu);
             }
         }
+        // ---- residual rows from P JxW (buffer 1, first fill of the quad) ----
+        mbar_wait(bar_a[1], 0);
+        if (res) {
+            const double* pj = TS + EL_TS + cl * 8;            // [9][32]
+            double r[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int qp = 0; qp < 4; ++qp)
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const double2 v = *reinterpret_cast<const double2*>(pj + (3 * i + j) * 32 + 2 * qp);
+                        r[i] += v.x * ga[2 * qp][j] + v.y * ga[2 * qp + 1][j];
+                    }
+            if (valid) {
+                atomicAdd(&res[na * 3 + 0], r[0]);
+                atomicAdd(&res[na * 3 + 1], r[1]);
+                atomicAdd(&res[na * 3 + 2], r[2]);
+            }
+        }
+        __syncwarp();                               // buffer 1 is free
+        el_fill(ts_a[1], bar_a[1], TAg + 27 * pitch + quad * 32, pitch, 27, lane);          // slice 1 -> buffer 1
 #pragma unroll 1
         for (int i = 0; i < 3; ++i) {
-            // prefetch the next slice into registers while this one is consumed
-#if ELEM_PREFETCH
-            double t[27];
-            if (i < 2) {
-#pragma unroll
-                for (int k = 0; k < 27; ++k) t[k] = __ldcs(TAg + ((i + 1) * 27 + k) * pitch + pl);
-            }
-#endif
+            const int buf = i & 1;
+            mbar_wait(bar_a[buf], (i == 0) ? 0u : 1u);     // buffer 0: slice 0 (1st fill), slice 2 (2nd); buffer 1: slice 1 (2nd)
+            const double* ts = TS + buf * EL_TS + cl * 8;
+            const double* gn = GN + cl * GN_CELL;
             double acc[24];
 #pragma unroll
             for (int j = 0; j < 24; ++j) acc[j] = 0.0;
-#pragma unroll 2
-            for (int qq = 0; qq < 8; ++qq) {
-                const double* ta = TS + cl * TS_CELL + qq * TS_PT;
-                const double* gq = GN + cl * GN_CELL + qq * 24;
-                const double ga0 = gq[a * 3], ga1 = gq[a * 3 + 1], ga2 = gq[a * 3 + 2];
-                double T[9];
 #pragma unroll
-                for (int kl = 0; kl < 9; ++kl) T[kl] = ga0 * ta[kl] + ga1 * ta[9 + kl] + ga2 * ta[18 + kl];
+            for (int qp = 0; qp < 4; ++qp) {
+                double T0[9], T1[9];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const double gb0 = gq[b * 3], gb1 = gq[b * 3 + 1], gb2 = gq[b * 3 + 2];
+                for (int kl = 0; kl < 9; ++kl) {
+                    const double2 v0 = *reinterpret_cast<const double2*>(ts + kl * 32 + 2 * qp);
+                    const double2 v1 = *reinterpret_cast<const double2*>(ts + (9 + kl) * 32 + 2 * qp);
+                    const double2 v2 = *reinterpret_cast<const double2*>(ts + (18 + kl) * 32 + 2 * qp);
+                    T0[kl] = ga[2 * qp][0] * v0.x + ga[2 * qp][1] * v1.x + ga[2 * qp][2] * v2.x;
+                    T1[kl] = ga[2 * qp + 1][0] * v0.y + ga[2 * qp + 1][1] * v1.y + ga[2 * qp + 1][2] * v2.y;
+                }
+                const double2* g0 = reinterpret_cast<const double2*>(gn + (2 * qp) * 24);
+                const double2* g1 = reinterpret_cast<const double2*>(gn + (2 * qp + 1) * 24);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) acc[3 * b + k] += T[3 * k] * gb0 + T[3 * k + 1] * gb1 + T[3 * k + 2] * gb2;
+                for (int t = 0; t < 4; ++t) {       // nodes 2t, 2t+1: six gradient entries = three double2
+                    const double2 p0 = g0[3 * t], p1 = g0[3 * t + 1], p2 = g0[3 * t + 2];
+                    const double2 q0 = g1[3 * t], q1 = g1[3 * t + 1], q2 = g1[3 * t + 2];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        acc[6 * t + k] += T0[3 * k] * p0.x + T0[3 * k + 1] * p0.y + T0[3 * k + 2] * p1.x +
+                                          T1[3 * k] * q0.x + T1[3 * k + 1] * q0.y + T1[3 * k + 2] * q1.x;
+                        acc[6 * t + 3 + k] += T0[3 * k] * p1.y + T0[3 * k + 1] * p2.x + T0[3 * k + 2] * p2.y +
+                                              T1[3 * k] * q1.y + T1[3 * k + 1] * q2.x + T1[3 * k + 2] * q2.y;
+                    }
                 }
             }
-            __syncwarp();                           // every lane is done reading slice i
-#if ELEM_PREFETCH
-            if (i < 2) {
-#pragma unroll
-                for (int k = 0; k < 27; ++k) ts[k] = t[k];
+            __syncwarp();                           // every lane is done reading this buffer
+            if (i == 0) {
+                el_fill(ts_a[0], bar_a[0], TAg + 54 * pitch + quad * 32, pitch, 27, lane);      // slice 2 -> buffer 0
+            } else if (next < nquads) {             // next quad: P JxW -> buffer 1 (after slice 1), slice 0 -> buffer 0 (after slice 2)
+                if (i == 1) el_fill(ts_a[1], bar_a[1], PJg + next * 32, pitch, 9, lane);
+                else el_fill(ts_a[0], bar_a[0], TAg + next * 32, pitch, 27, lane);
             }
-#else
-            if (i < 2) {
-                double t[27];
+            if (valid && coo_V) {
+                double* v = coo_V + c * 576 + (int64_t)(3 * a + i) * 24;
 #pragma unroll
-                for (int k = 0; k < 27; ++k) t[k] = __ldcs(TAg + ((i + 1) * 27 + k) * pitch + pl);
-#pragma unroll
-                for (int k = 0; k < 27; ++k) ts[k] = t[k];
-            }
-#endif
-            if (valid) {
-                if (coo_V) {
-                    double* v = coo_V + c * 576 + (int64_t)(3 * a + i) * 24;
-#pragma unroll
-                    for (int j = 0; j < 24; ++j) v[j] = acc[j];
-                }
+                for (int j = 0; j < 24; ++j) v[j] = acc[j];
             }
             if (csr_data) {
                 // coalesced scatter: every lane parks its row in shared memory, then one warp instruction adds one row:
@@ -872,8 +896,8 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
                     const long long base = ROWP[t];
                     if (lane < 24 && base >= 0) atomicAdd(csr_data + base + RB[t * 8 + jb] + jk, KE[t * KE_ROW + lane]);
                 }
+                __syncwarp();                       // KE / ROWP free again
             }
-            __syncwarp();                           // slice i+1 is visible, KE / ROWP free again
         }
     }
 }
