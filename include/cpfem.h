@@ -145,6 +145,21 @@ int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_material* mat
 int cpfem_apply_dirichlet(const cpfem_plan* plan, const int64_t* rows, const double* vals, int64_t nbc,
                           const double* sol, double* res, double* csr_data, void* stream);
 
+/* ---- device linear solver on the plan's pattern ---------------------------------------
+ * Replaces jax_solve (crystal_plasticity_OR_design/solver.py:19-48): get_A's host CSR -> BCOO round trip disappears,
+ * the matrix assembled by cpfem_newton_update (+ cpfem_apply_dirichlet) is used where it lies. */
+/* y = A x, A = (plan pattern, csr_data).  Node-block SpMV (three rows per node share one neighbour list). */
+int cpfem_spmv(const cpfem_plan* plan, const double* csr_data, const double* x, double* y, void* stream);
+/* diag(A) (solver.py:32 `A_sp_scipy.diagonal()`), or 1/diag(A) when invert != 0. */
+int cpfem_csr_diagonal(const cpfem_plan* plan, const double* csr_data, double* diag, int32_t invert, void* stream);
+/* BiCGStab with the semantics of jax.scipy.sparse.linalg.bicgstab(A, b, x0=x, M=Jacobi if precond, tol, atol, maxiter)
+ * as called at solver.py:34-40: x holds x0 on entry and the solution on return.  info[0] = iterations taken (JAX's
+ * negative breakdown codes -10 / -11 are passed through), info[1] = 1 if the tolerance was not reached; *resid, if not
+ * NULL, receives ||A x - b||_2 (the check of solver.py:43-45).  Unlike the assembly entry points this call
+ * synchronises the stream (it polls the device-side convergence flag) and owns a workspace inside the plan. */
+int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const double* b, double* x, int32_t precond, double tol,
+                   double atol, int64_t maxiter, int64_t* info, double* resid, void* stream);
+
 /* Interface exchange helper for element-partitioned runs: dst[map[i]] += src[i]. */
 int cpfem_scatter_add(const double* src, const int64_t* map, int64_t n, double* dst, void* stream);
 /* Pack helper: dst[i] = src[map[i]]. */

@@ -59,6 +59,10 @@ SIGNATURES = {
     'cpfem_point_stress_tangent': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, c_i64, ctypes.POINTER(State),
                                                   c_dbl, c_vp, c_vp, c_vp, c_vp]),
     'cpfem_apply_dirichlet': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'cpfem_spmv': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'cpfem_csr_diagonal': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_vp]),
+    'cpfem_bicgstab': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_dbl, c_dbl, c_i64, ctypes.POINTER(c_i64),
+                                      ctypes.POINTER(c_dbl), c_vp]),
     'cpfem_scatter_add': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     'cpfem_gather': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     'cpfem_sumsq': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
@@ -74,14 +78,14 @@ _lock = threading.Lock()
 
 
 def sources():
-    return [os.path.join(_CSRC, 'cpfem_kernels.cu')]
+    return [os.path.join(_CSRC, 'cpfem_kernels.cu'), os.path.join(_CSRC, 'cpfem_solver.cu')]
 
 
 def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(_CSRC, 'cp_point.cuh'), os.path.join(_INCLUDE, 'cpfem.h')]
+    deps = sources() + [os.path.join(_CSRC, 'cp_point.cuh'), os.path.join(_CSRC, 'cpfem_internal.h'), os.path.join(_INCLUDE, 'cpfem.h')]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

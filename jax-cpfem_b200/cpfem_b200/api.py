@@ -277,6 +277,36 @@ class Plan:
                                                    _ptr(csr_data), _stream()), 'cpfem_apply_dirichlet')
 
 
+    # ---- device linear solver (F2) -----------------------------------------------------------------
+    def spmv(self, csr_data, x, out=None):
+        """y = A x on the plan's pattern."""
+        with torch.cuda.device(self.device):
+            x = _dev_f64(x, self.device).reshape(-1)
+            if out is None:
+                out = torch.empty(self.ndof, dtype=torch.float64, device=self.device)
+            check(_lib.lib().cpfem_spmv(self._h, _ptr(csr_data), _ptr(x), _ptr(out), _stream()), 'cpfem_spmv')
+        return out
+
+    def csr_diagonal(self, csr_data, invert=False):
+        with torch.cuda.device(self.device):
+            out = torch.empty(self.ndof, dtype=torch.float64, device=self.device)
+            check(_lib.lib().cpfem_csr_diagonal(self._h, _ptr(csr_data), _ptr(out), int(bool(invert)), _stream()), 'cpfem_csr_diagonal')
+        return out
+
+    def bicgstab(self, csr_data, b, x0=None, precond=True, tol=1e-10, atol=1e-10, maxiter=10000):
+        """jax.scipy.sparse.linalg.bicgstab(A, b, x0, M=Jacobi, tol, atol, maxiter) on the device-resident matrix
+        (solver.py:34-40).  Returns (x, iterations, ||A x - b||)."""
+        with torch.cuda.device(self.device):
+            b = _dev_f64(b, self.device).reshape(-1)
+            x = torch.zeros(self.ndof, dtype=torch.float64, device=self.device) if x0 is None else \
+                _dev_f64(x0, self.device).reshape(-1).clone()
+            info = (ctypes.c_int64 * 2)()
+            resid = ctypes.c_double()
+            check(_lib.lib().cpfem_bicgstab(self._h, _ptr(csr_data), _ptr(b), _ptr(x), int(bool(precond)), float(tol), float(atol),
+                                            int(maxiter), info, ctypes.byref(resid), _stream()), 'cpfem_bicgstab')
+        return x, int(info[0]), float(resid.value)
+
+
 # ---- free helpers ------------------------------------------------------------------------------
 def scatter_add(src, index_map, dst):
     check(_lib.lib().cpfem_scatter_add(_ptr(src), _ptr(index_map), int(src.numel()), _ptr(dst), _stream()), 'cpfem_scatter_add')

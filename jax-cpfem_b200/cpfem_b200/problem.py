@@ -126,6 +126,7 @@ class FiniteElement:
     def update_Dirichlet_boundary_conditions(self, dirichlet_bc_info):
         """jax_fem: node_inds_list[i] = argwhere(location_fn(points)); vec_inds_list[i]; vals_list[i]."""
         self.dirichlet_bc_info = dirichlet_bc_info
+        self.bc_version = getattr(self, 'bc_version', 0) + 1        # lets the device solver cache the flat dof lists
         location_fns, vecs, value_fns = dirichlet_bc_info
         self.node_inds_list, self.vec_inds_list, self.vals_list = [], [], []
         for loc, v, val in zip(location_fns, vecs, value_fns):

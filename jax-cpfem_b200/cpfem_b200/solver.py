@@ -1,0 +1,162 @@
+"""Device-resident mirror of the reference's row-elimination Newton solver for the hot path
+(crystal_plasticity_OR_design/solver.py): same function names, arguments and control flow, but the residual, the CSR
+matrix and every vector stay on the GPU - `get_A` hands the matrix assembled by `problem.newton_update` to the device
+BiCGStab (`cpfem_bicgstab`) where it lies instead of building a scipy/PETSc matrix on the host.
+
+    solver(problem, solver_options)          solver.py:310-437
+    linear_incremental_solver                solver.py:213-237
+    linear_solver / jax_solve                solver.py:19-48, 92-116  ('jax_solver' branch; 'umfpack_solver' goes through scipy
+                                                                       on the host, for tests)
+    line_search                              solver.py:240-276
+    apply_bc_vec / get_A                     solver.py:119-133, 279-293  (one kernel: cpfem_apply_dirichlet)
+
+Out of scope here: arc-length, dynamic relaxation, adjoint / implicit_vjp, PETSc, P_mat constraints.
+"""
+from __future__ import annotations
+
+import logging
+import time
+
+import numpy as onp
+import torch
+
+from . import api
+
+logger = logging.getLogger('cpfem_b200.solver')
+
+
+def _bc_rows_vals(problem):
+    """Flat Dirichlet dof indices and values of problem.fes[0] (solver.py:125-131 / 290-292), cached on the problem
+    until update_Dirichlet_boundary_conditions replaces the lists."""
+    fe = problem.fes[0]
+    key = (getattr(fe, 'bc_version', 0), len(fe.node_inds_list))
+    hit = getattr(problem, '_bc_cache', None)
+    if hit is None or hit[0] != key:
+        if len(fe.node_inds_list):
+            rows = onp.concatenate([onp.asarray(n, dtype=onp.int64) * fe.vec + onp.asarray(v, dtype=onp.int64) + problem.offset[0]
+                                    for n, v in zip(fe.node_inds_list, fe.vec_inds_list)])
+            vals = onp.concatenate([onp.asarray(v, dtype=onp.float64) for v in fe.vals_list])
+        else:
+            rows, vals = onp.zeros(0, onp.int64), onp.zeros(0, onp.float64)
+        dev = problem.device
+        hit = (key, torch.as_tensor(rows, device=dev), torch.as_tensor(vals, device=dev))
+        problem._bc_cache = hit
+    return hit[1], hit[2]
+
+
+def apply_bc_vec(res_vec, dofs, problem, scale=1.):
+    """solver.py:119-133: res[bc] = dofs[bc] - scale * vals (in place on the device vector)."""
+    rows, vals = _bc_rows_vals(problem)
+    if rows.numel():
+        problem.plan.apply_dirichlet(rows, vals * scale if scale != 1. else vals, dofs, res=res_vec, csr_data=None)
+    return res_vec
+
+
+def get_A(problem, solver_options=None):
+    """solver.py:279-293: the reference builds scipy CSR from (V, I, J), copies it into PETSc and zeroes the Dirichlet
+    rows (diag = 1).  Here the CSR data was assembled on the device by newton_update; only the rows are rewritten."""
+    rows, vals = _bc_rows_vals(problem)
+    if rows.numel():
+        problem.plan.apply_dirichlet(rows, vals, problem._last_sol.reshape(-1), res=None, csr_data=problem.csr_data)
+    return problem.csr_data
+
+
+def jax_solve(problem, A, b, x0, precond):
+    """solver.py:19-48: Jacobi-preconditioned BiCGStab (tol = atol = 1e-10, maxiter = 10000) + acceptance test."""
+    x, k, err = problem.plan.bicgstab(A, b, x0=x0, precond=precond, tol=1e-10, atol=1e-10, maxiter=10000)
+    logger.debug('device BiCGStab: %d iterations, res = %g', k, err)
+    problem.last_linear_iterations = k
+    assert err < 0.1, f'linear solver failed to converge with err = {err}'
+    return x
+
+
+def umfpack_solve(problem, A, b):
+    """solver.py:50-61 (host, scipy): kept for tests and tiny problems."""
+    import scipy.sparse.linalg
+    Asp = problem.csr_scipy()
+    x = scipy.sparse.linalg.spsolve(Asp.tocsc(), b.cpu().numpy())
+    return torch.as_tensor(x, device=problem.device)
+
+
+def linear_solver(problem, A, b, x0, solver_options):
+    """solver.py:92-116."""
+    if len(solver_options.keys() & {'jax_solver', 'umfpack_solver', 'petsc_solver', 'custom_solver'}) == 0:
+        solver_options['jax_solver'] = {}
+    if 'jax_solver' in solver_options:
+        precond = solver_options['jax_solver'].get('precond', True)
+        return jax_solve(problem, A, b, x0, precond)
+    if 'umfpack_solver' in solver_options:
+        return umfpack_solve(problem, A, b)
+    if 'custom_solver' in solver_options:
+        return solver_options['custom_solver'](A, b, x0, solver_options)
+    raise NotImplementedError('petsc_solver is not part of the device path (SURVEY section 8: out of scope)')
+
+
+def line_search(problem, dofs, inc):
+    """solver.py:240-276: up to three halvings of the step while the residual norm decreases."""
+    def res_norm_fn(alpha):
+        d = dofs + alpha * inc
+        res = problem.compute_residual(problem.unflatten_fn_sol_list(d))[0].reshape(-1)
+        return float(torch.linalg.norm(apply_bc_vec(res, d, problem)))
+    alpha = 1.
+    res_norm = res_norm_fn(alpha)
+    for _ in range(3):
+        alpha *= 0.5
+        res_norm_half = res_norm_fn(alpha)
+        if res_norm_half > res_norm:
+            alpha *= 2.
+            break
+        res_norm = res_norm_half
+    return dofs + alpha * inc
+
+
+def linear_incremental_solver(problem, res_vec, A, dofs, solver_options):
+    """solver.py:213-237.  x0 is exact on the Dirichlet dofs: assign_bc(0) - copy_bc(dofs)."""
+    b = -res_vec
+    rows, vals = _bc_rows_vals(problem)
+    x0 = torch.zeros_like(dofs)
+    if rows.numel():
+        x0[rows] = vals - dofs[rows]
+    inc = linear_solver(problem, A, b, x0, solver_options)
+    if solver_options.get('line_search_flag', False):
+        return line_search(problem, dofs, inc)
+    return dofs + inc
+
+
+def solver(problem, solver_options=None):
+    """solver.py:310-437: Newton iteration with row elimination; returns sol_list (device tensors)."""
+    solver_options = {} if solver_options is None else solver_options
+    start = time.time()
+    dev = problem.device
+    if 'initial_guess' in solver_options:
+        dofs = torch.cat([api._dev_f64(s, dev).reshape(-1) for s in solver_options['initial_guess']]).clone()
+    else:
+        dofs = torch.zeros(problem.num_total_dofs_all_vars, dtype=torch.float64, device=dev)
+    rel_tol = solver_options.get('rel_tol', 1e-8)
+    tol = solver_options.get('tol', 1e-6)
+
+    def newton_update_helper(dofs):
+        sol_list = problem.unflatten_fn_sol_list(dofs)
+        res_vec = problem.newton_update(sol_list)[0].reshape(-1)
+        res_vec = apply_bc_vec(res_vec, dofs, problem)
+        A = get_A(problem, solver_options)
+        return res_vec, A
+
+    res_vec, A = newton_update_helper(dofs)
+    res_val = float(torch.linalg.norm(res_vec))
+    res_val_initial = res_val
+    rel_res_val = res_val / res_val_initial if res_val_initial > 0 else 0.0
+    logger.debug('Before, l_2 res = %g, relative l_2 res = %g', res_val, rel_res_val)
+    its = 0
+    while (rel_res_val > rel_tol) and (res_val > tol):
+        dofs = linear_incremental_solver(problem, res_vec, A, dofs, solver_options)
+        res_vec, A = newton_update_helper(dofs)
+        res_val = float(torch.linalg.norm(res_vec))
+        rel_res_val = res_val / res_val_initial
+        its += 1
+        logger.debug('l_2 res = %g, relative l_2 res = %g', res_val, rel_res_val)
+    assert onp.isfinite(res_val), 'res_val contains NaN, stop the program!'
+    assert bool(torch.isfinite(dofs).all()), 'dofs contains NaN, stop the program!'
+    problem.last_newton_iterations = its
+    logger.info('Solve took %g [s]', time.time() - start)
+    return problem.unflatten_fn_sol_list(dofs)

@@ -44,4 +44,6 @@ struct cpfem_plan {
     CpSlip slip;
     int device = 0;
     int sm_count = 148;
+    void* solver_ws = nullptr;    // device linear solver workspace (cpfem_solver.cu), allocated on first use
 };
+void cpfem_solver_ws_free(void* ws);

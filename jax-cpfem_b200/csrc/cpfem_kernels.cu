@@ -150,6 +150,7 @@ extern "C" int cpfem_plan_destroy(cpfem_plan* p) {
     if (!p) return 0;
     cudaFree(p->cells); cudaFree(p->points); cudaFree(p->indptr); cudaFree(p->indices); cudaFree(p->rank);
     cudaFree(p->nbr_ptr); cudaFree(p->nbr);
+    cpfem_solver_ws_free(p->solver_ws);
     cudaFree(p->scratch[0]); cudaFree(p->scratch[1]);
     if (p->elem_stream) cudaStreamDestroy(p->elem_stream);
     if (p->ev_start) cudaEventDestroy(p->ev_start);

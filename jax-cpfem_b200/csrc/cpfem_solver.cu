@@ -1,0 +1,392 @@
+// cpfem_solver.cu - device linear algebra on the plan's CSR pattern: the hand-off row F2 of SURVEY.md section 8(f).
+//
+// Replaces (reference JAX-CPFEM, crystal_plasticity_OR_design/solver.py):
+//   jax_solve            solver.py:19-48    scipy CSR -> BCOO, Jacobi preconditioner, jax.scipy.sparse.linalg.bicgstab
+//                                            (tol = atol = 1e-10, maxiter = 10000), residual check ||A x - b|| < 0.1
+// The reference copies the assembled matrix to the host (get_A, solver.py:279-288), back to the device as BCOO and
+// runs BiCGStab there; here the CSR data never leaves the device.  jax.scipy.sparse.linalg.bicgstab lives in JAX
+// (jax/_src/scipy/sparse/linalg.py, _bicgstab_solve; the model comments name JAX 0.4.13), not in the reference tree:
+// its published algorithm is restated below statement by statement (and once more, in numpy, by the test oracle).
+//
+// Kernels
+//   k_bicg_spmv<MODE>   node-block SpMV y = A x: one warp per node, i.e. per three CSR rows that share one sorted
+//                       neighbour list; the 9 m(n) matrix entries of the node are read as ONE contiguous run with fully
+//                       coalesced loads, column indices come from the node adjacency (4 bytes per 9 entries instead of
+//                       4 per entry).  HBM-bound: 8 + 4/9 bytes per stored entry.  The dot products BiCGStab needs of
+//                       the result are reduced in the same pass.
+//   k_bicg_vec<MODE>    the fused vector updates of one BiCGStab iteration with their reductions
+//   k_csr_diag          diagonal of A (Jacobi preconditioner, solver.py:32-33)
+// Reductions are deterministic: per-block partial sums in a fixed order, the last block to arrive adds them up and
+// runs the scalar recurrences (alpha, omega, beta, breakdown codes, convergence flag) on the device; the host only
+// polls the convergence flag every few iterations, converged iterations are no-ops, so the iterates do not depend on
+// the polling interval.
+#include <math.h>
+#include <stdio.h>
+#include <new>
+
+#include "cpfem_internal.h"
+
+struct BicgScal {
+    double rho, alpha, omega;      // values of the previous iteration (JAX: rho, alpha, omega)
+    double rho_;                   // <rhat, r> of the current iterate
+    double alpha_, omega_;         // values of this iteration
+    double ss, rs, bs, atol2;
+    long long k, maxiter;
+    int done, exit_early;
+    unsigned int ticket;
+    unsigned int pad;
+};
+
+struct BicgVecs {
+    const double *b, *minv;
+    double *x, *r, *rhat, *p, *q, *phat, *s, *shat, *t;
+};
+
+#define RED_BLOCK 256
+#define MAX_PARTIAL_BLOCKS 2048
+
+// block-wide sums of NV values -> partials[block][NV]; returns true in every thread of the LAST block to publish, with
+// the grid totals (fixed summation order for a fixed grid) in tot[].
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* partials, unsigned int* ticket, double (&tot)[NV]) {
+    __shared__ double sh[NV][RED_BLOCK / 32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sh[i][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0.0;
+            for (int w = 0; w < RED_BLOCK / 32; ++w) s += sh[i][w];
+            partials[(size_t)blockIdx.x * NV + i] = s;
+        }
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+    // the last block adds the partials: thread t takes blocks t, t + RED_BLOCK, ... then a fixed tree
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += RED_BLOCK) s += ((volatile double*)partials)[(size_t)b * NV + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncthreads();
+        if (lane == 0) sh[i][warp] = s;
+        __syncthreads();
+        double tt = 0.0;
+        for (int w = 0; w < RED_BLOCK / 32; ++w) tt += sh[i][w];
+        tot[i] = tt;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+    return true;
+}
+
+// MODE 0: r = b - A x ; rhat = p = q = r ; rs = <r,r>, bs = <b,b>      (initial_value of _bicgstab_solve)
+// MODE 1: q = A phat ; <rhat, q>  -> alpha_
+// MODE 2: t = A shat ; <t,s>, <t,t> -> omega_
+// MODE 3: y = A x only (plain SpMV: vin -> vout)
+template <int MODE>
+__global__ void __launch_bounds__(RED_BLOCK)
+k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr, const double* __restrict__ data,
+            int64_t nn, BicgScal* sc, double* partials, BicgVecs V, const double* __restrict__ vin, double* __restrict__ vout,
+            double tol, double atol, long long maxiter) {
+    if (MODE == 1 || MODE == 2) {
+        if (sc->done) return;
+    }
+    const double* __restrict__ xin = (MODE == 0) ? V.x : (MODE == 1) ? V.phat : (MODE == 2) ? V.shat : vin;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * RED_BLOCK + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * RED_BLOCK) >> 5;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t n = warp0; n < nn; n += nwarps) {
+        const int64_t b0 = nbr_ptr[n];
+        const int m = (int)(nbr_ptr[n + 1] - b0);
+        const int m3 = 3 * m, tot = 9 * m;
+        const double* __restrict__ base = data + 9 * b0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        // flat walk over the node's 9 m entries, [i][j][k]; (i, j, k) of entry e advance incrementally (32 = 3*10 + 2)
+        int i = 0, j = lane / 3, k = lane - 3 * (lane / 3), rem = lane;
+        while (rem >= m3 && i < 3) { rem -= m3; j -= m; ++i; }      // tiny nodes (m < 11)
+        for (int e = lane; e < tot; e += 32) {
+            const double a = __ldcs(base + e);
+            const double xv = xin[3 * (int64_t)nbr[b0 + j] + k];
+            const double pr = a * xv;
+            if (i == 0) s0 += pr; else if (i == 1) s1 += pr; else s2 += pr;
+            rem += 32; j += 10; k += 2;
+            if (k >= 3) { k -= 3; ++j; }
+            while (rem >= m3) { rem -= m3; j -= m; ++i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane < 3) {
+            const double y = (lane == 0) ? s0 : (lane == 1) ? s1 : s2;
+            const int64_t row = 3 * n + lane;
+            if (MODE == 0) {
+                const double bb = V.b[row];
+                const double rr = bb - y;
+                V.r[row] = rr; V.rhat[row] = rr; V.p[row] = rr; V.q[row] = rr;
+                acc[0] += rr * rr;
+                acc[1] += bb * bb;
+            } else if (MODE == 1) {
+                V.q[row] = y;
+                acc[0] += V.rhat[row] * y;
+            } else if (MODE == 2) {
+                V.t[row] = y;
+                acc[0] += y * V.s[row];
+                acc[1] += y * y;
+            } else {
+                vout[row] = y;
+            }
+        }
+    }
+    if (MODE == 3) return;
+    double tot2[2];
+    if (!grid_reduce<2>(acc, partials, &sc->ticket, tot2)) return;
+    if (threadIdx.x == 0) {
+        if (MODE == 0) {
+            const double t2 = tol * tol * tot2[1], a2 = atol * atol;
+            sc->bs = tot2[1];
+            sc->atol2 = (t2 > a2) ? t2 : a2;                   // jnp.maximum(square(tol) * bs, square(atol))
+            sc->rs = tot2[0];
+            sc->rho = 1.0; sc->alpha = 1.0; sc->omega = 1.0;   // rho0 = alpha0 = omega0 = 1
+            sc->rho_ = tot2[0];                                // <rhat, r> with rhat = r0
+            sc->k = 0; sc->maxiter = maxiter;
+            sc->exit_early = 0;
+            sc->done = !((tot2[0] > sc->atol2) && (0 < maxiter));
+        } else if (MODE == 1) {
+            sc->alpha_ = sc->rho_ / tot2[0];                   // alpha_ = rho_ / <rhat, q_>
+        } else {
+            sc->omega_ = tot2[0] / tot2[1];                    // omega_ = <t,s> / <t,t>
+        }
+    }
+}
+
+// MODE 0: beta = rho_/rho * alpha/omega ; p = r + beta (p - omega q) ; phat = M p
+// MODE 1: s = r - alpha_ q ; ss = <s,s> ; shat = M s ; exit_early = ss < atol2
+// MODE 2: x += alpha_ phat (+ omega_ shat) ; r = s (- omega_ t) ; rs = <r,r> ; rho_next = <rhat, r> ; k, breakdown, done
+template <int MODE>
+__global__ void __launch_bounds__(RED_BLOCK)
+k_bicg_vec(int64_t n, BicgScal* sc, double* partials, BicgVecs V) {
+    if (sc->done) return;
+    const int64_t i0 = (int64_t)blockIdx.x * RED_BLOCK + threadIdx.x, st = (int64_t)gridDim.x * RED_BLOCK;
+    double acc[2] = {0.0, 0.0};
+    if (MODE == 0) {
+        const double omega = sc->omega;
+        const double beta = sc->rho_ / sc->rho * sc->alpha / omega;
+        for (int64_t i = i0; i < n; i += st) {
+            const double pn = V.r[i] + beta * (V.p[i] - omega * V.q[i]);
+            V.p[i] = pn;
+            V.phat[i] = V.minv ? pn * V.minv[i] : pn;
+        }
+        return;
+    } else if (MODE == 1) {
+        const double al = sc->alpha_;
+        for (int64_t i = i0; i < n; i += st) {
+            const double sv = V.r[i] - al * V.q[i];
+            V.s[i] = sv;
+            V.shat[i] = V.minv ? sv * V.minv[i] : sv;
+            acc[0] += sv * sv;
+        }
+    } else {
+        const double al = sc->alpha_, om = sc->omega_;
+        const bool ee = sc->exit_early != 0;
+        for (int64_t i = i0; i < n; i += st) {
+            const double ap = al * V.phat[i];
+            const double sv = V.s[i];
+            const double xn = ee ? V.x[i] + ap : V.x[i] + (ap + om * V.shat[i]);
+            const double rn = ee ? sv : sv - om * V.t[i];
+            V.x[i] = xn;
+            V.r[i] = rn;
+            acc[0] += rn * rn;
+            acc[1] += V.rhat[i] * rn;
+        }
+    }
+    double tot[2];
+    if (!grid_reduce<2>(acc, partials, &sc->ticket, tot)) return;
+    if (threadIdx.x == 0) {
+        if (MODE == 1) {
+            sc->ss = tot[0];
+            sc->exit_early = (tot[0] < sc->atol2) ? 1 : 0;
+        } else {
+            long long k = (sc->omega_ == 0.0 || sc->alpha_ == 0.0) ? -11 : sc->k + 1;
+            if (sc->rho_ == 0.0) k = -10;
+            sc->k = k;
+            sc->rho = sc->rho_; sc->alpha = sc->alpha_; sc->omega = sc->omega_;
+            sc->rho_ = tot[1];
+            sc->rs = tot[0];
+            sc->done = !((tot[0] > sc->atol2) && (k < sc->maxiter) && (k >= 0));
+        }
+    }
+}
+
+__global__ void k_csr_diag(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr, const double* __restrict__ data,
+                           int64_t nn, double* __restrict__ diag, int invert) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * nn) return;
+    const int64_t n = t / 3;
+    const int i = (int)(t - 3 * n);
+    const int64_t b0 = nbr_ptr[n];
+    const int m = (int)(nbr_ptr[n + 1] - b0);
+    int lo = 0, hi = m - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (nbr[b0 + mid] < (int32_t)n) lo = mid + 1; else hi = mid;
+    }
+    const double d = data[9 * b0 + (int64_t)i * 3 * m + 3 * lo + i];
+    diag[t] = invert ? 1.0 / d : d;
+}
+
+// ||a - b||^2 -> sc->ss (deterministic grid reduction)
+__global__ void __launch_bounds__(RED_BLOCK)
+k_norm2_diff(const double* __restrict__ a, const double* __restrict__ b, int64_t n, BicgScal* sc, double* partials) {
+    double acc[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * RED_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_BLOCK) {
+        const double d = a[i] - b[i];
+        acc[0] += d * d;
+    }
+    double tot[1];
+    if (!grid_reduce<1>(acc, partials, &sc->ticket, tot)) return;
+    if (threadIdx.x == 0) sc->ss = tot[0];
+}
+
+// -----------------------------------------------------------------------------------------------
+// workspace (plan-owned, allocated on first use)
+// -----------------------------------------------------------------------------------------------
+struct cpfem_solver_ws {
+    int64_t n = 0;
+    double* vec = nullptr;         // 8 vectors of n + minv
+    BicgScal* sc = nullptr;
+    double* partials = nullptr;
+    BicgScal* host_sc = nullptr;   // pinned
+};
+
+static int ws_get(cpfem_plan* p, cpfem_solver_ws** out) {
+    if (!p->solver_ws) {
+        cpfem_solver_ws* w = new (std::nothrow) cpfem_solver_ws();
+        if (!w) return set_err(-3, "solver workspace: out of host memory");
+        w->n = 3 * p->nn;
+        cudaError_t e = cudaMalloc((void**)&w->vec, sizeof(double) * 9 * (size_t)w->n);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&w->sc, sizeof(BicgScal));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&w->partials, sizeof(double) * 2 * MAX_PARTIAL_BLOCKS);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&w->host_sc, sizeof(BicgScal));
+        if (e == cudaSuccess) e = cudaMemset(w->sc, 0, sizeof(BicgScal));
+        if (e != cudaSuccess) {
+            cudaFree(w->vec); cudaFree(w->sc); cudaFree(w->partials);
+            if (w->host_sc) cudaFreeHost(w->host_sc);
+            delete w;
+            return set_err(-2, "solver workspace allocation", e);
+        }
+        p->solver_ws = w;
+    }
+    *out = (cpfem_solver_ws*)p->solver_ws;
+    return 0;
+}
+void cpfem_solver_ws_free(void* ws) {
+    cpfem_solver_ws* w = (cpfem_solver_ws*)ws;
+    if (!w) return;
+    cudaFree(w->vec); cudaFree(w->sc); cudaFree(w->partials);
+    if (w->host_sc) cudaFreeHost(w->host_sc);
+    delete w;
+}
+
+static unsigned spmv_grid(const cpfem_plan* p) {
+    int64_t g = (p->nn + (RED_BLOCK / 32) - 1) / (RED_BLOCK / 32);
+    const int64_t cap = (int64_t)p->sm_count * 8;
+    if (g > cap) g = cap;
+    if (g > MAX_PARTIAL_BLOCKS) g = MAX_PARTIAL_BLOCKS;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+static unsigned vec_grid(const cpfem_plan* p, int64_t n) {
+    int64_t g = (n + RED_BLOCK - 1) / RED_BLOCK;
+    const int64_t cap = (int64_t)p->sm_count * 8;
+    if (g > cap) g = cap;
+    if (g > MAX_PARTIAL_BLOCKS) g = MAX_PARTIAL_BLOCKS;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+extern "C" int cpfem_spmv(const cpfem_plan* plan, const double* csr_data, const double* x, double* y, void* stream_) {
+    if (!plan || !csr_data || !x || !y) return set_err(-1, "cpfem_spmv: null argument");
+    BicgVecs V = {};
+    k_bicg_spmv<3><<<spmv_grid(plan), RED_BLOCK, 0, (cudaStream_t)stream_>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, nullptr,
+                                                                           nullptr, V, x, y, 0.0, 0.0, 0);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cpfem_csr_diagonal(const cpfem_plan* plan, const double* csr_data, double* diag, int32_t invert, void* stream_) {
+    if (!plan || !csr_data || !diag) return set_err(-1, "cpfem_csr_diagonal: null argument");
+    const int64_t n = 3 * plan->nn;
+    k_csr_diag<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, diag, invert);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const double* b, double* x, int32_t precond,
+                              double tol, double atol, int64_t maxiter, int64_t* info, double* resid, void* stream_) {
+    if (!plan || !csr_data || !b || !x) return set_err(-1, "cpfem_bicgstab: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cpfem_solver_ws* w = nullptr;
+    int rc = ws_get(plan, &w);
+    if (rc) return rc;
+    const int64_t n = w->n;
+    BicgVecs V;
+    V.b = b; V.x = x;
+    V.r = w->vec; V.rhat = w->vec + n; V.p = w->vec + 2 * n; V.q = w->vec + 3 * n; V.phat = w->vec + 4 * n;
+    V.s = w->vec + 5 * n; V.shat = w->vec + 6 * n; V.t = w->vec + 7 * n;
+    double* minv = w->vec + 8 * n;
+    V.minv = precond ? minv : nullptr;
+    const unsigned gs = spmv_grid(plan), gv = vec_grid(plan, n);
+    if (precond) {
+        k_csr_diag<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, minv, 1);
+    }
+    k_bicg_spmv<0><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, w->sc, w->partials, V, nullptr, nullptr,
+                                                tol, atol, (long long)maxiter);
+    CU_TRY(cudaGetLastError());
+    // the host polls the device-side flag; the interval grows so that small systems do not pay a sync per iteration
+    int64_t launched = 0;
+    int poll = 4;
+    for (;;) {
+        CU_TRY(cudaMemcpyAsync(w->host_sc, w->sc, sizeof(BicgScal), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        if (w->host_sc->done || launched >= maxiter) break;
+        for (int it = 0; it < poll && launched < maxiter; ++it, ++launched) {
+            k_bicg_vec<0><<<gv, RED_BLOCK, 0, stream>>>(n, w->sc, w->partials, V);
+            k_bicg_spmv<1><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, w->sc, w->partials, V, nullptr,
+                                                        nullptr, 0.0, 0.0, 0);
+            k_bicg_vec<1><<<gv, RED_BLOCK, 0, stream>>>(n, w->sc, w->partials, V);
+            k_bicg_spmv<2><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, w->sc, w->partials, V, nullptr,
+                                                        nullptr, 0.0, 0.0, 0);
+            k_bicg_vec<2><<<gv, RED_BLOCK, 0, stream>>>(n, w->sc, w->partials, V);
+        }
+        CU_TRY(cudaGetLastError());
+        if (poll < 32) poll *= 2;
+    }
+    if (info) {
+        info[0] = w->host_sc->k;                                   // iterations taken (negative: breakdown code of JAX)
+        info[1] = (w->host_sc->rs > w->host_sc->atol2) ? 1 : 0;    // 1 = stopped without reaching the tolerance
+    }
+    if (resid) {
+        // ||A x - b|| as jax_solve checks it (solver.py:43-45): one more SpMV into the t vector
+        k_bicg_spmv<3><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, nullptr, nullptr, V, x, V.t, 0.0, 0.0, 0);
+        k_norm2_diff<<<gv, RED_BLOCK, 0, stream>>>(V.t, b, n, w->sc, w->partials);
+        CU_TRY(cudaMemcpyAsync(w->host_sc, w->sc, sizeof(BicgScal), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        *resid = sqrt(w->host_sc->ss);
+    }
+    return 0;
+}

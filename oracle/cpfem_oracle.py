@@ -603,3 +603,97 @@ def solve_load_step(fe: FEOracle, sol, params, dt, bc_nodes, bc_comps, bc_vals, 
         if it > max_outer:
             raise RuntimeError('oracle: outer Newton did not converge')
     return sol, it
+
+
+# --------------------------------------------------------------------------------------------
+# Linear solver of the reference: jax_solve (crystal_plasticity_OR_design/solver.py:19-48).
+# The Krylov method itself is third-party: jax.scipy.sparse.linalg.bicgstab (JAX, jax/_src/scipy/sparse/linalg.py,
+# function _bicgstab_solve; JAX is not vendored and not installable here, the model files name version 0.4.13 at
+# models_copper.py:206).  Its published algorithm is restated below statement by statement; parity is anchored on the
+# reference's call site (solver.py:34-40: x0, M = Jacobi, tol = atol = 1e-10, maxiter = 10000) and on its acceptance
+# test ||A x - b|| < 0.1 (solver.py:43-45).
+# --------------------------------------------------------------------------------------------
+def bicgstab_ref(A, b, x0=None, M=None, tol=1e-5, atol=0.0, maxiter=None):
+    """numpy restatement of jax.scipy.sparse.linalg.bicgstab.  Returns (x, k): k = iterations taken, or JAX's
+    breakdown codes -10 (rho == 0) / -11 (omega == 0 or alpha == 0)."""
+    b = onp.asarray(b, dtype=onp.float64)
+    x = onp.zeros_like(b) if x0 is None else onp.array(x0, dtype=onp.float64)
+    if maxiter is None:
+        maxiter = 10 * len(b)
+    Mf = (lambda v: v) if M is None else M
+    bs = float(b @ b)
+    atol2 = max(tol ** 2 * bs, atol ** 2)
+    r = b - A @ x
+    rhat, p, q = r.copy(), r.copy(), r.copy()
+    alpha = omega = rho = 1.0
+    k = 0
+    while (float(r @ r) > atol2) and (k < maxiter) and (k >= 0):
+        rho_ = float(rhat @ r)
+        beta = rho_ / rho * alpha / omega
+        p = r + beta * (p - omega * q)
+        phat = Mf(p)
+        q = A @ phat
+        alpha_ = rho_ / float(rhat @ q)
+        s = r - alpha_ * q
+        exit_early = float(s @ s) < atol2
+        shat = Mf(s)
+        t = A @ shat
+        omega_ = float(t @ s) / float(t @ t)
+        if exit_early:
+            x = x + alpha_ * phat
+            r = s
+        else:
+            x = x + (alpha_ * phat + omega_ * shat)
+            r = s - omega_ * t
+        k_ = -11 if (omega_ == 0 or alpha_ == 0) else k + 1
+        if rho_ == 0:
+            k_ = -10
+        alpha, omega, rho, k = alpha_, omega_, rho_, k_
+    return x, k
+
+
+def jax_solve_ref(A, b, x0, precond=True):
+    """solver.py:19-48 on a scipy CSR matrix: Jacobi-preconditioned BiCGStab + the residual acceptance test."""
+    jacobi = A.diagonal()
+    M = (lambda v: v * (1. / jacobi)) if precond else None
+    x, k = bicgstab_ref(A, b, x0=x0, M=M, tol=1e-10, atol=1e-10, maxiter=10000)
+    err = onp.linalg.norm(A @ x - b)
+    assert err < 0.1, f'linear solver failed to converge with err = {err}'
+    return x, k, err
+
+
+def solve_load_step_bicgstab(fe: 'FEOracle', sol, params, dt, bc_nodes, bc_comps, bc_vals, tol=1e-6, rel_tol=1e-8,
+                             max_outer=50):
+    """solver.py:310-437 with the reference's own linear solver path (jax_solve) and its initial guess
+    (linear_incremental_solver, solver.py:213-237: x0 = assign_bc(0) - copy_bc(dofs))."""
+    ndof = fe.nn * 3
+    rows = onp.asarray(bc_nodes) * 3 + onp.asarray(bc_comps)
+    bc_vals = onp.asarray(bc_vals, dtype=onp.float64)
+    sol = onp.array(sol, dtype=onp.float64)
+
+    def assemble(sol):
+        res, V = fe.newton_update(sol, params, dt)
+        res = res.reshape(-1).copy()
+        res[rows] = sol.reshape(-1)[rows] - bc_vals
+        A = csr_from_coo(V, fe.I, fe.J, ndof).tolil()
+        for r_ in rows:
+            A.rows[r_] = [int(r_)]
+            A.data[r_] = [1.0]
+        return res, A.tocsr()
+
+    res, A = assemble(sol)
+    r0 = onp.linalg.norm(res)
+    rn = r0
+    it, lin_its = 0, []
+    while (rn / r0 > rel_tol) and (rn > tol):
+        x0 = onp.zeros(ndof)
+        x0[rows] = bc_vals - sol.reshape(-1)[rows]
+        inc, k, err = jax_solve_ref(A, -res, x0, True)
+        lin_its.append(k)
+        sol = sol + inc.reshape(-1, 3)
+        res, A = assemble(sol)
+        rn = onp.linalg.norm(res)
+        it += 1
+        if it > max_outer:
+            raise RuntimeError('oracle: outer Newton did not converge')
+    return sol, it, lin_its

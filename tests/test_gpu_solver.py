@@ -1,0 +1,147 @@
+"""GPU suite for row F2: node-block SpMV, Jacobi-BiCGStab and the device-resident Newton solver mirror, against the
+oracle (numpy restatement of jax.scipy.sparse.linalg.bicgstab, scipy direct solve) and against the reference's golden
+stress-strain curves run through the whole GPU path (assembly -> Dirichlet rows -> BiCGStab -> state update)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import cpfem_oracle as O
+from test_solver_oracle import _clamped_case
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _plan_and_matrix(N=3):
+    import torch
+    from cpfem_b200 import Plan, make_material
+    fe, mat, dt, deps, params, pts, nodes, comps, bottom, top, quat, ori = _clamped_case(N)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    m = make_material(mat.C11, mat.C12, mat.C44, mat.h, mat.t_sat, mat.gss_a, mat.xm, mat.r, mat.ao, mat.tol, mat.max_sub_step)
+    sol = np.stack([0 * pts[:, 0], 0 * pts[:, 1], 4 * deps * pts[:, 2]], 1)
+    res, data, _ = plan.newton_update(m, sol, params, dt)
+    rows = torch.as_tensor(nodes * 3 + comps, device='cuda')
+    vals = torch.zeros(len(rows), dtype=torch.float64, device='cuda')
+    dsol = torch.as_tensor(sol, device='cuda')
+    plan.apply_dirichlet(rows, vals, dsol.reshape(-1), res=res.reshape(-1), csr_data=data)
+    ip, ix = plan.csr_pattern()
+    import scipy.sparse
+    A = scipy.sparse.csr_array((data.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(plan.ndof, plan.ndof))
+    return plan, data, A, res
+
+
+def test_spmv_and_diagonal():
+    import torch
+    plan, data, A, res = _plan_and_matrix()
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=plan.ndof)
+    y = plan.spmv(data, torch.as_tensor(x, device='cuda')).cpu().numpy()
+    y_o = A @ x
+    assert np.abs(y - y_o).max() < 1e-13 * np.abs(y_o).max()
+    d = plan.csr_diagonal(data).cpu().numpy()
+    assert np.array_equal(d, A.diagonal())
+    di = plan.csr_diagonal(data, invert=True).cpu().numpy()
+    assert np.abs(di * A.diagonal() - 1).max() < 1e-15
+    # determinism of the solver's reductions: two runs give bitwise identical iterates
+    b = torch.as_tensor(rng.normal(size=plan.ndof), device='cuda')
+    x1, k1, e1 = plan.bicgstab(data, b)
+    x2, k2, e2 = plan.bicgstab(data, b)
+    assert k1 == k2 and torch.equal(x1, x2)
+
+
+def test_bicgstab_vs_oracle():
+    import torch
+    import scipy.sparse.linalg
+    plan, data, A, res = _plan_and_matrix()
+    b = -res.reshape(-1).cpu().numpy()
+    x0 = np.zeros(plan.ndof)
+    x_o, k_o, err_o = O.jax_solve_ref(A, b, x0, True)
+    x, k, err = plan.bicgstab(data, torch.as_tensor(b, device='cuda'), x0=torch.as_tensor(x0, device='cuda'))
+    x = x.cpu().numpy()
+    x_d = scipy.sparse.linalg.spsolve(A.tocsc(), b)
+    assert abs(k - k_o) <= 2 and k > 0                     # same algorithm; the dot products are summed in another order
+    assert err < 1e-9 * max(np.linalg.norm(b), 1.0) + 1e-9
+    assert np.abs(x - x_d).max() < 1e-8 * np.abs(x_d).max()
+    assert np.abs(x - x_o).max() < 1e-8 * np.abs(x_d).max()
+    # no preconditioner, tolerance already met by x0 (zero iterations, x returned untouched)
+    xu, ku, eu = plan.bicgstab(data, torch.as_tensor(b, device='cuda'), precond=False)
+    assert np.abs(xu.cpu().numpy() - x_d).max() < 1e-7 * np.abs(x_d).max()
+    xz, kz, ez = plan.bicgstab(data, torch.as_tensor(b, device='cuda'), x0=torch.as_tensor(x_d, device='cuda'), tol=1e-8, atol=1e-8)
+    assert kz == 0 and np.array_equal(xz.cpu().numpy(), x_d)
+
+
+def test_device_newton_solver_vs_oracle():
+    """solver(problem) of the mirror (device assembly + Dirichlet rows + device BiCGStab) vs the oracle's load step
+    (autodiff assembly + direct solve) over two load steps of the copper driver's boundary conditions."""
+    import torch
+    from cpfem_b200.generate_mesh import Mesh
+    from cpfem_b200.models_copper import CrystalPlasticity
+    from cpfem_b200.solver import solver
+    fe, mat, dt, deps, params_o, pts, nodes, comps, bottom, top, quat, ori = _clamped_case(3)
+    zb = lambda p: np.isclose(p[2], 0., atol=1e-9)
+    zt = lambda p: np.isclose(p[2], 1., atol=1e-9)
+    disp = [0.]
+    bc = [[zb, zb, zb, zt, zt, zt], [0, 1, 2, 0, 1, 2], [lambda p: 0.] * 5 + [lambda p: disp[0]]]
+    problem = CrystalPlasticity(Mesh(pts, fe.cells), vec=3, dim=3, ele_type='HEX8', dirichlet_bc_info=bc, additional_info=(quat, ori))
+    params = problem.internal_vars
+    sol_o = np.zeros((fe.nn, 3))
+    sol = torch.zeros(fe.nn, 3, dtype=torch.float64, device='cuda')
+    for step in (4, 8):
+        disp[0] = deps * step
+        bc[2][5] = (lambda d: (lambda p: d))(disp[0])
+        problem.fes[0].update_Dirichlet_boundary_conditions(bc)
+        problem.dt = dt
+        problem.set_params(params)
+        sol = solver(problem, {'jax_solver': {}, 'initial_guess': [sol]})[0]
+        vals = np.concatenate([0. * bottom] * 3 + [0. * top] * 2 + [0. * top + disp[0]])
+        sol_o, it_o = O.solve_load_step(fe, sol_o, params_o, dt, nodes, comps, vals)
+        assert problem.last_newton_iterations == it_o
+        assert np.abs(sol.cpu().numpy() - sol_o).max() < 1e-8 * np.abs(sol_o).max()
+        sg = problem.compute_avg_stress(sol, params)
+        assert cases.relerr(sg.cpu().numpy(), fe.compute_avg_stress(sol_o, params_o, dt)) < 1e-8
+        params = problem.update_int_vars_gp(sol, params)
+        params_o = fe.update_int_vars_gp(sol_o, params_o, dt)
+    assert int(problem.last_status[2]) > 2          # plastic flow reached
+
+
+def _gpu_one_element_curve(model, disps, ts, nsteps):
+    """The calibration drivers' loop (calibration_case1_...py:125-200) on the GPU path: 1 hex8 element,
+    BCs corner(x,y) / bottom(z) / top(z) = disp, Newton + Jacobi-BiCGStab, stress before the state update."""
+    import torch
+    from cpfem_b200.generate_mesh import Mesh
+    from cpfem_b200.solver import solver
+    pts, cells = O.box_mesh(1, 1, 1)
+    corner = lambda p: np.isclose(p[0], 0., atol=1e-5) & np.isclose(p[1], 0., atol=1e-5) & np.isclose(p[2], 0., atol=1e-5)
+    bottom = lambda p: np.isclose(p[2], 0., atol=1e-5)
+    top = lambda p: np.isclose(p[2], 1., atol=1e-5)
+    mk = lambda d: [[corner, corner, bottom, top], [0, 1, 2, 2], [lambda p: 0., lambda p: 0., lambda p: 0., lambda p: d]]
+    problem = model(Mesh(pts, cells), vec=3, dim=3, ele_type='HEX8', dirichlet_bc_info=mk(0.),
+                    additional_info=(np.array([[1., 0, 0, 0]]), np.zeros(1, int)))
+    params = problem.internal_vars
+    sol = torch.zeros(8, 3, dtype=torch.float64, device='cuda')
+    out = []
+    for i in range(nsteps):
+        problem.dt = ts[i + 1] - ts[i]
+        problem.fes[0].update_Dirichlet_boundary_conditions(mk(disps[i + 1]))
+        problem.set_params(params)
+        sol = solver(problem, {'jax_solver': {}, 'initial_guess': [sol], 'tol': 1e-7})[0]
+        out.append(float(problem.compute_avg_stress(sol, params)[0, 2, 2]))
+        params = problem.update_int_vars_gp(sol, params)
+    return np.array(out)
+
+
+def test_golden_curves_through_gpu_path():
+    """The reference's committed stress-strain curves (calibration_case1: FCC Cu, calibration_case2: BCC Ta) reproduced
+    by the CUDA path end to end, linear solver included.  The boundary conditions leave the rigid rotation about z free
+    (SURVEY App. H.1): like the reference, the Krylov solver copes with the singular tangent."""
+    from cpfem_b200.models_copper import CrystalPlasticity as Cu
+    from cpfem_b200.models_tantalum import CrystalPlasticity as Ta
+    n = 8
+    gold = np.loadtxt(os.path.join(GOLD, 'copper_ss_curve.txt'))
+    got = _gpu_one_element_curve(Cu, np.linspace(0., 0.025, 21), np.linspace(0., 2.5, 21), n)
+    assert np.abs(got / gold[:n] - 1).max() < 1e-8
+    gold = np.loadtxt(os.path.join(GOLD, 'tantalum_ss_curve.txt'))
+    got = _gpu_one_element_curve(Ta, np.linspace(0., -0.10, 41), np.linspace(0., 10., 41), n)
+    assert np.abs(got / gold[:n] - 1).max() < 1e-9
