@@ -23,3 +23,61 @@ if __name__ == '__main__':
     for dst, src in FILES.items():
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
         print('copied', src, '->', dst)
+
+
+# ---- VTU series the reference commits (outputs of its own drivers): decoded into small .npz fixtures --------------
+#   steel304_vtu.npz  <- polycrystal_304steel/data/vtk/polycrystal_304steel/u_000..u_007.vtu
+#                        (driver polycrystal_304steel/polycrystal_304steel.py:83-233, mesh domain0_mesh16.msh)
+#   dpsteel_vtu.npz   <- polycrystal_DPsteel/data/vtk/polycrystal_DPsteel/u_inhomo_000..007.vtu
+#                        (driver polycrystal_DPsteel/polycrystal_DPsteel_inhomo.py:78-260, mesh n1-id1-mesh10.msh); the
+#                        cell fields phase_inds / cell_ori_inds / C11.. make the driver's unseeded random draw recoverable
+def read_vtu(path):
+    """meshio's binary VTU: base64(uint32 header [nblocks, blocksize, lastsize, csizes...]) + base64(zlib blocks)."""
+    import base64, re, struct, zlib
+    import numpy as np
+    txt = open(path).read()
+    out = {}
+    types = {'Float32': np.float32, 'Float64': np.float64, 'Int32': np.int32, 'Int64': np.int64, 'UInt8': np.uint8}
+    for m in re.finditer(r'<DataArray([^>]*)>(.*?)</DataArray>', txt, re.S):
+        attrs = dict(re.findall(r'(\w+)="([^"]*)"', m.group(1)))
+        if attrs.get('format') != 'binary':
+            continue
+        raw = m.group(2).strip().encode()
+        nblocks = struct.unpack('<I', base64.b64decode(raw[:24])[:4])[0]
+        hbytes = 4 * (3 + nblocks)
+        hlen = ((hbytes + 2) // 3) * 4
+        hdr = np.frombuffer(base64.b64decode(raw[:hlen])[:hbytes], dtype=np.uint32)
+        data = base64.b64decode(raw[hlen:])
+        buf, off = b'', 0
+        for c in hdr[3:]:
+            buf += zlib.decompress(data[off:off + c])
+            off += c
+        arr = np.frombuffer(buf, dtype=types[attrs['type']])
+        nc = int(attrs.get('NumberOfComponents', 1))
+        out[attrs.get('Name', 'noname')] = arr.reshape(-1, nc) if nc > 1 else arr
+    return out
+
+
+def vtu_fixtures(nsteps=8):
+    import numpy as np
+    d304 = os.path.join(REF, 'polycrystal_304steel/data/vtk/polycrystal_304steel')
+    v = [read_vtu(os.path.join(d304, f'u_{k:03d}.vtu')) for k in range(nsteps)]
+    np.savez_compressed(os.path.join(HERE, 'steel304_vtu.npz'),
+                        points=v[0]['Points'], cells=v[0]['connectivity'].reshape(-1, 8).astype(np.int32),
+                        cell_ori_inds=v[0]['cell_ori_inds'].astype(np.int16),
+                        sigma_zz=np.stack([x['sigma_zz'] for x in v]), sigma_xx=np.stack([x['sigma_xx'] for x in v]),
+                        sigma_yy=np.stack([x['sigma_yy'] for x in v]))
+    ddp = os.path.join(REF, 'polycrystal_DPsteel/data/vtk/polycrystal_DPsteel')
+    v = [read_vtu(os.path.join(ddp, f'u_inhomo_{k:03d}.vtu')) for k in range(nsteps)]
+    np.savez_compressed(os.path.join(HERE, 'dpsteel_vtu.npz'),
+                        points=v[0]['Points'], cells=v[0]['connectivity'].reshape(-1, 8).astype(np.int32),
+                        cell_ori_inds=v[0]['cell_ori_inds'].astype(np.int16), phase_inds=v[0]['phase_inds'].astype(np.int8),
+                        C11=v[0]['C11'].astype(np.float64), C12=v[0]['C12'].astype(np.float64), C44=v[0]['C44'].astype(np.float64),
+                        sol=np.stack([x['sol'] for x in v]), sigma_zz=np.stack([x['sigma_zz'] for x in v]),
+                        sigma_xx=np.stack([x['sigma_xx'] for x in v]), sigma_yy=np.stack([x['sigma_yy'] for x in v]))
+    shutil.copyfile(os.path.join(REF, 'polycrystal_DPsteel/data/csv/polycrystal_DPsteel/quat.txt'), os.path.join(HERE, 'quat_dp.txt'))
+    print('wrote steel304_vtu.npz, dpsteel_vtu.npz, quat_dp.txt')
+
+
+if __name__ == '__main__':
+    vtu_fixtures()

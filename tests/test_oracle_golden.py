@@ -138,3 +138,39 @@ def test_fe_layer_consistency():
     assert np.abs(fd - lin).max() < 2e-7 * np.abs(lin).max()
     # nnz of a structured N^3 mesh: 9 (3N+1)^3  
     assert A.nnz == 9 * (3 * 2 + 1) ** 3
+
+
+def test_oracle_vs_dp_steel_vtu():
+    """The oracle's FE layer (multi-element mesh, per-point parameters, 24 slip systems) against the first two load
+    steps of the DP-steel VTU series the reference commits (tests/golden/dpsteel_vtu.npz; float32 storage: 1e-6)."""
+    g = np.load(os.path.join(GOLD, 'dpsteel_vtu.npz'))
+    quat = np.loadtxt(os.path.join(GOLD, 'quat_dp.txt'))[:20, 1:]
+    pts, cells = g['points'], g['cells']
+    nc = len(cells)
+    ph = g['phase_inds'].astype(int)
+    f, m = O.dp_ferrite(), O.dp_martensite()
+    pick = lambda a, b: np.array([a, b])[ph]
+    rep = lambda v: np.repeat(v[:, None], 8, axis=1)
+    ori = np.clip(g['cell_ori_inds'].astype(int), 0, len(quat) - 1)          # JAX gather clamps (SURVEY App. H.2)
+    R = np.repeat(O.get_rot_mat(quat)[ori][:, None], 8, axis=1)
+    C = np.stack([O.cubic_C(a, b, c) for a, b, c in zip(g['C11'], g['C12'], g['C44'])])    # as recorded in the files
+    params = [np.tile(np.eye(3)[None, None], (nc, 8, 1, 1)), np.repeat(rep(pick(f.gss_initial, m.gss_initial))[:, :, None], 24, axis=2),
+              np.zeros((nc, 8, 24)), R, rep(pick(f.gss_a, m.gss_a)), rep(pick(f.h, m.h)), rep(pick(f.t_sat, m.t_sat)),
+              rep(pick(f.xm, m.xm)), rep(pick(f.r, m.r)), np.repeat(C[:, None], 8, axis=1)]
+    fe = O.FEOracle(pts, cells, O.make_dp_batch_factory())
+    Lx, Lz = pts[:, 0].max(), pts[:, 2].max()
+    sel = lambda mask: np.where(mask)[0]
+    left, front = sel(np.isclose(pts[:, 0], 0., atol=1e-5)), sel(np.isclose(pts[:, 1], 0., atol=1e-5))
+    bottom, top = sel(np.isclose(pts[:, 2], 0., atol=1e-5)), sel(np.isclose(pts[:, 2], Lz, atol=1e-5))
+    nodes = np.concatenate([left, front, bottom, top])
+    comps = np.concatenate([0 * left, 0 * front + 1, 0 * bottom + 2, 0 * top + 2])
+    disps = np.linspace(0., 0.01 * Lx, 51)
+    sol = np.zeros((len(pts), 3))
+    for i in range(2):
+        vals = np.concatenate([0. * left, 0. * front, 0. * bottom, 0. * top + disps[i + 1]])
+        sol, _ = O.solve_load_step(fe, sol, params, 0.2, nodes, comps, vals)
+        sg = fe.compute_avg_stress(sol, params, 0.2)
+        params = fe.update_int_vars_gp(sol, params, 0.2)
+        assert np.abs(sol - g['sol'][i]).max() < 1e-6 * np.abs(g['sol'][i]).max()
+        assert np.abs(sg[:, 2, 2] - g['sigma_zz'][i]).max() < 1e-6 * np.abs(g['sigma_zz'][i]).max()
+        assert np.abs(sg[:, 0, 0] - g['sigma_xx'][i]).max() < 1e-6 * np.abs(g['sigma_zz'][i]).max()
