@@ -33,13 +33,15 @@ import torch
 F_UPDATE_FIXED = 1600.0     # set-up: Schmid rotation, B = F A M, hardening
 F_ITER = 5000.0             # one local Newton iteration incl. one line-search residual evaluation
 F_ASSEMBLY_FIXED = 16600.0  # set-up + consistent tangent (10 k) + element K_e share (5 k)
-# executed by this implementation (6x6 symmetric crystal-frame form), 2 x FP64 instructions from the ncu source page:
-X_UPDATE_FIXED = 3000.0     # kinematics, frame change, first residual, state update
-X_ITER = 3200.0             # Newton matrix (12 x 61) + LU + solve (1.0 k instr) + 1.7 residual evaluations x 0.36 k, x 2
-X_ASSEMBLY_FIXED = 17000.0  # + stress, 9-direction tangent (4.6 k instr), element K_e (2.4 k instr)
+# executed by this implementation (6x6 symmetric crystal-frame form, active-set slip processing, factored tangent):
+# 2 x FP64 thread instructions per point from ncu (profiles/r1/h_ncu_summary_n64.txt: dfma + dmul + dadd per cycle x cycles)
+X_UPDATE_FIXED = 3000.0     # kinematics, frame change, 1/g, first residual, state update (~1.5 k instructions)
+X_ITER = 1860.0             # per local Newton iteration: ~0.93 k instructions (matrix over the active systems + LU + solve
+                            # + 1.8 residual evaluations), x 2
+X_ASSEMBLY_FIXED = 12800.0  # update fixed part + factored tangent (2.5 k instr) + element K_e (2.4 k instr), x 2
 B_UPDATE = 610.0            # bytes/point: state in 336 + state out 264 + mesh/sol share 10
 B_ASSEMBLY = 2180.0         # bytes/point: state 240 + mesh/sol 10 + CSR memset 244 + CSR RMW 244 + scratch 2 x 720
-TRAFFIC_UPDATE_B_PER_POINT = 600.0   # ncu dram__bytes_read + write per point, k_update_state at 64^3 (profiles/r1)
+TRAFFIC_UPDATE_B_PER_POINT = 594.0   # ncu dram__bytes_read + write per point, k_update_state at 64^3 (profiles/r1/h_*)
 
 MESH_N = 200
 D_EPS, DT, PRE_STEPS = 2e-4, 2e-3, 10
@@ -301,6 +303,42 @@ def main():
     k_mean_a = float(st_a[3]) / (npts_global * K)
     res_norm = float(torch.sqrt(norm_buf)[0])
 
+    # ---- extra device-resident measurements (not part of `value`): fused update + average stress, F2 solver kernels ---------
+    def _time(fn, reps):
+        fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    sig = torch.empty(nc, 3, 3, dtype=torch.float64, device=dev)
+    t_fused = _time(lambda: plan.update_state_avg_stress(mat, sol, state, DT, out=out, sigma=sig, layout=layout), max(1, min(K, 3)))
+    t_avg = _time(lambda: plan.avg_stress(mat, sol, state, DT, out=sig, layout=layout), max(1, min(K, 3)))
+    solver_info = None
+    if world == 1:
+        xs = torch.randn(plan.ndof, dtype=torch.float64, device=dev)
+        ys = torch.empty_like(xs)
+        t_spmv = _time(lambda: plan.spmv(csr, xs, out=ys), 5)
+        spmv_bytes = plan.nnz * 8 + (plan.nnz // 9) * 4 + (plan.nn + 1) * 8 + 2 * plan.ndof * 8
+        nit = 20
+        tb0 = time.perf_counter()
+        _, kit, _ = plan.bicgstab(csr, res.reshape(-1), tol=0.0, atol=0.0, maxiter=nit)
+        torch.cuda.synchronize()
+        tb1 = time.perf_counter()
+        solver_info = {'spmv_ms': t_spmv, 'spmv_gbs': spmv_bytes / (t_spmv * 1e-3) / 1e9,
+                       'spmv_bytes': spmv_bytes, 'bicgstab_ms_per_iteration': 1e3 * (tb1 - tb0) / nit, 'bicgstab_iterations_timed': nit,
+                       'what': 'node-block SpMV on the assembled CSR (8 + 4/9 B per stored entry + vectors) and one Jacobi-BiCGStab '
+                               'iteration (2 SpMV + fused vector kernels, host wall clock incl. the convergence polls); '
+                               'row F2 of SURVEY 8(f): the reference does this through scipy -> BCOO on the host'}
+        del xs, ys
+
     # ---- e2e: host (pinned) buffers through the public API ---------------------------------------------------
     # update pass: Plan.update_state_host streams the host-resident state through the device (H2D of sol + state, update,
     # D2H of the new state, chunk-pipelined on three streams).  Assembly: H2D of sol + state, newton_update, D2H of the
@@ -384,8 +422,8 @@ def main():
             'flops_per_point': f_upd, 'flops_model': 'SURVEY 8(d): 1.6 k + k x 5.0 k, k = mean local Newton iterations (measured)',
             'mean_local_newton_iters': k_mean_u,
             'executed': {'flops_per_point': x_upd, 'achieved': tf(x_upd, upd_s), 'frac': tf(x_upd, upd_s) / fp64_peak,
-                         'model': '2 x FP64 instructions/point of the 6x6 crystal-frame form: 3.0 k + k x 3.2 k '
-                                  '(ncu source page, profiles/r1); ncu sm__pipe_fp64_cycles_active = 79 % at 64^3'},
+                         'model': '2 x FP64 instructions/point of the 6x6 crystal-frame form with active-set slip processing: '
+                                  '3.0 k + k x 1.86 k (ncu, profiles/r1/h_*); ncu sm__pipe_fp64_cycles_active = 56 % at 64^3'},
             'hbm': {'achieved': pts_rank * B_UPDATE / upd_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': pts_rank * B_UPDATE / upd_s / 1e9 / hbm_peak, 'bytes_per_point': B_UPDATE, 'peak_source': hbm_src},
             'note': 'arithmetic intensity ~%.0f flop/B >> B200 balance (~5.5): the FP64 pipe is the bound, not HBM or tensor '
@@ -398,6 +436,9 @@ def main():
                         'frac': pts_rank * B_ASSEMBLY / asm_s / 1e9 / hbm_peak, 'bytes_per_point': B_ASSEMBLY},
                 'note': 'duration includes the CSR memset, both kernels and (multi-GPU) the interface exchange'}
 
+    if solver_info is not None:
+        solver_info['spmv_roofline'] = {'bound': 'hbm', 'achieved': solver_info['spmv_gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
+                                        'frac': solver_info['spmv_gbs'] / hbm_peak, 'peak_source': hbm_src}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(N, args.cpu_sample_cells, 2, 1)
@@ -416,6 +457,7 @@ def main():
                    'l2': 'inputs (>= 2 GB of state per pass) are larger than the 126 MB L2; no flush needed'},
         'update_ms': t_upd / K, 'assembly_ms': t_asm / K, 'assembly_metric': 'ms per Newton-iteration assembly '
         '(stress+tangent, hex8 integration, residual scatter, CSR fill, interface exchange, norm allreduce)',
+        'update_avg_stress_fused_ms': t_fused, 'avg_stress_ms': t_avg, 'solver': solver_info,
         'mean_local_newton_iters': k_mean_u, 'points_at_iter_cap': int(st_u[0]) + int(st_a[0]),
         'nonfinite_points': int(st_u[1]) + int(st_a[1]), 'residual_norm': res_norm,
         'roofline': roof, 'roofline_assembly': roof_asm, 'cpu_baseline': cpu, 'e2e': e2e,

@@ -10,9 +10,9 @@
 //
 // Kernels
 //   k_bicg_spmv<MODE>   node-block SpMV y = A x: one warp per node, i.e. per three CSR rows that share one sorted
-//                       neighbour list; the 9 m(n) matrix entries of the node are read as ONE contiguous run with fully
-//                       coalesced loads, column indices come from the node adjacency (4 bytes per 9 entries instead of
-//                       4 per entry).  HBM-bound: 8 + 4/9 bytes per stored entry.  The dot products BiCGStab needs of
+//                       neighbour list; lane j owns neighbour j (3 x entries, a 3 x 3 block of the matrix); the 9 m(n)
+//                       entries of the node are one contiguous run of memory, column indices come from the node
+//                       adjacency (4 bytes per 9 entries instead of 4 per entry).  HBM-bound: 8 + 4/9 bytes per stored entry.  The dot products BiCGStab needs of
 //                       the result are reduced in the same pass.
 //   k_bicg_vec<MODE>    the fused vector updates of one BiCGStab iteration with their reductions
 //   k_csr_diag          diagonal of A (Jacobi preconditioner, solver.py:32-33)
@@ -96,8 +96,11 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* partials, u
 // MODE 1: q = A phat ; <rhat, q>  -> alpha_
 // MODE 2: t = A shat ; <t,s>, <t,t> -> omega_
 // MODE 3: y = A x only (plain SpMV: vin -> vout)
+#ifndef SPMV_MIN_BLOCKS
+#define SPMV_MIN_BLOCKS 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(RED_BLOCK)
+__global__ void __launch_bounds__(RED_BLOCK, SPMV_MIN_BLOCKS)
 k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr, const double* __restrict__ data,
             int64_t nn, BicgScal* sc, double* partials, BicgVecs V, const double* __restrict__ vin, double* __restrict__ vout,
             double tol, double atol, long long maxiter) {
@@ -112,20 +115,22 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
     for (int64_t n = warp0; n < nn; n += nwarps) {
         const int64_t b0 = nbr_ptr[n];
         const int m = (int)(nbr_ptr[n + 1] - b0);
-        const int m3 = 3 * m, tot = 9 * m;
+        const int m3 = 3 * m;
         const double* __restrict__ base = data + 9 * b0;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        // flat walk over the node's 9 m entries, [i][j][k]; (i, j, k) of entry e advance incrementally (32 = 3*10 + 2)
-        int i = 0, j = lane / 3, k = lane - 3 * (lane / 3), rem = lane;
-        while (rem >= m3 && i < 3) { rem -= m3; j -= m; ++i; }      // tiny nodes (m < 11)
-        for (int e = lane; e < tot; e += 32) {
-            const double a = __ldcs(base + e);
-            const double xv = xin[3 * (int64_t)nbr[b0 + j] + k];
-            const double pr = a * xv;
-            if (i == 0) s0 += pr; else if (i == 1) s1 += pr; else s2 += pr;
-            rem += 32; j += 10; k += 2;
-            if (k >= 3) { k -= 3; ++j; }
-            while (rem >= m3) { rem -= m3; j -= m; ++i; }
+        // lane j takes neighbour j: its three x entries once, then the 3 x 3 block of the node's rows.  For a fixed (i, k)
+        // the lanes read with a 24-byte stride; the three k-loads of a row hit the same sectors (L1), so every sector
+        // of the matrix still crosses L2/HBM exactly once, and there is no index arithmetic beyond one multiply-add.
+        for (int j = lane; j < m; j += 32) {
+            const double* __restrict__ xp = xin + 3 * (int64_t)nbr[b0 + j];
+            const double* __restrict__ ap = base + 3 * j;
+            const double a00 = __ldcs(ap), a01 = __ldcs(ap + 1), a02 = __ldcs(ap + 2);
+            const double a10 = __ldcs(ap + m3), a11 = __ldcs(ap + m3 + 1), a12 = __ldcs(ap + m3 + 2);
+            const double a20 = __ldcs(ap + 2 * m3), a21 = __ldcs(ap + 2 * m3 + 1), a22 = __ldcs(ap + 2 * m3 + 2);
+            const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
+            s0 += a00 * x0 + a01 * x1 + a02 * x2;
+            s1 += a10 * x0 + a11 * x1 + a12 * x2;
+            s2 += a20 * x0 + a21 * x1 + a22 * x2;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
