@@ -47,6 +47,11 @@ MESH_N = 200
 D_EPS, DT, PRE_STEPS = 2e-4, 2e-3, 10
 
 
+def workload_name(n):
+    return (f'synthetic {n}^3 hex8 polycrystal ({n ** 3} cells, {8 * n ** 3} quad points), 304 steel FCC12 exponent 120, '
+            f'load step {PRE_STEPS + 1} (all points plastic), z-slab element partition')
+
+
 def _peaks():
     p = {}
     try:
@@ -164,8 +169,8 @@ def run_reference(args):
             'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'synthetic {args.n}^3 hex8 polycrystal, 304 steel FCC12, load step 11 (bounded sample)',
-                       'sample_cells': sample_cells},
+            'config': {'workload': workload_name(args.n), 'partition': 'host cores', 'state_layout': 'aos',
+                       'sample_cells': sample_cells, 'l2': 'n/a (CPU arm)'},
             'assembly_ms': None, 'assembly_us_per_cell': r['assembly_us_per_cell'],
             'cpu_baseline': {'value': r['updates_per_s'], 'unit': 'quad-point updates/s', 'cores': r['cores'], 'kind': 'port',
                              'sample': sample, 'assembly_us_per_cell': r['assembly_us_per_cell']},
@@ -451,8 +456,7 @@ def main():
         'metric': 'cp_quad_point_updates_per_s', 'value': npts_global * K / (t_upd * 1e-3), 'unit': 'quad-point updates/s',
         'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': t_tot / K, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'synthetic {N}^3 hex8 polycrystal ({N ** 3} cells, {npts_global} quad points), 304 steel FCC12 '
-                               f'exponent 120, load step {PRE_STEPS + 1} (all points plastic), z-slab element partition',
+        'config': {'workload': workload_name(N),
                    'partition': f'{world} slab(s)', 'state_layout': args.layout,
                    'l2': 'inputs (>= 2 GB of state per pass) are larger than the 126 MB L2; no flush needed'},
         'update_ms': t_upd / K, 'assembly_ms': t_asm / K, 'assembly_metric': 'ms per Newton-iteration assembly '

@@ -17,6 +17,7 @@
 #include <cub/cub.cuh>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <new>
@@ -229,11 +230,17 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
         PLAN_TRY(dev_alloc(&p->indptr, 3 * nnodes + 1));
         PLAN_TRY(dev_alloc(&p->indices, p->nnz));
         PLAN_TRY(dev_alloc(&p->rank, nc * 64));
-        // chunking: CPFEM_CHUNK_CELLS per chunk for big meshes, four chunks for mid-size ones (so that the two
-        // kernels of the assembly overlap), one chunk for tiny ones; always a multiple of 16 cells (one 128-thread block)
-        if (nc >= 4 * CPFEM_CHUNK_CELLS) p->chunk_cells = CPFEM_CHUNK_CELLS;
-        else if (nc >= 4096 && CPFEM_OVERLAP) p->chunk_cells = (((nc + 3) / 4) + 15) / 16 * 16;
-        else p->chunk_cells = nc < CPFEM_CHUNK_CELLS ? nc : CPFEM_CHUNK_CELLS;
+        // chunking: at most CPFEM_CHUNK_CELLS cells per assembly chunk (bounds the scratch), always a multiple of 16 cells
+        // (one 128-thread block of points).  The environment variable CPFEM_CHUNK_CELLS overrides the limit (tests use
+        // it to exercise the multi-chunk path on small meshes).
+        {
+            int64_t lim = CPFEM_CHUNK_CELLS;
+            if (const char* e = getenv("CPFEM_CHUNK_CELLS")) {
+                const long long v = atoll(e);
+                if (v >= 16) lim = (v / 16) * 16;
+            }
+            p->chunk_cells = nc < lim ? nc : lim;
+        }
         {
             const bool two = p->chunk_cells < nc;
             PLAN_TRY(dev_alloc(&p->scratch[0], (size_t)90 * scratch_pitch(p->chunk_cells)));

@@ -1,6 +1,8 @@
 """GPU suite (-m gpu): the CUDA path, called through the C ABI (cpfem_b200.Plan / the Problem mirror), against the
 CPU oracle on the same seeded inputs.  Tolerance: 1e-10 relative to the field maximum for fp64 values (north_star),
 bit-exact for the CSR pattern."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse
@@ -275,6 +277,33 @@ def test_fused_update_avg_stress():
     new2 = problem.update_int_vars_gp(dsol, dpar)
     ref2 = plan.update_state(m, dsol, dpar, dt)
     assert all(torch.equal(a, b) for a, b in zip(new2[:3], ref2)) and not torch.equal(new2[0], new_f[0])
+
+
+def test_chunked_assembly_matches_single_chunk():
+    """The 200^3 benchmark assembles in 16 chunks of 2^19 cells through one scratch buffer; the multi-chunk path (chunk
+    boundaries inside the bulk-copy pipeline of the element kernel, partial last chunk, partial last quad of cells) is
+    exercised here on a small mesh by lowering the chunk limit: V is bitwise the single-chunk V, the CSR data and the
+    residual agree to atomic-summation order, and both match the oracle."""
+    import torch
+    from cpfem_b200 import Plan
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('304steel', N=5, steps=6)     # 125 cells
+    m = _mat(mat)
+    ref = Plan(fe.cells, fe.points, mat.slip)
+    assert ref.chunk_cells == 125
+    res0, data0, V0 = ref.newton_update(m, sol, params, dt, want_V=True)
+    try:
+        for lim in (16, 48):
+            os.environ['CPFEM_CHUNK_CELLS'] = str(lim)
+            plan = Plan(fe.cells, fe.points, mat.slip)
+            assert plan.chunk_cells == lim
+            res, data, V = plan.newton_update(m, sol, params, dt, want_V=True)
+            assert torch.equal(V, V0)
+            assert float((data - data0).abs().max()) < 1e-13 * float(data0.abs().max())
+            assert float((res - res0).abs().max()) < 1e-12 * float(V0.abs().max())
+    finally:
+        os.environ.pop('CPFEM_CHUNK_CELLS', None)
+    res_o, V_o = fe.newton_update(sol, params, dt)
+    assert cases.relerr(V0.cpu().numpy(), V_o) < TOL
 
 
 def test_full_size_properties():
