@@ -469,7 +469,9 @@ __device__ __forceinline__ void warp_status(const CpSolveInfo& info, bool valid,
 
 // Per-point kernels: one thread per quadrature point, PT_BLOCK threads per block; the two per-slip-system arrays
 // (1/g, w) of every thread are columns of a [2][NS][PT_BLOCK] shared-memory tile.
+#ifndef PT_BLOCK
 #define PT_BLOCK 128
+#endif
 // The slip-system records are read with data-dependent indices (only the active systems are processed), which the
 // constant bank serves slowly (LDC); every per-point kernel therefore starts by copying the table of its kernel
 // parameter into shared memory (4.6 kB) and reads it from there (LDS, same address in every lane = broadcast).
@@ -501,24 +503,39 @@ static constexpr size_t update_smem() { return sizeof(double) * (2 * NS + 10) * 
 template <int NS>
 static constexpr size_t tangent_smem() { return sizeof(double) * (NS + (NS > CP_TANGENT_PARK ? NS : CP_TANGENT_PARK)) * PT_BLOCK; }
 
+// Kernel-side material: the C-ABI struct + the per-point parameter block of a UNIFORM material, precomputed on the host.
+// With PP = false (no per-point arrays in the state) the kernels read the block straight from the kernel-parameter
+// constant bank - as free instruction operands instead of ~22 registers per thread; PP = true loads it per point.
+struct KMat {
+    CpMaterial m;
+    CpPointParams u;
+};
+static KMat make_kmat(const CpMaterial& m) {
+    KMat k;
+    k.m = m;
+    cp_params_elastic(k.u, m.C11, m.C12, m.C44, m.xm);
+    k.u.h = m.h; k.u.t_sat = m.t_sat; k.u.gss_a = m.gss_a; k.u.r = m.r;
+    return k;
+}
+
 // u_grad + state -> local Newton solve.  R is reloaded by the callers after the solve (keeps it out of the loop's registers).
 template <int NS, int POWN>
 __device__ __forceinline__ void solve_point(const StateView& st, const CpMaterial& mat, const CpSlipRef& slip, double dt,
-                                            int64_t p, int64_t np, const double* H, CpPointParams& pm, CpPointState<SArr>& ps) {
+                                            int64_t p, int64_t np, const double* H, const CpPointParams& pm,
+                                            CpPointState<SArr>& ps) {
     double A[9], R[9];
     load9(st.Fp_inv, st.soa, p, np, A);
     load9(st.rot, st.soa, p, np, R);
-    load_point_params(mat, st, p, pm);
     cp_point_solve<NS, POWN>(slip, mat, pm, dt, H, A, gin(st.g, st.soa, p, NS, np), R, ps);
 }
 
 // -----------------------------------------------------------------------------------------------
 // K1: state update
 // -----------------------------------------------------------------------------------------------
-template <int NS, int POWN>
+template <int NS, int POWN, bool PP>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
-               StateView st, cpfem_state_out out, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt,
+               StateView st, cpfem_state_out out, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip, double dt,
                int64_t np, int64_t cell0, double* __restrict__ sigma_cell, long long* status) {
     // the state arrays hold the np points of cells [cell0, cell0 + np/8); p indexes them, the mesh is indexed by cell0 + p/8
     extern __shared__ double smem[];
@@ -529,7 +546,10 @@ k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ poi
     if (!valid) p = np - 1;
     CpPointState<SArr> ps;
     point_arrays<NS>(smem, ps);
-    CpPointParams pm;
+    const CpMaterial& mat = km.m;
+    CpPointParams pmv;
+    if (PP) load_point_params(mat, st, p, pmv);
+    const CpPointParams& pm = PP ? pmv : km.u;
     // fused compute_avg_stress (sigma_cell != nullptr): u_grad and JxW of the point wait in 10 more shared-memory rows
     double* hs = smem + 2 * NS * PT_BLOCK + threadIdx.x;
     {
@@ -574,7 +594,7 @@ k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ poi
     if (valid) {
         const int so = (out.layout == CPFEM_LAYOUT_SOA);
         double An[9];
-        load_point_params_hard(mat, st, p, pm);
+        if (PP) load_point_params_hard(mat, st, p, pmv);
         cp_point_state_update<NS>(slp, pm, ps, gin(st.g, st.soa, p, NS, np), gin(st.slip, st.soa, p, NS, np), R, An,
                                   gout(out.g, so, p, NS, np), gout(out.slip, so, p, NS, np));
         const GOut Ao = gout(out.Fp_inv, so, p, 9, np);
@@ -595,10 +615,10 @@ k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ poi
 template <int NS>
 static constexpr size_t residual_smem() { return point_smem<NS>() + sizeof(double) * (PT_BLOCK / 32) * 4 * (GN_CELL + PJ_CELL); }
 
-template <int NS, int POWN>
+template <int NS, int POWN, bool PP>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
-           StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t nc,
+           StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip, double dt, int64_t nc,
            double* __restrict__ res, long long* status) {
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
@@ -615,7 +635,10 @@ k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points,
     CpPointState<SArr> ps;
     point_arrays<NS>(smem, ps);
     {
-        CpPointParams pm;
+        const CpMaterial& mat = km.m;
+    CpPointParams pmv;
+    if (PP) load_point_params(mat, st, p, pmv);
+    const CpPointParams& pm = PP ? pmv : km.u;
         double JxW;
         {
             double H[9], gN[8][3];
@@ -662,10 +685,10 @@ k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points,
 // K3a: stress + consistent tangent at every point of a chunk of cells -> scratch (component-major, coalesced):
 //   PJ[9][npc]  = P_ij JxW          TA[81][npc] = dP_ij/dH_kl JxW        (npc = points in the chunk)
 // -----------------------------------------------------------------------------------------------
-template <int NS, int POWN>
+template <int NS, int POWN, bool PP>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
-                StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np, int64_t p0,
+                StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip, double dt, int64_t np, int64_t p0,
                 int64_t npc, int64_t pitch, double* __restrict__ PJ, double* __restrict__ TA, long long* status) {
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
@@ -675,7 +698,10 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
     const int64_t p = p0 + (valid ? pl : npc - 1);
     CpPointState<SArr> ps;
     point_arrays<NS>(smem, ps);
-    CpPointParams pm;
+    const CpMaterial& mat = km.m;
+    CpPointParams pmv;
+    if (PP) load_point_params(mat, st, p, pmv);
+    const CpPointParams& pm = PP ? pmv : km.u;
     double JxW;
     {
         double H[9], gN[8][3];
@@ -913,10 +939,10 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
 // -----------------------------------------------------------------------------------------------
 // K5: average Cauchy stress per cell (models_copper.py:297-319)
 // -----------------------------------------------------------------------------------------------
-template <int NS, int POWN>
+template <int NS, int POWN, bool PP>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
-             StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip, double dt, int64_t np,
+             StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip, double dt, int64_t np,
              double* __restrict__ sigma_cell, long long* status) {
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
@@ -928,7 +954,10 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
     const int q = (int)(p & 7);
     CpPointState<SArr> ps;
     point_arrays<NS>(smem, ps);
-    CpPointParams pm;
+    const CpMaterial& mat = km.m;
+    CpPointParams pmv;
+    if (PP) load_point_params(mat, st, p, pmv);
+    const CpPointParams& pm = PP ? pmv : km.u;
     double F[9], JxW;
     {
         double gN[8][3];
@@ -963,9 +992,9 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
 // -----------------------------------------------------------------------------------------------
 // tensor_map on explicit u_grads (and its jacfwd)
 // -----------------------------------------------------------------------------------------------
-template <int NS, int POWN>
+template <int NS, int POWN, bool PP>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
-k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, const __grid_constant__ CpSlip slip,
+k_point_eval(const double* __restrict__ u_grads, StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip,
              double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, long long* status) {
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
@@ -975,7 +1004,10 @@ k_point_eval(const double* __restrict__ u_grads, StateView st, CpMaterial mat, c
     if (!valid) p = np - 1;
     CpPointState<SArr> ps;
     point_arrays<NS>(smem, ps);
-    CpPointParams pm;
+    const CpMaterial& mat = km.m;
+    CpPointParams pmv;
+    if (PP) load_point_params(mat, st, p, pmv);
+    const CpPointParams& pm = PP ? pmv : km.u;
     {
         double H[9];
 #pragma unroll
@@ -1087,16 +1119,21 @@ static int rate_pown(const CpMaterial& m, const StateView& v) {
     if (n1 == 9.0) return 9;
     return 0;
 }
-// instantiated (NS, POWN) pairs: FCC/BCC12 x {run-time, 9 (copper), 119 (304 steel)}, BCC24 x {run-time, 19 (DP steel)}
-#define CP_DISPATCH(ns, pown, CALL)                                             \
+// per-point parameter arrays present?  (DP-steel / calibration forms of the state)
+static bool per_point(const StateView& v) { return v.C || v.xm || v.h || v.t_sat || v.gss_a || v.r; }
+// instantiated (NS, POWN, PP) triples: uniform material: FCC/BCC12 x {run-time, 9 (copper), 119 (304 steel)}, BCC24 x
+// {run-time, 19}; per-point parameters: run-time exponent only (the exponent itself may vary from point to point)
+#define CP_DISPATCH(ns, pown, pp, CALL)                                         \
     do {                                                                        \
-        if ((ns) == 12) {                                                       \
-            if ((pown) == 119) { CALL(12, 119); }                               \
-            else if ((pown) == 9) { CALL(12, 9); }                              \
-            else { CALL(12, 0); }                                               \
+        if (pp) {                                                               \
+            if ((ns) == 12) { CALL(12, 0, true); } else { CALL(24, 0, true); }  \
+        } else if ((ns) == 12) {                                                \
+            if ((pown) == 119) { CALL(12, 119, false); }                        \
+            else if ((pown) == 9) { CALL(12, 9, false); }                       \
+            else { CALL(12, 0, false); }                                        \
         } else {                                                                \
-            if ((pown) == 19) { CALL(24, 19); }                                 \
-            else { CALL(24, 0); }                                               \
+            if ((pown) == 19) { CALL(24, 19, false); }                          \
+            else { CALL(24, 0, false); }                                        \
         }                                                                       \
     } while (0)
 
@@ -1118,12 +1155,13 @@ static int update_state_impl(const cpfem_plan* plan, const cpfem_material* mat, 
     const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
     StateView v = make_view(in);
     CpMaterial m = to_mat(mat);
-#define CALL(NS, PW)                                                                                                   \
-    CU_TRY(allow_smem(k_update_state<NS, PW>, update_smem<NS>()));                                                     \
-    k_update_state<NS, PW><<<grid, PT_BLOCK, update_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, *out, m,  \
+    const KMat km = make_kmat(m);
+#define CALL(NS, PW, PPV)                                                                                                   \
+    CU_TRY(allow_smem(k_update_state<NS, PW, PPV>, update_smem<NS>()));                                                     \
+    k_update_state<NS, PW, PPV><<<grid, PT_BLOCK, update_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, *out, km, \
                                                                           plan->slip, dt, np, cell0, sigma_cell,       \
                                                                           (long long*)status)
-    CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
+    CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
@@ -1158,13 +1196,14 @@ extern "C" int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat,
     CU_TRY(cudaMemsetAsync(res, 0, plan->nn * 3 * sizeof(double), stream));
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
+    const KMat km = make_kmat(m);
     const int64_t np = plan->nc_active * 8;
     const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
-#define CALL(NS, PW)                                                                                                   \
-    CU_TRY(allow_smem(k_residual<NS, PW>, residual_smem<NS>()));                                                       \
-    k_residual<NS, PW><<<grid, PT_BLOCK, residual_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, \
+#define CALL(NS, PW, PPV)                                                                                                   \
+    CU_TRY(allow_smem(k_residual<NS, PW, PPV>, residual_smem<NS>()));                                                       \
+    k_residual<NS, PW, PPV><<<grid, PT_BLOCK, residual_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, km, plan->slip, \
                                                                         dt, plan->nc_active, res, (long long*)status)
-    CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
+    CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
@@ -1181,6 +1220,7 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
     if (csr_data) CU_TRY(cudaMemsetAsync(csr_data, 0, plan->nnz * sizeof(double), stream));
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
+    const KMat km = make_kmat(m);
     const int pown = rate_pown(m, v);
     const int64_t np = plan->nc_active * 8;
     const size_t esmem = sizeof(double) * ELEM_WARP_DOUBLES * ELEM_WARPS;
@@ -1204,11 +1244,11 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
         double* TA = plan->scratch[buf] + 9 * pitch;
         if (piped && ichunk >= 2) CU_TRY(cudaStreamWaitEvent(stream, plan->ev_elem[buf], 0));   // buffer free again
         const unsigned grid = (unsigned)((npc + PT_BLOCK - 1) / PT_BLOCK);
-#define CALL(NS, PW)                                                                                                   \
-    CU_TRY(allow_smem(k_point_tangent<NS, PW>, tangent_smem<NS>()));                                                   \
-    k_point_tangent<NS, PW><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, \
+#define CALL(NS, PW, PPV)                                                                                                   \
+    CU_TRY(allow_smem(k_point_tangent<NS, PW, PPV>, tangent_smem<NS>()));                                                   \
+    k_point_tangent<NS, PW, PPV><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, km, plan->slip, \
                                                                           dt, np, c0 * 8, npc, pitch, PJ, TA, (long long*)status)
-        CP_DISPATCH(plan->ns, pown, CALL);
+        CP_DISPATCH(plan->ns, pown, per_point(v), CALL);
 #undef CALL
         CU_TRY(cudaGetLastError());
         if (piped) {
@@ -1240,11 +1280,12 @@ extern "C" int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* ma
     const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
-#define CALL(NS, PW)                                                                                                   \
-    CU_TRY(allow_smem(k_avg_stress<NS, PW>, point_smem<NS>()));                                                        \
-    k_avg_stress<NS, PW><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, m, plan->slip, dt, \
+    const KMat km = make_kmat(m);
+#define CALL(NS, PW, PPV)                                                                                                   \
+    CU_TRY(allow_smem(k_avg_stress<NS, PW, PPV>, point_smem<NS>()));                                                        \
+    k_avg_stress<NS, PW, PPV><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, km, plan->slip, dt, \
                                                                        np, sigma_cell, (long long*)status)
-    CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
+    CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
@@ -1261,11 +1302,12 @@ extern "C" int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_ma
     const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
-#define CALL(NS, PW)                                                                                                   \
-    CU_TRY(allow_smem(k_point_eval<NS, PW>, tangent_smem<NS>()));                                                      \
-    k_point_eval<NS, PW><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(u_grads, v, m, plan->slip, dt, np, P, tangent,   \
+    const KMat km = make_kmat(m);
+#define CALL(NS, PW, PPV)                                                                                                   \
+    CU_TRY(allow_smem(k_point_eval<NS, PW, PPV>, tangent_smem<NS>()));                                                      \
+    k_point_eval<NS, PW, PPV><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(u_grads, v, km, plan->slip, dt, np, P, tangent,   \
                                                                        (long long*)status)
-    CP_DISPATCH(plan->ns, rate_pown(m, v), CALL);
+    CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;

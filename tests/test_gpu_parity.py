@@ -306,6 +306,99 @@ def test_chunked_assembly_matches_single_chunk():
     assert cases.relerr(V0.cpu().numpy(), V_o) < TOL
 
 
+def test_partitioned_assembly_sums_to_global():
+    """Element-partitioned assembly on the device (what every rank of a multi-GPU run does): the slabs of a 2- and a
+    3-way partition are assembled one after the other on this GPU - owned cells active, ghost cells pattern only -
+    and their matrices / residuals, mapped to global dofs, add up to the single-plan assembly.  (The exchange itself is
+    index plumbing over torch.distributed and is covered by the gloo tests in test_partition.py.)"""
+    from cpfem_b200 import Plan
+    from cpfem_b200.partition import slab_partition_structured, partition_cells
+    name, N = '304steel', 4
+    fac, deps, dt = cases.MATERIALS[name]
+    mat = fac()
+    m = _mat(mat)
+    pts, cells = O.box_mesh(N, N, N)
+    rng = np.random.default_rng(7)
+    quat = cases.rand_quat(rng, 6)
+    ori = rng.integers(0, 6, size=len(cells))
+    fe = O.FEOracle(pts, cells, O.make_uniform_batch_factory(mat))
+    params = O.initial_internal_vars(len(cells), mat, O.get_rot_mat(quat)[ori])
+    disp = lambda e: np.stack([-0.3 * e * pts[:, 0], -0.3 * e * pts[:, 1], e * pts[:, 2]], 1) + rng.uniform(-1, 1, pts.shape) * 1e-6
+    whole = Plan(cells, pts, mat.slip)
+    for s_ in range(1, 8):                                  # into plastic flow, on the device
+        new = whole.update_state(m, disp(deps * s_), params, dt)
+        params = [new[0].cpu().numpy(), new[1].cpu().numpy(), new[2].cpu().numpy(), params[3]]
+    sol = disp(deps * 8)
+    res_g, data_g, _ = whole.newton_update(m, sol, params, dt)
+    ip, ix = whole.csr_pattern()
+    ndof = whole.ndof
+    A_g = scipy.sparse.csr_array((data_g.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(ndof, ndof))
+    for world, structured in ((2, True), (3, False)):
+        A_sum = scipy.sparse.csr_array((ndof, ndof))
+        res_sum = np.zeros((len(pts), 3))
+        owners = np.zeros(len(pts), int)
+        for r in range(world):
+            rm = slab_partition_structured(N, world, r) if structured else partition_cells(cells, pts, world, r)
+            plan = Plan(rm.cells, rm.points, mat.slip)
+            plan.set_active_cells(rm.n_owned_cells)
+            own_c = rm.cell_gid[:rm.n_owned_cells]
+            st = [v[own_c] for v in params]
+            res, data, _ = plan.newton_update(m, sol[rm.node_gid], st, dt)
+            lp, lx = plan.csr_pattern()
+            lp, lx, d = lp.cpu().numpy(), lx.cpu().numpy().astype(np.int64), data.cpu().numpy()
+            rows = np.repeat(np.arange(plan.ndof), np.diff(lp))
+            gdof = lambda l: 3 * rm.node_gid[l // 3] + l % 3
+            A_sum = A_sum + scipy.sparse.csr_array((d, (gdof(rows), gdof(lx))), shape=(ndof, ndof))
+            res_sum[rm.node_gid] += res.cpu().numpy()
+            owners[rm.node_gid[rm.owned_node_mask]] += 1
+        assert (owners == 1).all()
+        diff = (A_sum - A_g)
+        assert np.abs(diff.data).max() < 1e-12 * np.abs(A_g.data).max()
+        assert np.abs(res_sum - res_g.cpu().numpy()).max() < 1e-12 * np.abs(A_g.data).max()
+
+
+def test_error_and_status_conventions():
+    """Boundary behaviour (SURVEY 8(b) 'Error conventions'): hard errors are negative return codes with a message and no
+    abort; soft conditions are counted in the 4-word status (points at the iteration cap, non-finite results, max and
+    total local Newton iterations)."""
+    import ctypes
+    from cpfem_b200 import Plan, _lib, make_material
+    from cpfem_b200._lib import CpfemError
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('304steel', N=2, steps=6)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    m = _mat(mat)
+    L = _lib.lib()
+    # hard errors
+    assert L.cpfem_newton_update(plan._h, None, None, None, 0.1, None, None, None, None, None) < 0
+    assert b'null' in L.cpfem_last_error()
+    with pytest.raises(CpfemError):
+        Plan(fe.cells, fe.points, mat.slip[:5])                       # ns must be 12 or 24
+    bad = fe.cells.copy()
+    bad[0, 0] = len(fe.points) + 3
+    with pytest.raises(CpfemError):
+        Plan(bad, fe.points, mat.slip)                                # node index out of range
+    with pytest.raises(CpfemError):
+        plan.set_active_cells(plan.nc + 1)
+    with pytest.raises(CpfemError):
+        plan.update_state(make_material(mat.C11, mat.C12, mat.C44, mat.h, mat.t_sat, mat.gss_a, mat.xm, mat.r, mat.ao, mat.tol, 0),
+                          sol, params, dt)                            # max_sub_step < 1
+    # soft conditions: iteration cap
+    st = plan.new_status()
+    capped = make_material(mat.C11, mat.C12, mat.C44, mat.h, mat.t_sat, mat.gss_a, mat.xm, mat.r, mat.ao, mat.tol, mat.max_sub_step, 3)
+    plan.update_state(capped, sol, params, dt, status=st)
+    assert int(st[0]) > 0 and int(st[2]) == 3 and int(st[1]) == 0
+    # ... and non-finite input: one poisoned node -> its 8 x 8 quadrature points report non-finite, nobody else
+    st = plan.new_status()
+    bad_sol = np.array(sol)
+    bad_sol[13, 1] = np.nan                                            # centre node of the 2^3 mesh touches all 8 cells
+    new = plan.update_state(m, bad_sol, params, dt, status=st)
+    assert int(st[1]) == 64 and int(st[0]) == 0
+    st = plan.new_status()
+    ok = plan.update_state(m, sol, params, dt, status=st)
+    assert int(st[0]) == 0 and int(st[1]) == 0 and int(st[2]) > 3 and int(st[3]) >= int(st[2])
+    assert bool(torch.isfinite(ok[0]).all())
+
+
 def test_full_size_properties():
     """Size-independent properties on a mesh the oracle cannot follow (64^3, 2.1 M points): the residual of a rigid
     translation of the converged field is unchanged, the tangent annihilates rigid translations, CSR row sums of the

