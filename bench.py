@@ -34,14 +34,14 @@ F_UPDATE_FIXED = 1600.0     # set-up: Schmid rotation, B = F A M, hardening
 F_ITER = 5000.0             # one local Newton iteration incl. one line-search residual evaluation
 F_ASSEMBLY_FIXED = 16600.0  # set-up + consistent tangent (10 k) + element K_e share (5 k)
 # executed by this implementation (6x6 symmetric crystal-frame form, active-set slip processing, factored tangent):
-# 2 x FP64 thread instructions per point from ncu (profiles/r1/h_ncu_summary_n64.txt: dfma + dmul + dadd per cycle x cycles)
+# 2 x FP64 thread instructions per point from ncu (profiles/r1/k_ncu_summary_n64.txt: dfma + dmul + dadd per cycle x cycles)
 X_UPDATE_FIXED = 3000.0     # kinematics, frame change, 1/g, first residual, state update (~1.5 k instructions)
 X_ITER = 1860.0             # per local Newton iteration: ~0.93 k instructions (matrix over the active systems + LU + solve
                             # + 1.8 residual evaluations), x 2
 X_ASSEMBLY_FIXED = 12800.0  # update fixed part + factored tangent (2.5 k instr) + element K_e (2.4 k instr), x 2
 B_UPDATE = 610.0            # bytes/point: state in 336 + state out 264 + mesh/sol share 10
 B_ASSEMBLY = 2180.0         # bytes/point: state 240 + mesh/sol 10 + CSR memset 244 + CSR RMW 244 + scratch 2 x 720
-TRAFFIC_UPDATE_B_PER_POINT = 594.0   # ncu dram__bytes_read + write per point, k_update_state at 64^3 (profiles/r1/h_*)
+TRAFFIC_UPDATE_B_PER_POINT = 592.0   # ncu dram__bytes_read + write per point, k_update_state at 64^3 (profiles/r1/k_ncu_summary_n64.txt)
 
 MESH_N = 200
 D_EPS, DT, PRE_STEPS = 2e-4, 2e-3, 10
@@ -420,7 +420,7 @@ def main():
     roof = {'bound': 'fp64', 'kernel': 'k_update_state<12,119>', 'achieved': tf(f_upd, upd_s), 'peak': fp64_peak,
             'unit': 'TFLOP/s', 'frac': tf(f_upd, upd_s) / fp64_peak,
             'traffic': TRAFFIC_UPDATE_B_PER_POINT * pts_rank,
-            'traffic_source': 'ncu --set full at 64^3 (profiles/r1): dram read+write = 600 B/point, scaled to this launch; '
+            'traffic_source': 'ncu --set full at 64^3 (profiles/r1/k_ncu_summary_n64.txt): dram read+write = 592 B/point, scaled to this launch; '
                               'algorithmic bytes 610 B/point',
             'peak_source': 'DFMA microbenchmark (cpfem_dfma_peak_kernel) measured in this run = 148 SMs x 64 DFMA/clk x SM clock; '
                            'MEASURED_PEAKS.json has no FP64 entry',
@@ -428,7 +428,7 @@ def main():
             'mean_local_newton_iters': k_mean_u,
             'executed': {'flops_per_point': x_upd, 'achieved': tf(x_upd, upd_s), 'frac': tf(x_upd, upd_s) / fp64_peak,
                          'model': '2 x FP64 instructions/point of the 6x6 crystal-frame form with active-set slip processing: '
-                                  '3.0 k + k x 1.86 k (ncu, profiles/r1/h_*); ncu sm__pipe_fp64_cycles_active = 56 % at 64^3'},
+                                  '3.0 k + k x 1.86 k (ncu, profiles/r1/k_*); ncu sm__pipe_fp64_cycles_active = 60 % at 64^3'},
             'hbm': {'achieved': pts_rank * B_UPDATE / upd_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': pts_rank * B_UPDATE / upd_s / 1e9 / hbm_peak, 'bytes_per_point': B_UPDATE, 'peak_source': hbm_src},
             'note': 'arithmetic intensity ~%.0f flop/B >> B200 balance (~5.5): the FP64 pipe is the bound, not HBM or tensor '
