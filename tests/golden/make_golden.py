@@ -79,5 +79,24 @@ def vtu_fixtures(nsteps=8):
     print('wrote steel304_vtu.npz, dpsteel_vtu.npz, quat_dp.txt')
 
 
+def case4_fixture():
+    """calibration_case4 (304 steel, 20^3 cells / 50 grains; calibration_case4_UQ_polyCrystalSteel_1D_GB.py:100-230): the
+    Neper mesh n50-id0.msh is exactly the structured box (checked here), so the fixture is the grain id of every cell +
+    the 50 quaternions; the known answer is steel304_uq_zz_curve.txt (copied above)."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(HERE, '..', '..', 'jax-cpfem_b200'))
+    from cpfem_b200.generate_mesh import read_gmsh22_hex, box_mesh
+    m = read_gmsh22_hex(os.path.join(REF, 'calibration/data/neper/calibration_case4/UQ/n50-id0.msh'))
+    L = m.points.max(0)
+    b = box_mesh(20, 20, 20, *L)
+    assert np.allclose(b.points, m.points, atol=1e-12) and np.array_equal(b.cells_dict['hexahedron'], m.cells_dict['hexahedron'])
+    quat = np.loadtxt(os.path.join(REF, 'calibration/data/csv/calibration_case4/quat.txt'))[:50, 1:]
+    np.savez_compressed(os.path.join(HERE, 'steel304_case4.npz'), cell_grain_inds=(m.cell_data['gmsh:physical'][0] - 1).astype(np.int8),
+                        quat=quat, L=L)
+    print('wrote steel304_case4.npz')
+
+
 if __name__ == '__main__':
     vtu_fixtures()
+    case4_fixture()
