@@ -75,6 +75,14 @@ def vtu_fixtures(nsteps=8):
                         C11=v[0]['C11'].astype(np.float64), C12=v[0]['C12'].astype(np.float64), C44=v[0]['C44'].astype(np.float64),
                         sol=np.stack([x['sol'] for x in v]), sigma_zz=np.stack([x['sigma_zz'] for x in v]),
                         sigma_xx=np.stack([x['sigma_xx'] for x in v]), sigma_yy=np.stack([x['sigma_yy'] for x in v]))
+    # tantalum_vtu.npz <- singlecrystal_tantalum/data/vtk/singlecrystal_tantalum/u_000..007.vtu (10^3 cells, BCC12, quat = identity,
+    #                     driver singlecrystal_tantalum/singlecrystal_tantalum.py:65-251)
+    dta = os.path.join(REF, 'singlecrystal_tantalum/data/vtk/singlecrystal_tantalum')
+    v = [read_vtu(os.path.join(dta, f'u_{k:03d}.vtu')) for k in range(nsteps)]
+    np.savez_compressed(os.path.join(HERE, 'tantalum_vtu.npz'),
+                        points=v[0]['Points'], cells=v[0]['connectivity'].reshape(-1, 8).astype(np.int32),
+                        sol=np.stack([x['sol'] for x in v]), sigma_zz=np.stack([x['sigma_zz'] for x in v]),
+                        sigma_xx=np.stack([x['sigma_xx'] for x in v]))
     shutil.copyfile(os.path.join(REF, 'polycrystal_DPsteel/data/csv/polycrystal_DPsteel/quat.txt'), os.path.join(HERE, 'quat_dp.txt'))
     print('wrote steel304_vtu.npz, dpsteel_vtu.npz, quat_dp.txt')
 
