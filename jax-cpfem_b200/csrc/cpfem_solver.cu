@@ -19,7 +19,8 @@
 // Reductions are deterministic: per-block partial sums in a fixed order, the last block to arrive adds them up and
 // runs the scalar recurrences (alpha, omega, beta, breakdown codes, convergence flag) on the device; the host only
 // polls the convergence flag every few iterations, converged iterations are no-ops, so the iterates do not depend on
-// the polling interval.
+// the polling interval.  Eight iterations (40 kernel launches) are captured once per plan into a CUDA graph and replayed:
+// on the meshes of the reference's own drivers the iteration is launch-bound.
 #include <math.h>
 #include <stdio.h>
 #include <new>
@@ -37,8 +38,10 @@ struct BicgScal {
     unsigned int pad;
 };
 
+// Every pointer a BiCGStab iteration touches.  The iteration kernels read this block from DEVICE memory (one uniform load
+// each), so that the captured CUDA graph of the iteration does not depend on the caller's buffers.
 struct BicgVecs {
-    const double *b, *minv;
+    const double *data, *b, *minv;
     double *x, *r, *rhat, *p, *q, *phat, *s, *shat, *t;
 };
 
@@ -101,12 +104,15 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* partials, u
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(RED_BLOCK, SPMV_MIN_BLOCKS)
-k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr, const double* __restrict__ data,
-            int64_t nn, BicgScal* sc, double* partials, BicgVecs V, const double* __restrict__ vin, double* __restrict__ vout,
-            double tol, double atol, long long maxiter) {
+k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr, const double* __restrict__ data_arg,
+            int64_t nn, BicgScal* sc, double* partials, const BicgVecs* __restrict__ Vp, const double* __restrict__ vin,
+            double* __restrict__ vout, double tol, double atol, long long maxiter) {
     if (MODE == 1 || MODE == 2) {
         if (sc->done) return;
     }
+    BicgVecs V = {};
+    if (MODE != 3) V = *Vp;
+    const double* __restrict__ data = (MODE == 3) ? data_arg : V.data;
     const double* __restrict__ xin = (MODE == 0) ? V.x : (MODE == 1) ? V.phat : (MODE == 2) ? V.shat : vin;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * RED_BLOCK + threadIdx.x) >> 5;
@@ -186,8 +192,9 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
 // MODE 2: x += alpha_ phat (+ omega_ shat) ; r = s (- omega_ t) ; rs = <r,r> ; rho_next = <rhat, r> ; k, breakdown, done
 template <int MODE>
 __global__ void __launch_bounds__(RED_BLOCK)
-k_bicg_vec(int64_t n, BicgScal* sc, double* partials, BicgVecs V) {
+k_bicg_vec(int64_t n, BicgScal* sc, double* partials, const BicgVecs* __restrict__ Vp) {
     if (sc->done) return;
+    const BicgVecs V = *Vp;
     const int64_t i0 = (int64_t)blockIdx.x * RED_BLOCK + threadIdx.x, st = (int64_t)gridDim.x * RED_BLOCK;
     double acc[2] = {0.0, 0.0};
     if (MODE == 0) {
@@ -272,12 +279,18 @@ k_norm2_diff(const double* __restrict__ a, const double* __restrict__ b, int64_t
 // -----------------------------------------------------------------------------------------------
 // workspace (plan-owned, allocated on first use)
 // -----------------------------------------------------------------------------------------------
+#define BICG_GRAPH_ITERS 8
 struct cpfem_solver_ws {
     int64_t n = 0;
     double* vec = nullptr;         // 8 vectors of n + minv
     BicgScal* sc = nullptr;
     double* partials = nullptr;
     BicgScal* host_sc = nullptr;   // pinned
+    BicgVecs* dV = nullptr;        // device copy of the pointer block
+    BicgVecs* hV = nullptr;        // pinned staging copy
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t iter_graph = nullptr;    // BICG_GRAPH_ITERS iterations = 5 x BICG_GRAPH_ITERS kernel nodes
+    bool graph_failed = false;
 };
 
 static int ws_get(cpfem_plan* p, cpfem_solver_ws** out) {
@@ -289,10 +302,13 @@ static int ws_get(cpfem_plan* p, cpfem_solver_ws** out) {
         if (e == cudaSuccess) e = cudaMalloc((void**)&w->sc, sizeof(BicgScal));
         if (e == cudaSuccess) e = cudaMalloc((void**)&w->partials, sizeof(double) * 2 * MAX_PARTIAL_BLOCKS);
         if (e == cudaSuccess) e = cudaMallocHost((void**)&w->host_sc, sizeof(BicgScal));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&w->dV, sizeof(BicgVecs));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&w->hV, sizeof(BicgVecs));
         if (e == cudaSuccess) e = cudaMemset(w->sc, 0, sizeof(BicgScal));
         if (e != cudaSuccess) {
-            cudaFree(w->vec); cudaFree(w->sc); cudaFree(w->partials);
+            cudaFree(w->vec); cudaFree(w->sc); cudaFree(w->partials); cudaFree(w->dV);
             if (w->host_sc) cudaFreeHost(w->host_sc);
+            if (w->hV) cudaFreeHost(w->hV);
             delete w;
             return set_err(-2, "solver workspace allocation", e);
         }
@@ -304,8 +320,11 @@ static int ws_get(cpfem_plan* p, cpfem_solver_ws** out) {
 void cpfem_solver_ws_free(void* ws) {
     cpfem_solver_ws* w = (cpfem_solver_ws*)ws;
     if (!w) return;
-    cudaFree(w->vec); cudaFree(w->sc); cudaFree(w->partials);
+    cudaFree(w->vec); cudaFree(w->sc); cudaFree(w->partials); cudaFree(w->dV);
     if (w->host_sc) cudaFreeHost(w->host_sc);
+    if (w->hV) cudaFreeHost(w->hV);
+    if (w->iter_graph) cudaGraphExecDestroy(w->iter_graph);
+    if (w->cap_stream) cudaStreamDestroy(w->cap_stream);
     delete w;
 }
 
@@ -326,9 +345,8 @@ static unsigned vec_grid(const cpfem_plan* p, int64_t n) {
 
 extern "C" int cpfem_spmv(const cpfem_plan* plan, const double* csr_data, const double* x, double* y, void* stream_) {
     if (!plan || !csr_data || !x || !y) return set_err(-1, "cpfem_spmv: null argument");
-    BicgVecs V = {};
     k_bicg_spmv<3><<<spmv_grid(plan), RED_BLOCK, 0, (cudaStream_t)stream_>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, nullptr,
-                                                                           nullptr, V, x, y, 0.0, 0.0, 0);
+                                                                           nullptr, nullptr, x, y, 0.0, 0.0, 0);
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -341,6 +359,40 @@ extern "C" int cpfem_csr_diagonal(const cpfem_plan* plan, const double* csr_data
     return 0;
 }
 
+// one BiCGStab iteration = five kernels (body_fun of _bicgstab_solve)
+static void launch_iteration(const cpfem_plan* plan, cpfem_solver_ws* w, unsigned gs, unsigned gv, cudaStream_t stream) {
+    k_bicg_vec<0><<<gv, RED_BLOCK, 0, stream>>>(w->n, w->sc, w->partials, w->dV);
+    k_bicg_spmv<1><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, nullptr, plan->nn, w->sc, w->partials, w->dV, nullptr, nullptr,
+                                                0.0, 0.0, 0);
+    k_bicg_vec<1><<<gv, RED_BLOCK, 0, stream>>>(w->n, w->sc, w->partials, w->dV);
+    k_bicg_spmv<2><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, nullptr, plan->nn, w->sc, w->partials, w->dV, nullptr, nullptr,
+                                                0.0, 0.0, 0);
+    k_bicg_vec<2><<<gv, RED_BLOCK, 0, stream>>>(w->n, w->sc, w->partials, w->dV);
+}
+
+// The iteration is launch-bound on the meshes of the reference's own drivers (10^3 ... 25^3 cells: tens of microseconds
+// of work per kernel), so BICG_GRAPH_ITERS iterations are captured once per plan into a CUDA graph (40 kernel nodes)
+// and replayed; every kernel checks the device-side `done` flag first, so replaying past convergence changes nothing.
+static cudaGraphExec_t iteration_graph(const cpfem_plan* plan, cpfem_solver_ws* w, unsigned gs, unsigned gv) {
+    if (w->iter_graph || w->graph_failed) return w->iter_graph;
+    cudaGraph_t g = nullptr;
+    bool ok = true;
+    if (!w->cap_stream) ok = cudaStreamCreateWithFlags(&w->cap_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) ok = cudaStreamBeginCapture(w->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        for (int it = 0; it < BICG_GRAPH_ITERS; ++it) launch_iteration(plan, w, gs, gv, w->cap_stream);
+        ok = cudaStreamEndCapture(w->cap_stream, &g) == cudaSuccess && g != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&w->iter_graph, g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    if (!ok) {
+        cudaGetLastError();            // clear; fall back to plain launches
+        w->iter_graph = nullptr;
+        w->graph_failed = true;
+    }
+    return w->iter_graph;
+}
+
 extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const double* b, double* x, int32_t precond,
                               double tol, double atol, int64_t maxiter, int64_t* info, double* resid, void* stream_) {
     if (!plan || !csr_data || !b || !x) return set_err(-1, "cpfem_bicgstab: null argument");
@@ -350,36 +402,37 @@ extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const do
     if (rc) return rc;
     const int64_t n = w->n;
     BicgVecs V;
-    V.b = b; V.x = x;
+    V.data = csr_data; V.b = b; V.x = x;
     V.r = w->vec; V.rhat = w->vec + n; V.p = w->vec + 2 * n; V.q = w->vec + 3 * n; V.phat = w->vec + 4 * n;
     V.s = w->vec + 5 * n; V.shat = w->vec + 6 * n; V.t = w->vec + 7 * n;
     double* minv = w->vec + 8 * n;
     V.minv = precond ? minv : nullptr;
+    *w->hV = V;
+    CU_TRY(cudaMemcpyAsync(w->dV, w->hV, sizeof(BicgVecs), cudaMemcpyHostToDevice, stream));
     const unsigned gs = spmv_grid(plan), gv = vec_grid(plan, n);
     if (precond) {
         k_csr_diag<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, minv, 1);
     }
-    k_bicg_spmv<0><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, w->sc, w->partials, V, nullptr, nullptr,
+    k_bicg_spmv<0><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, nullptr, plan->nn, w->sc, w->partials, w->dV, nullptr, nullptr,
                                                 tol, atol, (long long)maxiter);
     CU_TRY(cudaGetLastError());
-    // the host polls the device-side flag; the interval grows so that small systems do not pay a sync per iteration
+    cudaGraphExec_t graph = iteration_graph(plan, w, gs, gv);
+    // the host polls the device-side flag between batches of iterations (the flag also covers k >= maxiter)
     int64_t launched = 0;
-    int poll = 4;
+    int batches = 1;
     for (;;) {
         CU_TRY(cudaMemcpyAsync(w->host_sc, w->sc, sizeof(BicgScal), cudaMemcpyDeviceToHost, stream));
-        CU_TRY(cudaStreamSynchronize(stream));
-        if (w->host_sc->done || launched >= maxiter) break;
-        for (int it = 0; it < poll && launched < maxiter; ++it, ++launched) {
-            k_bicg_vec<0><<<gv, RED_BLOCK, 0, stream>>>(n, w->sc, w->partials, V);
-            k_bicg_spmv<1><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, w->sc, w->partials, V, nullptr,
-                                                        nullptr, 0.0, 0.0, 0);
-            k_bicg_vec<1><<<gv, RED_BLOCK, 0, stream>>>(n, w->sc, w->partials, V);
-            k_bicg_spmv<2><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, w->sc, w->partials, V, nullptr,
-                                                        nullptr, 0.0, 0.0, 0);
-            k_bicg_vec<2><<<gv, RED_BLOCK, 0, stream>>>(n, w->sc, w->partials, V);
+        CU_TRY(cudaStreamSynchronize(stream));      // also guarantees hV was consumed before the next call rewrites it
+        if (w->host_sc->done || launched >= maxiter + BICG_GRAPH_ITERS) break;
+        for (int bi = 0; bi < batches; ++bi, launched += BICG_GRAPH_ITERS) {
+            if (graph) {
+                CU_TRY(cudaGraphLaunch(graph, stream));
+            } else {
+                for (int it = 0; it < BICG_GRAPH_ITERS; ++it) launch_iteration(plan, w, gs, gv, stream);
+            }
         }
         CU_TRY(cudaGetLastError());
-        if (poll < 32) poll *= 2;
+        if (batches < 8) batches *= 2;
     }
     if (info) {
         info[0] = w->host_sc->k;                                   // iterations taken (negative: breakdown code of JAX)
@@ -387,7 +440,7 @@ extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const do
     }
     if (resid) {
         // ||A x - b|| as jax_solve checks it (solver.py:43-45): one more SpMV into the t vector
-        k_bicg_spmv<3><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, nullptr, nullptr, V, x, V.t, 0.0, 0.0, 0);
+        k_bicg_spmv<3><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, nullptr, nullptr, nullptr, x, V.t, 0.0, 0.0, 0);
         k_norm2_diff<<<gv, RED_BLOCK, 0, stream>>>(V.t, b, n, w->sc, w->partials);
         CU_TRY(cudaMemcpyAsync(w->host_sc, w->sc, sizeof(BicgScal), cudaMemcpyDeviceToHost, stream));
         CU_TRY(cudaStreamSynchronize(stream));
