@@ -174,3 +174,22 @@ def test_oracle_vs_dp_steel_vtu():
         assert np.abs(sol - g['sol'][i]).max() < 1e-6 * np.abs(g['sol'][i]).max()
         assert np.abs(sg[:, 2, 2] - g['sigma_zz'][i]).max() < 1e-6 * np.abs(g['sigma_zz'][i]).max()
         assert np.abs(sg[:, 0, 0] - g['sigma_xx'][i]).max() < 1e-6 * np.abs(g['sigma_zz'][i]).max()
+
+
+@pytest.mark.parametrize('name', ['304steel', 'tantalum'])
+def test_point_algebra_statistics(name, hostcheck):
+    """A larger seeded sample (6000 point-evaluations per material): every result within 1e-10 of the oracle; the
+    iteration / evaluation counts agree except at the rare points where a line-search or convergence comparison is
+    decided in the last bit (observed 1e-4 of the points over 120 k evaluations, results there still within 3e-11)."""
+    worst, mism, tot = 0.0, 0, 0
+    for step, mat, dt, H, A, g, sl, R in cases.point_history(name, n=600, steps=10, seed=1):
+        pb = O.PointBatch(A, g, sl, R, mat)
+        y, it_o, ev_o = pb.newton_solver(H, dt, return_iters=True)
+        P_o, T_o = pb.first_PK_stress(H, dt, y).numpy(), pb.tangent(H, dt, y).numpy()
+        An_o, gn_o, sn_o = [v.numpy() for v in pb.update_int_vars(H, dt, y)]
+        P_h, T_h, An_h, gn_h, sn_h, info = hostcheck_build.evaluate(hostcheck, mat, dt, H, A, g, sl, R, pown=cases.RATE_POWN[name])
+        mism += int(((info[:, 0] != it_o.numpy()) | (info[:, 1] != ev_o.numpy())).sum())
+        tot += len(H)
+        worst = max(worst, cases.relerr(P_h, P_o), cases.relerr(T_h, T_o), cases.relerr(An_h, An_o), cases.relerr(gn_h, gn_o))
+    assert worst < 1e-10
+    assert mism <= max(2, tot // 1000)
