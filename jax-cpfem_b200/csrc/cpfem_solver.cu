@@ -123,6 +123,13 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
         const int m = (int)(nbr_ptr[n + 1] - b0);
         const int m3 = 3 * m;
         const double* __restrict__ base = data + 9 * b0;
+        // the vector entry the epilogue of lanes 0..2 needs (b, rhat or s of this node's rows) is requested up front, so
+        // that its latency hides under the matrix loads instead of trailing the warp reduction
+        double aux = 0.0;
+        if (MODE != 3 && lane < 3) {
+            const double* __restrict__ av = (MODE == 0) ? V.b : (MODE == 1) ? (const double*)V.rhat : (const double*)V.s;
+            aux = av[3 * n + lane];
+        }
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         // lane j takes neighbour j: its three x entries once, then the 3 x 3 block of the node's rows.  For a fixed (i, k)
         // the lanes read with a 24-byte stride; the three k-loads of a row hit the same sectors (L1), so every sector
@@ -148,17 +155,17 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
             const double y = (lane == 0) ? s0 : (lane == 1) ? s1 : s2;
             const int64_t row = 3 * n + lane;
             if (MODE == 0) {
-                const double bb = V.b[row];
+                const double bb = aux;
                 const double rr = bb - y;
                 V.r[row] = rr; V.rhat[row] = rr; V.p[row] = rr; V.q[row] = rr;
                 acc[0] += rr * rr;
                 acc[1] += bb * bb;
             } else if (MODE == 1) {
                 V.q[row] = y;
-                acc[0] += V.rhat[row] * y;
+                acc[0] += aux * y;
             } else if (MODE == 2) {
                 V.t[row] = y;
-                acc[0] += y * V.s[row];
+                acc[0] += y * aux;
                 acc[1] += y * y;
             } else {
                 vout[row] = y;
