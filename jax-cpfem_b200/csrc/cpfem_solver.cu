@@ -23,6 +23,7 @@
 // on the meshes of the reference's own drivers the iteration is launch-bound.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <new>
 
 #include "cpfem_internal.h"
@@ -118,9 +119,20 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
     const int64_t warp0 = ((int64_t)blockIdx.x * RED_BLOCK + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * RED_BLOCK) >> 5;
     double acc[2] = {0.0, 0.0};
+    // The index data of a node (its two nbr_ptr entries, then the neighbour id of every lane) sit in front of the x gather
+    // in a chain of three dependent memory latencies.  They are fetched ONE NODE AHEAD: while the matrix loads of node n
+    // are in flight the warp already holds (b0, m, col) of node n and requests those of node n + nwarps.
+    int64_t b0 = 0;
+    int m = 0, col = 0;
+    if (warp0 < nn) {
+        b0 = nbr_ptr[warp0];
+        m = (int)(nbr_ptr[warp0 + 1] - b0);
+        col = (lane < m) ? nbr[b0 + lane] : 0;
+    }
     for (int64_t n = warp0; n < nn; n += nwarps) {
-        const int64_t b0 = nbr_ptr[n];
-        const int m = (int)(nbr_ptr[n + 1] - b0);
+        const int64_t nxt = n + nwarps;
+        int64_t b0n = 0, e0n = 0;
+        if (nxt < nn) { b0n = nbr_ptr[nxt]; e0n = nbr_ptr[nxt + 1]; }
         const int m3 = 3 * m;
         const double* __restrict__ base = data + 9 * b0;
         // the vector entry the epilogue of lanes 0..2 needs (b, rhat or s of this node's rows) is requested up front, so
@@ -134,17 +146,28 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
         // lane j takes neighbour j: its three x entries once, then the 3 x 3 block of the node's rows.  For a fixed (i, k)
         // the lanes read with a 24-byte stride; the three k-loads of a row hit the same sectors (L1), so every sector
         // of the matrix still crosses L2/HBM exactly once, and there is no index arithmetic beyond one multiply-add.
-        for (int j = lane; j < m; j += 32) {
-            const double* __restrict__ xp = xin + 3 * (int64_t)nbr[b0 + j];
-            const double* __restrict__ ap = base + 3 * j;
+        if (lane < m) {
+            const double* __restrict__ xp = xin + 3 * (int64_t)col;
+            const double* __restrict__ ap = base + 3 * lane;
             const double a00 = __ldcs(ap), a01 = __ldcs(ap + 1), a02 = __ldcs(ap + 2);
             const double a10 = __ldcs(ap + m3), a11 = __ldcs(ap + m3 + 1), a12 = __ldcs(ap + m3 + 2);
             const double a20 = __ldcs(ap + 2 * m3), a21 = __ldcs(ap + 2 * m3 + 1), a22 = __ldcs(ap + 2 * m3 + 2);
             const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
-            s0 += a00 * x0 + a01 * x1 + a02 * x2;
-            s1 += a10 * x0 + a11 * x1 + a12 * x2;
-            s2 += a20 * x0 + a21 * x1 + a22 * x2;
+            s0 = a00 * x0 + a01 * x1 + a02 * x2;
+            s1 = a10 * x0 + a11 * x1 + a12 * x2;
+            s2 = a20 * x0 + a21 * x1 + a22 * x2;
         }
+        for (int j = lane + 32; j < m; j += 32) {                  // m > 32 (unstructured meshes): the remaining neighbours
+            const double* __restrict__ xp = xin + 3 * (int64_t)nbr[b0 + j];
+            const double* __restrict__ ap = base + 3 * j;
+            const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
+            s0 += __ldcs(ap) * x0 + __ldcs(ap + 1) * x1 + __ldcs(ap + 2) * x2;
+            s1 += __ldcs(ap + m3) * x0 + __ldcs(ap + m3 + 1) * x1 + __ldcs(ap + m3 + 2) * x2;
+            s2 += __ldcs(ap + 2 * m3) * x0 + __ldcs(ap + 2 * m3 + 1) * x1 + __ldcs(ap + 2 * m3 + 2) * x2;
+        }
+        // next node's neighbour ids: b0n has arrived by now (it was requested before the matrix loads were)
+        const int mn = (int)(e0n - b0n);
+        const int coln = (lane < mn) ? nbr[b0n + lane] : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -171,6 +194,7 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
                 vout[row] = y;
             }
         }
+        b0 = b0n; m = mn; col = coln;
     }
     if (MODE == 3) return;
     double tot2[2];
@@ -441,6 +465,10 @@ extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const do
         CU_TRY(cudaGetLastError());
         if (batches < 8) batches *= 2;
     }
+    if ((w->host_sc->k < 0 || getenv("CPFEM_DEBUG_BICG_ALL")) && getenv("CPFEM_DEBUG_BICG"))
+        fprintf(stderr, "bicgstab breakdown k=%lld rho=%.17g rho_=%.17g alpha=%.17g alpha_=%.17g omega=%.17g omega_=%.17g ss=%.17g rs=%.17g atol2=%.17g\n",
+                w->host_sc->k, w->host_sc->rho, w->host_sc->rho_, w->host_sc->alpha, w->host_sc->alpha_, w->host_sc->omega,
+                w->host_sc->omega_, w->host_sc->ss, w->host_sc->rs, w->host_sc->atol2);
     if (info) {
         info[0] = w->host_sc->k;                                   // iterations taken (negative: breakdown code of JAX)
         info[1] = (w->host_sc->rs > w->host_sc->atol2) ? 1 : 0;    // 1 = stopped without reaching the tolerance
