@@ -27,7 +27,8 @@ def test_dp_steel_vtu_series():
     """polycrystal_DPsteel_inhomo.py:78-260 (10^3 cells, BCC24, per-phase parameters, line search on).  The VTUs were
     written by a revision whose elastic constants are swapped between the phases: the per-cell
     C11/C12/C44 fields of the files are used as they are; orientation ids 7..19 clamp to quaternion row 7 (App. H.2).
-    VTU data are float32: tolerance 1e-6 relative to the field maximum."""
+    VTU data are float32 (6e-8): observed agreement 5.7e-8 over all 50 committed steps (profiles/r1/k_long_replay.txt),
+    tolerance 2e-7 relative to the field maximum."""
     import torch
     from cpfem_b200.generate_mesh import Mesh
     from cpfem_b200.models_DPsteel_inhomo import CrystalPlasticity
@@ -61,10 +62,10 @@ def test_dp_steel_vtu_series():
         sg = problem.compute_avg_stress(sol, params).cpu().numpy()
         params = problem.update_int_vars_gp(sol, params)
         s_ref = g['sol'][i].astype(np.float64)
-        assert np.abs(sol.cpu().numpy() - s_ref).max() < 1e-6 * np.abs(s_ref).max(), i
+        assert np.abs(sol.cpu().numpy() - s_ref).max() < 2e-7 * np.abs(s_ref).max(), i
         for comp, name in ((2, 'sigma_zz'), (0, 'sigma_xx'), (1, 'sigma_yy')):
             ref = g[name][i].astype(np.float64)
-            assert np.abs(sg[:, comp, comp] - ref).max() < 1e-6 * np.abs(g['sigma_zz'][i]).max(), (i, name)
+            assert np.abs(sg[:, comp, comp] - ref).max() < 2e-7 * np.abs(g['sigma_zz'][i]).max(), (i, name)
     assert int(problem.last_status[2]) > 3 and int(problem.last_status[0]) == 0      # plastic flow, no iteration cap hit
 
 
@@ -152,8 +153,8 @@ def test_case4_polycrystal_curve():
 
 def test_tantalum_vtu_series():
     """singlecrystal_tantalum.py:65-251 (10^3 cells, BCC12 {110}<111>, rate exponent 45.2726 -> the kernels' run-time pow()
-    path, single crystal with quat = identity) against the VTU series the reference committed: per-cell sigma_zz to 2e-6
-    (float32 storage + the free rigid rotation of these boundary conditions), mean sigma_zz to 1e-6."""
+    path, single crystal with quat = identity) against the VTU series the reference committed: per-cell sigma_zz to 5e-7,
+    mean sigma_zz to 2e-7 (float32 storage; observed 1.0e-7 / 4.4e-8 over all 50 committed steps)."""
     import torch
     from cpfem_b200.generate_mesh import Mesh
     from cpfem_b200.models_tantalum import CrystalPlasticity
@@ -179,6 +180,6 @@ def test_tantalum_vtu_series():
         sg = problem.compute_avg_stress(sol, params).cpu().numpy()
         params = problem.update_int_vars_gp(sol, params)
         ref = g['sigma_zz'][i].astype(np.float64)
-        assert abs(sg[:, 2, 2].mean() / ref.mean() - 1) < 1e-6, (i, sg[:, 2, 2].mean(), ref.mean())
-        assert np.abs(sg[:, 2, 2] - ref).max() < 2e-6 * np.abs(ref).max(), i
+        assert abs(sg[:, 2, 2].mean() / ref.mean() - 1) < 2e-7, (i, sg[:, 2, 2].mean(), ref.mean())
+        assert np.abs(sg[:, 2, 2] - ref).max() < 5e-7 * np.abs(ref).max(), i
     assert int(problem.last_status[2]) > 3 and int(problem.last_status[0]) == 0
