@@ -280,3 +280,137 @@ class ExchangePlan:
         s = self.owned_sumsq(res).clone()
         dist.all_reduce(s, op=dist.ReduceOp.SUM, group=self.pg)
         return torch.sqrt(s)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# distributed linear solve on the row-partitioned matrix (beyond the reference, whose jax_solve is single-device)
+# ----------------------------------------------------------------------------------------------------------
+class HaloPlan:
+    """Before a sparse matrix-vector product every rank needs the vector entries of the local nodes it does not own
+    (interface nodes of lower ranks, nodes of the ghost cells): `update(v)` fetches them from their owners.  Built once
+    per partition from RankMesh.node_owner / node_gid: each rank tells every owner which global nodes it needs."""
+
+    def __init__(self, rm: RankMesh, device, pg=None):
+        import torch.distributed as dist
+        self.rm, self.pg, self.device = rm, pg, torch.device(device)
+        owner = onp.asarray(rm.node_owner)
+        gid = onp.asarray(rm.node_gid)
+        self.need = {}                                   # peer -> local dof indices I receive (nodes owned by peer)
+        need_gid = {}
+        for p in sorted(set(owner.tolist()) - {rm.rank}):
+            loc = onp.nonzero(owner == p)[0]
+            self.need[int(p)] = _rows_of_nodes(torch.as_tensor(loc, device=self.device))
+            need_gid[int(p)] = torch.as_tensor(gid[loc], device=self.device)
+        # who needs what from me: every rank announces its request sizes to every other rank, then the gid lists
+        world = rm.world
+        sizes = torch.zeros(world, dtype=torch.int64, device=self.device)
+        for p, g in need_gid.items():
+            sizes[p] = g.numel()
+        all_sizes = [torch.zeros(world, dtype=torch.int64, device=self.device) for _ in range(world)]
+        dist.all_gather(all_sizes, sizes, group=pg)
+        wanted = {p: int(all_sizes[p][rm.rank]) for p in range(world) if p != rm.rank and int(all_sizes[p][rm.rank]) > 0}
+        bufs = {p: torch.empty(n, dtype=torch.int64, device=self.device) for p, n in wanted.items()}
+        ops = [dist.P2POp(dist.isend, need_gid[p], p, group=pg) for p in sorted(need_gid)]
+        ops += [dist.P2POp(dist.irecv, bufs[p], p, group=pg) for p in sorted(bufs)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        gid_t = torch.as_tensor(gid, device=self.device)
+        self.give = {}                                   # peer -> local dof indices (nodes I own) whose values I send
+        for p, g in bufs.items():
+            loc = torch.searchsorted(gid_t, g)
+            if not bool((gid_t[loc] == g).all()) or not bool(torch.as_tensor(owner, device=self.device)[loc].eq(rm.rank).all()):
+                raise RuntimeError('HaloPlan: a neighbour requests a node this rank does not own')
+            self.give[p] = _rows_of_nodes(loc)
+        self._recv = {p: torch.empty(idx.numel(), dtype=torch.float64, device=self.device) for p, idx in self.need.items()}
+
+    def update(self, v: torch.Tensor):
+        import torch.distributed as dist
+        ops, keep = [], []
+        for p in sorted(self.give):
+            sb = v[self.give[p]]
+            keep.append(sb)
+            ops.append(dist.P2POp(dist.isend, sb, p, group=self.pg))
+        for p in sorted(self.need):
+            ops.append(dist.P2POp(dist.irecv, self._recv[p], p, group=self.pg))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for p, idx in self.need.items():
+            v[idx] = self._recv[p]
+        return v
+
+
+class DistributedBicgstab:
+    """jax.scipy.sparse.linalg.bicgstab (solver.py:34-40 semantics: x0, Jacobi, tol, atol, maxiter) on a matrix whose rows
+    are partitioned by node owner.  Every rank holds local-length vectors; only the entries of owned rows are meaningful,
+    the others are refreshed by the halo exchange before each matrix-vector product.  Dot products are partial sums over
+    the owned rows + one all-reduce; the recurrence scalars live on every rank identically.
+
+    matvec(v) -> A_local v (local length; rows of non-owned nodes are ignored).  On the GPU that is
+    `lambda v: plan.spmv(csr_data, v)` after ExchangePlan.exchange completed the owned rows."""
+
+    def __init__(self, rm: RankMesh, halo: HaloPlan, pg=None):
+        self.rm, self.halo, self.pg = rm, halo, pg
+        dev = halo.device
+        own = torch.nonzero(torch.as_tensor(rm.owned_node_mask, device=dev)).reshape(-1)
+        self.owned = _rows_of_nodes(own)
+        self.contig = _is_contiguous_range(self.owned)
+        if self.contig and self.owned.numel():
+            self.sl = slice(int(self.owned[0]), int(self.owned[0]) + self.owned.numel())
+
+    def _o(self, v):
+        return v[self.sl] if self.contig else v[self.owned]
+
+    def _allsum(self, *vals):
+        import torch.distributed as dist
+        t = torch.stack(list(vals))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+        return t
+
+    def solve(self, matvec, b, x0=None, minv=None, tol=1e-10, atol=1e-10, maxiter=10000):
+        """Returns (x, k, err): x local-length (owned entries + fresh halo), k iterations (JAX's negative breakdown codes
+        passed through), err = global ||A x - b|| over owned rows."""
+        o = self._o
+        dot = lambda a, c: torch.dot(o(a), o(c))
+        x = torch.zeros_like(b) if x0 is None else x0.clone()
+        M = (lambda v: v) if minv is None else (lambda v: v * minv)
+        bs = float(self._allsum(dot(b, b))[0])
+        atol2 = max(tol ** 2 * bs, atol ** 2)
+        self.halo.update(x)
+        r = b - matvec(x)
+        rhat, p, q = r.clone(), r.clone(), r.clone()
+        rho = alpha = omega = 1.0
+        t2 = self._allsum(dot(r, r), dot(rhat, r))
+        rs, rho_ = float(t2[0]), float(t2[1])
+        k = 0
+        while (rs > atol2) and (k < maxiter) and (k >= 0):
+            beta = rho_ / rho * alpha / omega
+            p = r + beta * (p - omega * q)
+            phat = M(p)
+            self.halo.update(phat)
+            q = matvec(phat)
+            alpha_ = rho_ / float(self._allsum(dot(rhat, q))[0])
+            s = r - alpha_ * q
+            exit_early = float(self._allsum(dot(s, s))[0]) < atol2
+            shat = M(s)
+            self.halo.update(shat)
+            t = matvec(shat)
+            t2 = self._allsum(dot(t, s), dot(t, t))
+            omega_ = float(t2[0]) / float(t2[1])
+            if exit_early:
+                x = x + alpha_ * phat
+                r = s
+            else:
+                x = x + (alpha_ * phat + omega_ * shat)
+                r = s - omega_ * t
+            k_ = -11 if (omega_ == 0 or alpha_ == 0) else k + 1
+            if rho_ == 0:
+                k_ = -10
+            alpha, omega, rho, k = alpha_, omega_, rho_, k_
+            t2 = self._allsum(dot(r, r), dot(rhat, r))
+            rs, rho_ = float(t2[0]), float(t2[1])
+        self.halo.update(x)
+        res = matvec(x) - b
+        err = float(torch.sqrt(self._allsum(dot(res, res))[0]))
+        return x, k, err

@@ -105,3 +105,57 @@ def test_partition_exchange_gloo(world, N, structured):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, port, N, structured, ret), nprocs=world, join=True)
     assert sorted(ret.keys()) == list(range(world))
+
+
+def _solver_worker(rank, world, port, N, structured, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import sys
+        here = os.path.dirname(os.path.abspath(__file__))
+        sys.path[:0] = [os.path.join(here, '..', 'jax-cpfem_b200'), os.path.join(here, '..', 'oracle')]
+        from cpfem_b200 import partition
+        pts, cells = O.box_mesh(N, N, N)
+        rm = partition.slab_partition_structured(N, world, rank) if structured else partition.partition_cells(cells, pts, world, rank)
+        # a global FE-patterned, non-symmetric, diagonally dominant matrix with a few identity (Dirichlet) rows
+        rng = np.random.default_rng(11)
+        Ig, Jg = O.coo_indices(cells)
+        ndof = 3 * len(pts)
+        Ag = scipy.sparse.csr_array((rng.normal(size=len(Ig)), (Ig, Jg)), shape=(ndof, ndof)).tolil()
+        Ag.setdiag(np.abs(Ag).sum(axis=1).ravel() + 1.0)
+        for r_ in range(0, ndof, 17):
+            Ag.rows[r_] = [r_]
+            Ag.data[r_] = [1.0]
+        Ag = Ag.tocsr()
+        bg = rng.normal(size=ndof)
+        x0g = rng.normal(size=ndof) * 0.1
+        gd = (3 * rm.node_gid[:, None] + np.arange(3)[None, :]).reshape(-1)
+        Al = Ag[gd][:, gd].tocsr()                                   # local rows x local columns
+        matvec = lambda v: torch.as_tensor(Al @ v.numpy())
+        halo = partition.HaloPlan(rm, 'cpu')
+        sol = partition.DistributedBicgstab(rm, halo)
+        minv = torch.as_tensor(1.0 / Ag.diagonal()[gd])
+        x, k, err = sol.solve(matvec, torch.as_tensor(bg[gd]), x0=torch.as_tensor(x0g[gd]), minv=minv, tol=1e-10, atol=1e-10, maxiter=500)
+        jac = Ag.diagonal()
+        xo, ko = O.bicgstab_ref(Ag, bg, x0=x0g, M=lambda v: v * (1. / jac), tol=1e-10, atol=1e-10, maxiter=500)
+        own = np.nonzero(rm.owned_node_mask)[0]
+        od = (3 * own[:, None] + np.arange(3)[None, :]).reshape(-1)
+        assert k > 0 and abs(k - ko) <= 2, (k, ko)
+        assert np.abs(x.numpy()[od] - xo[gd][od]).max() < 1e-9 * np.abs(xo).max()
+        assert err < 1e-8 * np.linalg.norm(bg)
+        # the halo of the returned x is fresh: non-owned local entries equal the owners' values
+        assert np.abs(x.numpy() - xo[gd]).max() < 1e-9 * np.abs(xo).max()
+        ret[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,N,structured', [(2, 4, True), (3, 4, False)])
+def test_distributed_bicgstab_gloo(world, N, structured):
+    """Row-partitioned Jacobi-BiCGStab (halo exchange + all-reduced dot products) against the serial restatement of
+    jax.scipy.sparse.linalg.bicgstab on the global system."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_solver_worker, args=(world, port, N, structured, ret), nprocs=world, join=True)
+    assert sorted(ret.keys()) == list(range(world))
