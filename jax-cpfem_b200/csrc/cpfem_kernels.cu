@@ -838,6 +838,9 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
             __syncwarp();                           // GA is dead: the space is the K_e row tile from here on
         }
         const int64_t na = cells[c * 8 + a];
+        // CSR row starts of this lane's three rows: requested here, a whole slice of arithmetic before the scatter needs them
+        long long rp0 = -1, rp1 = -1, rp2 = -1;
+        if (csr_data && valid) { rp0 = indptr[na * 3]; rp1 = indptr[na * 3 + 1]; rp2 = indptr[na * 3 + 2]; }
         if (csr_data) {
             const uint2 rk = *reinterpret_cast<const uint2*>(rank + (c * 8 + a) * 8);
 #pragma unroll
@@ -922,7 +925,7 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
                 double* ke = KE + lane * KE_ROW;
 #pragma unroll
                 for (int j = 0; j < 24; ++j) ke[j] = acc[j];
-                ROWP[lane] = valid ? (long long)indptr[na * 3 + i] : -1LL;
+                ROWP[lane] = (i == 0) ? rp0 : (i == 1) ? rp1 : rp2;
                 __syncwarp();
                 const int jb = (lane < 24) ? lane / 3 : 0, jk = (lane < 24) ? lane - 3 * (lane / 3) : 0;
 #pragma unroll 4
