@@ -154,12 +154,15 @@ class Plan:
               'cpfem_update_state_cells')
         return out
 
-    def update_state_host(self, mat: Material, sol, params, dt, out=None, status=None, chunk_cells=None):
+    def update_state_host(self, mat: Material, sol, params, dt, out=None, status=None, chunk_cells=None, cache_rot=True):
         """update_int_vars_gp for a HOST-resident state (reference layout, torch CPU tensors; pinned memory makes the
         copies asynchronous): the state streams through the device in chunks of `chunk_cells` cells on three streams,
         so that the H2D copy of chunk k+1, the update of chunk k and the D2H copy of chunk k-1 overlap (PCIe is full
         duplex).  `out` = [Fp_inv_new, g_new, slip_new] host tensors (allocated pinned when None).  Returns `out` after
-        synchronising; the per-point material arrays of the DP-steel form (params[4:]) are streamed with the state."""
+        synchronising; the per-point material arrays of the DP-steel form (params[4:]) are streamed with the state.
+        `cache_rot`: rot_mats_gp never changes during a simulation (models_copper.py:282 passes it through), so a device
+        copy is kept between calls - keyed on the host tensor's identity and version counter - and only the 264 B/point
+        that do change cross the bus in each direction."""
         hs = [p if isinstance(p, torch.Tensor) else torch.as_tensor(onp.ascontiguousarray(p, dtype=onp.float64)) for p in params]
         nc = self.nc_active
         if any(h.is_cuda or h.dtype != torch.float64 or not h.is_contiguous() or h.shape[0] != nc for h in hs):
@@ -181,6 +184,13 @@ class Plan:
                 self._host_out = [[torch.empty((cc,) + tuple(h.shape[1:]), dtype=torch.float64, device=self.device) for h in hs[:3]]
                                   for _ in range(nbuf)]
                 self._host_key = key
+            rot_dev = None
+            if cache_rot:
+                rkey = (hs[3].data_ptr(), hs[3]._version, tuple(hs[3].shape))
+                if getattr(self, '_rot_key', None) != rkey:
+                    self._rot_dev = hs[3].to(self.device, non_blocking=True)
+                    self._rot_key = rkey
+                rot_dev = self._rot_dev
             ev_in = [torch.cuda.Event() for _ in range(nbuf)]
             ev_cmp = [torch.cuda.Event() for _ in range(nbuf)]
             ev_out = [torch.cuda.Event() for _ in range(nbuf)]
@@ -197,9 +207,13 @@ class Plan:
                 with torch.cuda.stream(s_in):
                     if k >= nbuf:
                         s_in.wait_event(ev_cmp[b])            # the update that read this input buffer is done
-                    for d, h in zip(din, hs):
+                    for j, (d, h) in enumerate(zip(din, hs)):
+                        if j == 3 and rot_dev is not None:
+                            continue                          # resident on the device already
                         d.copy_(h[c0:c0 + n], non_blocking=True)
                     ev_in[b].record(s_in)
+                if rot_dev is not None:
+                    din = din[:3] + [rot_dev[c0:c0 + n]] + din[4:]
                 cur.wait_event(ev_in[b])
                 if k >= nbuf:
                     cur.wait_event(ev_out[b])                 # the D2H copy that read this output buffer is done

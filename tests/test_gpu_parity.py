@@ -146,6 +146,13 @@ def test_host_streaming_state_update():
         for a, b in zip(new, ref):
             assert not a.is_cuda and torch.equal(a, b)
         assert int(st[0]) == 0 and int(st[3]) > 0
+    # rot_mats is kept on the device between calls (it never changes in a simulation); an edited tensor must be re-read
+    host[3].copy_(host[3][torch.randperm(host[3].shape[0])])          # in-place edit: version counter moves
+    ref2 = [t.cpu() for t in plan.update_state(m, sol, [host[0], host[1], host[2], host[3]], dt)]
+    new2 = plan.update_state_host(m, torch.as_tensor(sol), host, dt, chunk_cells=24)
+    assert all(torch.equal(a, b) for a, b in zip(new2, ref2)) and not torch.equal(new2[0], ref[0])
+    new3 = plan.update_state_host(m, torch.as_tensor(sol), host, dt, chunk_cells=24, cache_rot=False)
+    assert all(torch.equal(a, b) for a, b in zip(new3, ref2))
 
 
 def test_csr_pattern_ragged_and_unstructured():
