@@ -98,20 +98,44 @@ class Plan:
         return self._indptr, self._indices
 
     # ---- helpers -----------------------------------------------------------------------------
-    def _state(self, params: Sequence[torch.Tensor], layout=LAYOUT_AOS):
-        """cpfem_state from the reference's internal_vars list (4, 9 or 10 arrays)."""
+    def _uniform_value(self, t: torch.Tensor):
+        """The value of a per-point parameter array if it is the same at every point, else None.  One reduction + host
+        read per distinct tensor (identity + version counter), remembered afterwards."""
+        key = (t.data_ptr(), t._version, tuple(t.shape))
+        cache = self.__dict__.setdefault('_uniform_cache', {})
+        if key not in cache:
+            if len(cache) > 64:
+                cache.clear()
+            lo, hi = torch.aminmax(t)
+            cache[key] = float(lo) if float(lo) == float(hi) else None
+        return cache[key]
+
+    def _state(self, params: Sequence[torch.Tensor], layout=LAYOUT_AOS, mat: Optional[Material] = None):
+        """cpfem_state from the reference's internal_vars list (4, 9 or 10 arrays).  With `mat` given, per-point parameter
+        arrays that hold one value everywhere (the calibration drivers scale whole arrays, calibration_case4_...py:238-251;
+        DP steel shares the rate sensitivity between its phases) are demoted to scalars of a copy of the material, so the
+        kernels take their uniform-parameter / compile-time-exponent paths; returns (state, tensors, material)."""
         n = len(params)
         if n not in (4, 9, 10):
             raise ValueError('internal_vars must have 4 (uniform), 9 (calibration) or 10 (DP steel) arrays')
         ts = [_dev_f64(p, self.device) for p in params]
         st = State()
         st.Fp_inv, st.g, st.slip, st.rot = (t.data_ptr() for t in ts[:4])
+        m = mat
         if n >= 9:
-            st.gss_a, st.h, st.t_sat, st.xm, st.r = (t.data_ptr() for t in ts[4:9])
+            names = ('gss_a', 'h', 't_sat', 'xm', 'r')
+            vals = [self._uniform_value(t) for t in ts[4:9]] if mat is not None else [None] * 5
+            if any(v is not None for v in vals):
+                m = Material.from_buffer_copy(mat)
+            for name, t, v in zip(names, ts[4:9], vals):
+                if v is None:
+                    setattr(st, name, t.data_ptr())
+                else:
+                    setattr(m, name, v)
         if n == 10:
             st.C = ts[9].data_ptr()
         st.layout = layout
-        return st, ts
+        return (st, ts) if mat is None else (st, ts, m)
 
     def new_status(self):
         return torch.zeros(4, dtype=torch.int64, device=self.device)
@@ -120,7 +144,7 @@ class Plan:
     def update_state(self, mat: Material, sol, params, dt, out=None, status=None, layout=LAYOUT_AOS):
         """cpfem_update_state.  Returns (Fp_inv_new, g_new, slip_new) with the shapes of the inputs."""
         with torch.cuda.device(self.device):
-            st, ts = self._state(params, layout)
+            st, ts, mat = self._state(params, layout, mat)
             sol = _dev_f64(sol, self.device)
             if out is None:
                 out = [torch.empty_like(ts[0]), torch.empty_like(ts[1]), torch.empty_like(ts[2])]
@@ -133,7 +157,7 @@ class Plan:
         """cpfem_update_state_avg_stress: update_int_vars_gp and compute_avg_stress from ONE local solve per point.
         Returns ((Fp_inv_new, g_new, slip_new), sigma_cell (nc, 3, 3))."""
         with torch.cuda.device(self.device):
-            st, ts = self._state(params, layout)
+            st, ts, mat = self._state(params, layout, mat)
             sol = _dev_f64(sol, self.device)
             if out is None:
                 out = [torch.empty_like(ts[0]), torch.empty_like(ts[1]), torch.empty_like(ts[2])]
@@ -238,7 +262,7 @@ class Plan:
 
     def residual(self, mat: Material, sol, params, dt, res=None, status=None, layout=LAYOUT_AOS):
         with torch.cuda.device(self.device):
-            st, ts = self._state(params, layout)
+            st, ts, mat = self._state(params, layout, mat)
             sol = _dev_f64(sol, self.device)
             if res is None:
                 res = torch.empty(self.nn, 3, dtype=torch.float64, device=self.device)
@@ -249,7 +273,7 @@ class Plan:
     def newton_update(self, mat: Material, sol, params, dt, res=None, csr_data=None, coo_V=None, want_csr=True,
                       want_V=False, status=None, layout=LAYOUT_AOS):
         with torch.cuda.device(self.device):
-            st, ts = self._state(params, layout)
+            st, ts, mat = self._state(params, layout, mat)
             sol = _dev_f64(sol, self.device)
             if res is None:
                 res = torch.empty(self.nn, 3, dtype=torch.float64, device=self.device)
@@ -264,7 +288,7 @@ class Plan:
 
     def avg_stress(self, mat: Material, sol, params, dt, out=None, status=None, layout=LAYOUT_AOS):
         with torch.cuda.device(self.device):
-            st, ts = self._state(params, layout)
+            st, ts, mat = self._state(params, layout, mat)
             sol = _dev_f64(sol, self.device)
             if out is None:
                 out = torch.empty(self.nc_active, 3, 3, dtype=torch.float64, device=self.device)
@@ -275,7 +299,7 @@ class Plan:
     def point_stress_tangent(self, mat: Material, u_grads, params, dt, want_tangent=True, status=None):
         """tensor_map (and its jacfwd) on explicit u_grads (np, 3, 3); state arrays have leading size np."""
         with torch.cuda.device(self.device):
-            st, ts = self._state(params, LAYOUT_AOS)
+            st, ts, mat = self._state(params, LAYOUT_AOS, mat)
             ug = _dev_f64(u_grads, self.device)
             n = int(ug.numel() // 9)
             P = torch.empty(n, 3, 3, dtype=torch.float64, device=self.device)

@@ -1125,11 +1125,16 @@ static int rate_pown(const CpMaterial& m, const StateView& v) {
 // per-point parameter arrays present?  (DP-steel / calibration forms of the state)
 static bool per_point(const StateView& v) { return v.C || v.xm || v.h || v.t_sat || v.gss_a || v.r; }
 // instantiated (NS, POWN, PP) triples: uniform material: FCC/BCC12 x {run-time, 9 (copper), 119 (304 steel)}, BCC24 x
-// {run-time, 19}; per-point parameters: run-time exponent only (the exponent itself may vary from point to point)
+// {run-time, 19}; per-point parameters: run-time exponent when the exponent itself is a per-point array, else the
+// compile-time chains of the two sets that use the per-point form in the reference (304 calibration: 119, DP steel: 19)
 #define CP_DISPATCH(ns, pown, pp, CALL)                                         \
     do {                                                                        \
         if (pp) {                                                               \
-            if ((ns) == 12) { CALL(12, 0, true); } else { CALL(24, 0, true); }  \
+            if ((ns) == 12) {                                                   \
+                if ((pown) == 119) { CALL(12, 119, true); } else { CALL(12, 0, true); }  \
+            } else {                                                            \
+                if ((pown) == 19) { CALL(24, 19, true); } else { CALL(24, 0, true); }    \
+            }                                                                   \
         } else if ((ns) == 12) {                                                \
             if ((pown) == 119) { CALL(12, 119, false); }                        \
             else if ((pown) == 9) { CALL(12, 9, false); }                       \

@@ -110,6 +110,42 @@ def test_dp_steel_per_point_parameters():
     assert cases.relerr(new[0].cpu().numpy(), new_o[0]) < TOL and cases.relerr(new[1].cpu().numpy(), new_o[1]) < TOL
 
 
+def test_calibration_form_uniform_arrays_are_demoted():
+    """9-array 'calibration' form of the state (calibration/case4.py:88-92: per-point gss_a, h, t_sat, xm, r).  Arrays that
+    hold one value everywhere are demoted to scalars by the binding (uniform-parameter kernels, compile-time exponent);
+    arrays that vary take the per-point kernels.  Both against the oracle; an in-place edit of an array must be noticed."""
+    from cpfem_b200 import Plan
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('304steel', N=3, steps=6)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    m = _mat(mat)
+    nc = len(fe.cells)
+    full = lambda v: torch.full((nc, 8), v, dtype=torch.float64, device='cuda')
+    dev4 = [torch.as_tensor(np.ascontiguousarray(p), device='cuda') for p in params]
+    extra = [full(mat.gss_a), full(mat.h), full(mat.t_sat), full(mat.xm), full(mat.r)]
+    # material struct with WRONG scalars: the arrays must win, demoted or not
+    wrong = _mat(O.copper())
+    wrong.C11, wrong.C12, wrong.C44, wrong.max_sub_step = mat.C11, mat.C12, mat.C44, mat.max_sub_step
+    new_o = fe.update_int_vars_gp(sol, params, dt)
+    res_o, V_o = fe.newton_update(sol, params, dt)
+    new_u = plan.update_state(wrong, sol, dev4 + extra, dt)
+    assert len(plan._uniform_cache) == 5 and all(v is not None for v in plan._uniform_cache.values())
+    _, _, V_u = plan.newton_update(wrong, sol, dev4 + extra, dt, want_V=True)
+    for k in range(2):
+        assert cases.relerr(new_u[k].cpu().numpy(), new_o[k]) < TOL
+    assert cases.relerr(V_u.cpu().numpy(), V_o) < TOL
+    # one entry of h moved by an ulp-scale amount: no longer uniform -> per-point kernels, same answers to 1e-10
+    extra[1][0, 0] *= (1.0 + 4e-16)
+    new_p = plan.update_state(wrong, sol, dev4 + extra, dt)
+    assert any(v is None for v in plan._uniform_cache.values())
+    for k in range(2):
+        assert cases.relerr(new_p[k].cpu().numpy(), new_o[k]) < TOL
+    # a genuinely different hardening modulus on half of the cells changes g there and only there
+    extra[1][: nc // 2] *= 2.0
+    new_h = plan.update_state(wrong, sol, dev4 + extra, dt)
+    d = (new_h[1] - new_p[1]).abs().amax(dim=(1, 2))
+    assert float(d[: nc // 2].max()) > 0 and float(d[nc // 2:].max()) == 0.0
+
+
 def test_soa_layout_and_transposes():
     """Native SoA state layout gives the same bits as the reference AoS layout; the transposes round-trip."""
     from cpfem_b200 import Plan, api
