@@ -51,6 +51,47 @@ def test_spmv_and_diagonal():
     assert k1 == k2 and torch.equal(x1, x2)
 
 
+def test_high_valence_node():
+    """A node shared by 16 cells with 53 neighbour nodes (two 2x2x2 blocks glued at their centre node - the plan's valence
+    limit): the neighbour list is longer than a warp, which exercises the tail loop of the SpMV and the pattern / slot
+    map / assembly on a node with m > 32.  Pattern bit-exact vs scipy, assembly vs the oracle, SpMV vs scipy."""
+    import torch
+    import scipy.sparse
+    from cpfem_b200 import Plan, make_material
+    pts, cells = O.box_mesh(2, 2, 2)
+    centre = 13
+    pts2 = pts + np.array([0.013, -0.007, 0.011])                # second block slightly shifted: distinct geometry
+    cells2 = cells + 27
+    cells2[cells2 == 27 + centre] = centre                        # glue: block 2 uses block 1's centre node
+    allpts = np.concatenate([pts, pts2])
+    allcells = np.concatenate([cells, cells2])
+    keep = np.ones(54, bool); keep[27 + centre] = False           # drop the orphan, renumber
+    remap = np.cumsum(keep) - 1
+    allpts, allcells = allpts[keep], remap[allcells].astype(np.int32)
+    mat = O.copper()
+    rng = np.random.default_rng(4)
+    quat = cases.rand_quat(rng, 3)
+    ori = rng.integers(0, 3, size=len(allcells))
+    fe = O.FEOracle(allpts, allcells, O.make_uniform_batch_factory(mat))
+    params = O.initial_internal_vars(len(allcells), mat, O.get_rot_mat(quat)[ori])
+    sol = np.stack([-0.3e-3 * allpts[:, 0], -0.3e-3 * allpts[:, 1], 1e-3 * allpts[:, 2]], 1) + rng.uniform(-1, 1, allpts.shape) * 1e-5
+    plan = Plan(allcells, allpts, mat.slip)
+    assert plan.max_valence == 16
+    m = make_material(mat.C11, mat.C12, mat.C44, mat.h, mat.t_sat, mat.gss_a, mat.xm, mat.r, mat.ao, mat.tol, mat.max_sub_step)
+    res, data, V = plan.newton_update(m, sol, params, 0.01, want_V=True)
+    res_o, V_o = fe.newton_update(sol, params, 0.01)
+    A_o = O.csr_from_coo(V_o, fe.I, fe.J, fe.nn * 3)
+    ip, ix = plan.csr_pattern()
+    assert np.array_equal(ip.cpu().numpy(), A_o.indptr.astype(np.int64)) and np.array_equal(ix.cpu().numpy(), A_o.indices.astype(np.int32))
+    assert np.diff(A_o.indptr).max() == 3 * 53
+    assert cases.relerr(V.cpu().numpy(), V_o) < 1e-10 and cases.relerr(data.cpu().numpy(), A_o.data) < 1e-10
+    x = rng.normal(size=plan.ndof)
+    y = plan.spmv(data, torch.as_tensor(x, device='cuda')).cpu().numpy()
+    A = scipy.sparse.csr_array((data.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(plan.ndof, plan.ndof))
+    assert np.abs(y - A @ x).max() < 1e-13 * np.abs(A @ x).max()
+    assert np.array_equal(plan.csr_diagonal(data).cpu().numpy(), A.diagonal())
+
+
 def test_bicgstab_vs_oracle():
     import torch
     import scipy.sparse.linalg
