@@ -187,3 +187,24 @@ def test_golden_curves_through_gpu_path():
     gold = np.loadtxt(os.path.join(GOLD, 'tantalum_ss_curve.txt'))
     got = _gpu_one_element_curve(Ta, np.linspace(0., -0.10, 41), np.linspace(0., 10., 41), n)
     assert np.abs(got / gold[:n] - 1).max() < 1e-9
+
+
+@pytest.mark.parametrize('case', ['copper', 'tantalum', '304steel', 'dpsteel'])
+def test_example_driver_runs(case, tmp_path):
+    """examples/run_driver.py (the reference's four forward drivers with the imports swapped) runs two load steps of every
+    case on a small box mesh, writes VTU files that read back, and reports finite stresses."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / 'vtk'
+    r = subprocess.run([sys.executable, os.path.join(root, 'examples', 'run_driver.py'), '--case', case, '--n', '4', '--steps', '2',
+                        '--vtk', str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith('step')]
+    assert len(lines) == 2
+    szz = [float(l.split('mean sigma_zz')[1].split()[0]) for l in lines]
+    assert all(np.isfinite(szz)) and abs(szz[1]) > abs(szz[0]) > 0
+    sys.path.insert(0, os.path.join(root, 'jax-cpfem_b200'))
+    from cpfem_b200.utils import read_vtu
+    d = read_vtu(str(out / 'u_001.vtu'))
+    assert d['sol'].shape == (125, 3) and d['sigma_zz'].shape == (64,) and abs(float(d['sigma_zz'].mean()) / szz[1] - 1) < 1e-6
