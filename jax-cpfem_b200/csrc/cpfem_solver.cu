@@ -465,7 +465,7 @@ extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const do
         CU_TRY(cudaGetLastError());
         if (batches < 8) batches *= 2;
     }
-    if ((w->host_sc->k < 0 || getenv("CPFEM_DEBUG_BICG_ALL")) && getenv("CPFEM_DEBUG_BICG"))
+    if (w->host_sc->k < 0 && getenv("CPFEM_DEBUG_BICG"))       // diagnostic: the scalars at a breakdown (JAX codes -10 / -11)
         fprintf(stderr, "bicgstab breakdown k=%lld rho=%.17g rho_=%.17g alpha=%.17g alpha_=%.17g omega=%.17g omega_=%.17g ss=%.17g rs=%.17g atol2=%.17g\n",
                 w->host_sc->k, w->host_sc->rho, w->host_sc->rho_, w->host_sc->alpha, w->host_sc->alpha_, w->host_sc->omega,
                 w->host_sc->omega_, w->host_sc->ss, w->host_sc->rs, w->host_sc->atol2);
