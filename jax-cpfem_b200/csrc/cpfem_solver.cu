@@ -118,7 +118,7 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * RED_BLOCK + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * RED_BLOCK) >> 5;
-    double acc[2] = {0.0, 0.0};
+    double acc1 = 0.0;                 // lanes 0..2: first dot product, lanes 3..5: second one
     // The index data of a node (its two nbr_ptr entries, then the neighbour id of every lane) sit in front of the x gather
     // in a chain of three dependent memory latencies.  They are fetched ONE NODE AHEAD: while the matrix loads of node n
     // are in flight the warp already holds (b0, m, col) of node n and requests those of node n + nwarps.
@@ -137,10 +137,13 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
         const double* __restrict__ base = data + 9 * b0;
         // the vector entry the epilogue of lanes 0..2 needs (b, rhat or s of this node's rows) is requested up front, so
         // that its latency hides under the matrix loads instead of trailing the warp reduction
+        // (lanes 3..5 mirror lanes 0..2 and carry the second dot product of modes 0 and 2, so that the loop holds ONE
+        // accumulator per lane: at 64 registers a second one spilled)
+        const int j3 = (lane < 3) ? lane : lane - 3;
         double aux = 0.0;
-        if (MODE != 3 && lane < 3) {
+        if (MODE != 3 && lane < ((MODE == 1) ? 3 : 6)) {
             const double* __restrict__ av = (MODE == 0) ? V.b : (MODE == 1) ? (const double*)V.rhat : (const double*)V.s;
-            aux = av[3 * n + lane];
+            aux = av[3 * n + j3];
         }
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         // lane j takes neighbour j: its three x entries once, then the 3 x 3 block of the node's rows.  For a fixed (i, k)
@@ -174,29 +177,32 @@ k_bicg_spmv(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
-        if (lane < 3) {
-            const double y = (lane == 0) ? s0 : (lane == 1) ? s1 : s2;
-            const int64_t row = 3 * n + lane;
-            if (MODE == 0) {
-                const double bb = aux;
-                const double rr = bb - y;
-                V.r[row] = rr; V.rhat[row] = rr; V.p[row] = rr; V.q[row] = rr;
-                acc[0] += rr * rr;
-                acc[1] += bb * bb;
-            } else if (MODE == 1) {
-                V.q[row] = y;
-                acc[0] += aux * y;
-            } else if (MODE == 2) {
-                V.t[row] = y;
-                acc[0] += y * aux;
-                acc[1] += y * y;
+        if (lane < 6) {
+            const double y = (j3 == 0) ? s0 : (j3 == 1) ? s1 : s2;
+            const int64_t row = 3 * n + j3;
+            if (lane < 3) {
+                if (MODE == 0) {
+                    const double rr = aux - y;
+                    V.r[row] = rr; V.rhat[row] = rr; V.p[row] = rr; V.q[row] = rr;
+                    acc1 += rr * rr;
+                } else if (MODE == 1) {
+                    V.q[row] = y;
+                    acc1 += aux * y;
+                } else if (MODE == 2) {
+                    V.t[row] = y;
+                    acc1 += y * aux;
+                } else {
+                    vout[row] = y;
+                }
             } else {
-                vout[row] = y;
+                if (MODE == 0) acc1 += aux * aux;          // <b, b>
+                else if (MODE == 2) acc1 += y * y;         // <t, t>
             }
         }
         b0 = b0n; m = mn; col = coln;
     }
     if (MODE == 3) return;
+    double acc[2] = {(lane < 3) ? acc1 : 0.0, (lane >= 3 && lane < 6) ? acc1 : 0.0};
     double tot2[2];
     if (!grid_reduce<2>(acc, partials, &sc->ticket, tot2)) return;
     if (threadIdx.x == 0) {
@@ -312,8 +318,8 @@ k_norm2_diff(const double* __restrict__ a, const double* __restrict__ b, int64_t
 // -----------------------------------------------------------------------------------------------
 #define BICG_GRAPH_ITERS 8
 struct cpfem_solver_ws {
-    int64_t n = 0;
-    double* vec = nullptr;         // 8 vectors of n + minv
+    int64_t n = 0, pitch = 0;
+    double* vec = nullptr;         // 8 vectors + minv, `pitch` doubles apart
     BicgScal* sc = nullptr;
     double* partials = nullptr;
     BicgScal* host_sc = nullptr;   // pinned
@@ -329,7 +335,10 @@ static int ws_get(cpfem_plan* p, cpfem_solver_ws** out) {
         cpfem_solver_ws* w = new (std::nothrow) cpfem_solver_ws();
         if (!w) return set_err(-3, "solver workspace: out of host memory");
         w->n = 3 * p->nn;
-        cudaError_t e = cudaMalloc((void**)&w->vec, sizeof(double) * 9 * (size_t)w->n);
+        // vector pitch: 256-byte aligned rows + an odd number of KiB of skew, so that the nine vectors neither start
+        // misaligned nor sit a power of two (or the same DRAM channel phase) apart
+        w->pitch = ((w->n + 31) / 32) * 32 + 32 * 37;
+        cudaError_t e = cudaMalloc((void**)&w->vec, sizeof(double) * 9 * (size_t)w->pitch);
         if (e == cudaSuccess) e = cudaMalloc((void**)&w->sc, sizeof(BicgScal));
         if (e == cudaSuccess) e = cudaMalloc((void**)&w->partials, sizeof(double) * 2 * MAX_PARTIAL_BLOCKS);
         if (e == cudaSuccess) e = cudaMallocHost((void**)&w->host_sc, sizeof(BicgScal));
@@ -434,9 +443,10 @@ extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const do
     const int64_t n = w->n;
     BicgVecs V;
     V.data = csr_data; V.b = b; V.x = x;
-    V.r = w->vec; V.rhat = w->vec + n; V.p = w->vec + 2 * n; V.q = w->vec + 3 * n; V.phat = w->vec + 4 * n;
-    V.s = w->vec + 5 * n; V.shat = w->vec + 6 * n; V.t = w->vec + 7 * n;
-    double* minv = w->vec + 8 * n;
+    const int64_t vp = w->pitch;
+    V.r = w->vec; V.rhat = w->vec + vp; V.p = w->vec + 2 * vp; V.q = w->vec + 3 * vp; V.phat = w->vec + 4 * vp;
+    V.s = w->vec + 5 * vp; V.shat = w->vec + 6 * vp; V.t = w->vec + 7 * vp;
+    double* minv = w->vec + 8 * vp;
     V.minv = precond ? minv : nullptr;
     *w->hV = V;
     CU_TRY(cudaMemcpyAsync(w->dV, w->hV, sizeof(BicgVecs), cudaMemcpyHostToDevice, stream));
