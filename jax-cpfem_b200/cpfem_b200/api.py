@@ -4,6 +4,7 @@ sm_100a kernels in libcpfem_b200.so.  Arrays are torch CUDA tensors (float64 / i
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import List, Optional, Sequence
 
 import numpy as onp
@@ -101,14 +102,19 @@ class Plan:
     def _uniform_value(self, t: torch.Tensor):
         """The value of a per-point parameter array if it is the same at every point, else None.  One reduction + host
         read per distinct tensor (identity + version counter), remembered afterwards."""
-        key = (t.data_ptr(), t._version, tuple(t.shape))
+        # keyed on the tensor OBJECT (weak reference) + its version counter: an address alone can be recycled by the
+        # allocator for a new array with other values
+        key = (id(t), t._version)
         cache = self.__dict__.setdefault('_uniform_cache', {})
-        if key not in cache:
-            if len(cache) > 64:
-                cache.clear()
-            lo, hi = torch.aminmax(t)
-            cache[key] = float(lo) if float(lo) == float(hi) else None
-        return cache[key]
+        hit = cache.get(key)
+        if hit is not None and hit[0]() is t:
+            return hit[1]
+        if len(cache) > 64:
+            cache.clear()
+        lo, hi = torch.aminmax(t)
+        val = float(lo) if float(lo) == float(hi) else None
+        cache[key] = (weakref.ref(t), val)
+        return val
 
     def _state(self, params: Sequence[torch.Tensor], layout=LAYOUT_AOS, mat: Optional[Material] = None):
         """cpfem_state from the reference's internal_vars list (4, 9 or 10 arrays).  With `mat` given, per-point parameter
@@ -210,10 +216,10 @@ class Plan:
                 self._host_key = key
             rot_dev = None
             if cache_rot:
-                rkey = (hs[3].data_ptr(), hs[3]._version, tuple(hs[3].shape))
-                if getattr(self, '_rot_key', None) != rkey:
+                rk = getattr(self, '_rot_key', None)             # (weak reference to the host tensor, its version counter)
+                if rk is None or rk[0]() is not hs[3] or rk[1] != hs[3]._version:
                     self._rot_dev = hs[3].to(self.device, non_blocking=True)
-                    self._rot_key = rkey
+                    self._rot_key = (weakref.ref(hs[3]), hs[3]._version)
                 rot_dev = self._rot_dev
             ev_in = [torch.cuda.Event() for _ in range(nbuf)]
             ev_cmp = [torch.cuda.Event() for _ in range(nbuf)]

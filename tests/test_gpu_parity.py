@@ -128,7 +128,7 @@ def test_calibration_form_uniform_arrays_are_demoted():
     new_o = fe.update_int_vars_gp(sol, params, dt)
     res_o, V_o = fe.newton_update(sol, params, dt)
     new_u = plan.update_state(wrong, sol, dev4 + extra, dt)
-    assert len(plan._uniform_cache) == 5 and all(v is not None for v in plan._uniform_cache.values())
+    assert len(plan._uniform_cache) == 5 and all(v[1] is not None for v in plan._uniform_cache.values())
     _, _, V_u = plan.newton_update(wrong, sol, dev4 + extra, dt, want_V=True)
     for k in range(2):
         assert cases.relerr(new_u[k].cpu().numpy(), new_o[k]) < TOL
@@ -136,9 +136,17 @@ def test_calibration_form_uniform_arrays_are_demoted():
     # one entry of h moved by an ulp-scale amount: no longer uniform -> per-point kernels, same answers to 1e-10
     extra[1][0, 0] *= (1.0 + 4e-16)
     new_p = plan.update_state(wrong, sol, dev4 + extra, dt)
-    assert any(v is None for v in plan._uniform_cache.values())
+    assert any(v[1] is None for v in plan._uniform_cache.values())
     for k in range(2):
         assert cases.relerr(new_p[k].cpu().numpy(), new_o[k]) < TOL
+    # a NEW array object (the calibration loop builds `coeff * array` every evaluation; the allocator may hand it the
+    # address of a freed one) is looked at afresh
+    h2 = torch.full((nc, 8), 2.0 * mat.h, dtype=torch.float64, device='cuda')
+    new_2h = plan.update_state(wrong, sol, dev4 + [extra[0], h2, extra[2], extra[3], extra[4]], dt)
+    del h2
+    h3 = torch.full((nc, 8), mat.h, dtype=torch.float64, device='cuda')          # likely the same address as h2
+    new_1h = plan.update_state(wrong, sol, dev4 + [extra[0], h3, extra[2], extra[3], extra[4]], dt)
+    assert not torch.equal(new_2h[1], new_1h[1]) and cases.relerr(new_1h[1].cpu().numpy(), new_o[1]) < TOL
     # a genuinely different hardening modulus on half of the cells changes g there and only there
     extra[1][: nc // 2] *= 2.0
     new_h = plan.update_state(wrong, sol, dev4 + extra, dt)
