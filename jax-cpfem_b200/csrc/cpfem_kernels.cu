@@ -919,19 +919,20 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
                 for (int j = 0; j < 24; ++j) v[j] = acc[j];
             }
             if (csr_data) {
-                // coalesced scatter: every lane parks its row in shared memory, then one warp instruction adds one row:
-                // lanes 0..23 hit the 8 x 24-byte pieces of that CSR row (x-neighbour pairs are contiguous), i.e. a
-                // handful of sectors per instruction instead of 32
                 double* ke = KE + lane * KE_ROW;
 #pragma unroll
                 for (int j = 0; j < 24; ++j) ke[j] = acc[j];
                 ROWP[lane] = (i == 0) ? rp0 : (i == 1) ? rp1 : rp2;
                 __syncwarp();
-                const int jb = (lane < 24) ? lane / 3 : 0, jk = (lane < 24) ? lane - 3 * (lane / 3) : 0;
+                // coalesced scatter: every lane parked its row in shared memory; the 32 x 24 values of the tile then go out as
+                // 24 warp instructions with all 32 lanes busy (1 1/3 rows each: consecutive lanes hit the 24-byte pieces of a
+                // CSR row, x-neighbour pairs are contiguous)
 #pragma unroll 4
-                for (int t = 0; t < 32; ++t) {
+                for (int it = 0; it < 24; ++it) {
+                    const int v = it * 32 + lane;
+                    const int t = v / 24, j = v - 24 * t;
                     const long long base = ROWP[t];
-                    if (lane < 24 && base >= 0) atomicAdd(csr_data + base + RB[t * 8 + jb] + jk, KE[t * KE_ROW + lane]);
+                    if (base >= 0) atomicAdd(csr_data + base + RB[t * 8 + j / 3] + (j - 3 * (j / 3)), KE[t * KE_ROW + j]);
                 }
                 __syncwarp();                       // KE / ROWP free again
             }
