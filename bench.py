@@ -34,14 +34,14 @@ F_UPDATE_FIXED = 1600.0     # set-up: Schmid rotation, B = F A M, hardening
 F_ITER = 5000.0             # one local Newton iteration incl. one line-search residual evaluation
 F_ASSEMBLY_FIXED = 16600.0  # set-up + consistent tangent (10 k) + element K_e share (5 k)
 # executed by this implementation (6x6 symmetric crystal-frame form, active-set slip processing, factored tangent):
-# 2 x FP64 thread instructions per point from ncu (profiles/r1/n_ncu_summary_n64.txt: dfma + dmul + dadd per cycle x cycles)
+# 2 x FP64 thread instructions per point from ncu (profiles/r1/o_ncu_summary_n64.txt: dfma + dmul + dadd per cycle x cycles)
 X_UPDATE_FIXED = 3000.0     # kinematics, frame change, 1/g, first residual, state update (~1.5 k instructions)
 X_ITER = 1860.0             # per local Newton iteration: ~0.93 k instructions (matrix over the active systems + LU + solve
                             # + 1.8 residual evaluations), x 2
 X_ASSEMBLY_FIXED = 12800.0  # update fixed part + factored tangent (2.5 k instr) + element K_e (2.4 k instr), x 2
 B_UPDATE = 610.0            # bytes/point: state in 336 + state out 264 + mesh/sol share 10
 B_ASSEMBLY = 2180.0         # bytes/point: state 240 + mesh/sol 10 + CSR memset 244 + CSR RMW 244 + scratch 2 x 720
-TRAFFIC_UPDATE_B_PER_POINT = 592.0   # ncu dram__bytes_read + write per point, k_update_state at 64^3 (profiles/r1/n_ncu_summary_n64.txt)
+TRAFFIC_UPDATE_B_PER_POINT = 592.0   # ncu dram__bytes_read + write per point, k_update_state at 64^3 (profiles/r1/o_ncu_summary_n64.txt)
 
 MESH_N = 200
 D_EPS, DT, PRE_STEPS = 2e-4, 2e-3, 10
@@ -466,7 +466,7 @@ def main():
     roof = {'bound': 'fp64', 'kernel': 'k_update_state<12,119>', 'achieved': tf(f_upd, upd_s), 'peak': fp64_peak,
             'unit': 'TFLOP/s', 'frac': tf(f_upd, upd_s) / fp64_peak,
             'traffic': TRAFFIC_UPDATE_B_PER_POINT * pts_rank,
-            'traffic_source': 'ncu --set full at 64^3 (profiles/r1/n_ncu_summary_n64.txt): dram read+write = 592 B/point, scaled to this launch; '
+            'traffic_source': 'ncu --set full at 64^3 (profiles/r1/o_ncu_summary_n64.txt): dram read+write = 592 B/point, scaled to this launch; '
                               'algorithmic bytes 610 B/point',
             'peak_source': 'max(DFMA microbenchmark of this run (cpfem_dfma_peak_kernel): %.2f TFLOP/s, nominal SMs x 64 DFMA/clk x '
                            'max SM clock: %.2f TFLOP/s); MEASURED_PEAKS.json has no FP64 entry' % (fp64_meas, fp64_nominal),

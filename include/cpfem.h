@@ -96,7 +96,9 @@ int cpfem_plan_csr(const cpfem_plan* plan, const int64_t** indptr, const int32_t
  * (3*nnodes+1), indices_out int32 (nnz).  Either may be NULL. */
 int cpfem_plan_csr_copy(const cpfem_plan* plan, int64_t* indptr_out, int32_t* indices_out, void* stream);
 /* Element-partitioned runs: the plan's mesh is "owned cells followed by ghost cells" (ghost cells only contribute
- * sparsity); restrict the kernels to the first n_active cells.  State arrays then have n_active*8 points. */
+ * sparsity); restrict the kernels to the first n_active cells.  State arrays then have n_active*8 points.
+ * n_active = 0 (a rank that owns no cell) is legal: the state pointers may then be NULL, residual / CSR values come
+ * back zeroed and nothing is launched. */
 int cpfem_plan_set_active_cells(cpfem_plan* plan, int64_t n_active);
 /* Sizes: nc, nnodes, ns, nnz, max node valence, cells per assembly chunk. out[6]. */
 int cpfem_plan_info(const cpfem_plan* plan, int64_t* out);

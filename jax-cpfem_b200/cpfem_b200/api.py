@@ -198,7 +198,9 @@ class Plan:
         if any(h.is_cuda or h.dtype != torch.float64 or not h.is_contiguous() or h.shape[0] != nc for h in hs):
             raise ValueError('update_state_host: params must be contiguous float64 CPU tensors with leading dimension nc')
         if out is None:
-            out = [torch.empty(h.shape, dtype=torch.float64, pin_memory=True) for h in hs[:3]]
+            out = [torch.empty(h.shape, dtype=torch.float64, pin_memory=nc > 0) for h in hs[:3]]
+        if nc == 0:                                     # a rank that owns no cells
+            return out
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream()
             s_in, s_out = self._host_streams()

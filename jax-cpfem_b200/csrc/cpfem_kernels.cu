@@ -297,7 +297,7 @@ extern "C" int cpfem_plan_csr_copy(const cpfem_plan* p, int64_t* indptr_out, int
 }
 extern "C" int cpfem_plan_set_active_cells(cpfem_plan* p, int64_t n_active) {
     if (!p) return set_err(-1, "cpfem_plan_set_active_cells: null plan");
-    if (n_active < 1 || n_active > p->nc) return set_err(-1, "cpfem_plan_set_active_cells: out of range");
+    if (n_active < 0 || n_active > p->nc) return set_err(-1, "cpfem_plan_set_active_cells: out of range");
     p->nc_active = n_active;
     return 0;
 }
@@ -1102,9 +1102,12 @@ __global__ void k_dfma_peak(int64_t iters, double* sink) {
 // -----------------------------------------------------------------------------------------------
 // C ABI launchers
 // -----------------------------------------------------------------------------------------------
-static int check_common(const cpfem_plan* plan, const cpfem_material* mat, const cpfem_state* st, const char* who) {
+// A plan restricted to zero active cells (a rank that owns no element) has empty state arrays: their pointers may be
+// NULL, every entry point zeroes what it would accumulate into and launches nothing.
+static int check_common(const cpfem_plan* plan, const cpfem_material* mat, const cpfem_state* st, const char* who,
+                        bool need_state = true) {
     if (!plan || !mat || !st) return set_err(-1, (std::string(who) + ": null argument").c_str());
-    if (!st->Fp_inv || !st->g || !st->rot) return set_err(-1, (std::string(who) + ": null state array").c_str());
+    if (need_state && (!st->Fp_inv || !st->g || !st->rot)) return set_err(-1, (std::string(who) + ": null state array").c_str());
     if (mat->max_sub_step < 1) return set_err(-1, (std::string(who) + ": max_sub_step must be >= 1").c_str());
     return 0;
 }
@@ -1185,7 +1188,9 @@ extern "C" int cpfem_update_state_cells(const cpfem_plan* plan, const cpfem_mate
 extern "C" int cpfem_update_state_avg_stress(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
                                              const cpfem_state* in, const cpfem_state_out* out, double dt,
                                              double* sigma_cell, int64_t* status, void* stream_) {
-    if (!plan || !sigma_cell) return set_err(-1, "cpfem_update_state_avg_stress: null argument");
+    if (!plan) return set_err(-1, "cpfem_update_state_avg_stress: null argument");
+    if (plan->nc_active == 0) return check_common(plan, mat, in, "cpfem_update_state_avg_stress", false);
+    if (!sigma_cell) return set_err(-1, "cpfem_update_state_avg_stress: null argument");
     return update_state_impl(plan, mat, sol, in, out, dt, 0, plan->nc_active, sigma_cell, status, stream_);
 }
 
@@ -1193,16 +1198,18 @@ extern "C" int cpfem_update_state(const cpfem_plan* plan, const cpfem_material* 
                                   const cpfem_state* in, const cpfem_state_out* out, double dt, int64_t* status,
                                   void* stream_) {
     if (!plan) return set_err(-1, "cpfem_update_state: null argument");
+    if (plan->nc_active == 0) return check_common(plan, mat, in, "cpfem_update_state", false);
     return cpfem_update_state_cells(plan, mat, sol, in, out, dt, 0, plan->nc_active, status, stream_);
 }
 
 extern "C" int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
                               const cpfem_state* st, double dt, double* res, int64_t* status, void* stream_) {
-    int rc = check_common(plan, mat, st, "cpfem_residual");
+    int rc = check_common(plan, mat, st, "cpfem_residual", !plan || plan->nc_active > 0);
     if (rc) return rc;
     if (!sol || !res) return set_err(-1, "cpfem_residual: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     CU_TRY(cudaMemsetAsync(res, 0, plan->nn * 3 * sizeof(double), stream));
+    if (plan->nc_active == 0) return 0;
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
     const KMat km = make_kmat(m);
@@ -1221,12 +1228,13 @@ extern "C" int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat,
 extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
                                    const cpfem_state* st, double dt, double* res, double* csr_data, double* coo_V,
                                    int64_t* status, void* stream_) {
-    int rc = check_common(plan, mat, st, "cpfem_newton_update");
+    int rc = check_common(plan, mat, st, "cpfem_newton_update", !plan || plan->nc_active > 0);
     if (rc) return rc;
     if (!sol || !res) return set_err(-1, "cpfem_newton_update: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     CU_TRY(cudaMemsetAsync(res, 0, plan->nn * 3 * sizeof(double), stream));
     if (csr_data) CU_TRY(cudaMemsetAsync(csr_data, 0, plan->nnz * sizeof(double), stream));
+    if (plan->nc_active == 0) return 0;
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
     const KMat km = make_kmat(m);
@@ -1281,8 +1289,9 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
 
 extern "C" int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* mat, const double* sol,
                                 const cpfem_state* st, double dt, double* sigma_cell, int64_t* status, void* stream_) {
-    int rc = check_common(plan, mat, st, "cpfem_avg_stress");
+    int rc = check_common(plan, mat, st, "cpfem_avg_stress", !plan || plan->nc_active > 0);
     if (rc) return rc;
+    if (plan->nc_active == 0) return 0;
     if (!sol || !sigma_cell) return set_err(-1, "cpfem_avg_stress: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t np = plan->nc_active * 8;

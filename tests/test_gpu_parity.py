@@ -450,6 +450,39 @@ def test_error_and_status_conventions():
     assert bool(torch.isfinite(ok[0]).all())
 
 
+def test_single_cell_mesh_and_zero_active_cells():
+    """Smallest inputs: a one-cell copper mesh (8 points: a quarter of one warp, one element of an 8-warp block) against
+    the oracle, and a plan restricted to zero active cells (every kernel launch is skipped or empty: outputs are zero,
+    no error, status untouched)."""
+    from cpfem_b200 import Plan
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('copper', N=1, steps=5)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    m = _mat(mat)
+    assert plan.nc == 1 and plan.nnz == 24 * 24
+    new_o = fe.update_int_vars_gp(sol, params, dt)
+    new = plan.update_state(m, sol, params, dt)
+    for k in range(2):
+        assert cases.relerr(new[k].cpu().numpy(), new_o[k]) < TOL
+    res_o, V_o = fe.newton_update(sol, params, dt)
+    res, data, V = plan.newton_update(m, sol, params, dt, want_V=True)
+    assert cases.relerr(V.cpu().numpy(), V_o) < TOL
+    assert np.abs(res.cpu().numpy() - res_o).max() < TOL * np.abs(res_o).max()
+    A_o = O.csr_from_coo(V_o, fe.I, fe.J, fe.nn * 3)
+    indptr, indices = plan.csr_pattern()
+    assert np.array_equal(indptr.cpu().numpy(), A_o.indptr.astype(np.int64))
+    assert np.array_equal(indices.cpu().numpy(), A_o.indices.astype(np.int32))
+    assert cases.relerr(data.cpu().numpy(), A_o.data) < TOL
+    assert cases.relerr(plan.avg_stress(m, sol, params, dt).cpu().numpy(), fe.compute_avg_stress(sol, params, dt)) < TOL
+    # zero active cells: the pattern stays, the values are all zero
+    plan.set_active_cells(0)
+    empty = [torch.empty((0,) + tuple(np.shape(p)[1:]), dtype=torch.float64, device='cuda') for p in params]
+    st = plan.new_status()
+    res0, data0, _ = plan.newton_update(m, sol, empty, dt, status=st)
+    assert float(res0.abs().max()) == 0.0 and float(data0.abs().max()) == 0.0 and data0.numel() == 576
+    out = plan.update_state(m, sol, empty, dt, status=st)
+    assert out[0].shape[0] == 0 and int(st.abs().sum()) == 0
+
+
 def test_full_size_properties():
     """Size-independent properties on a mesh the oracle cannot follow (64^3, 2.1 M points): the residual of a rigid
     translation of the converged field is unchanged, the tangent annihilates rigid translations, CSR row sums of the
