@@ -188,6 +188,8 @@ def main():
     ap.add_argument('--n', type=int, default=MESH_N, help='mesh cells per edge (default 200 = BASELINE config)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--overlap-exchange', action='store_true',
+                    help='multi-GPU: start the interface exchange after the first assembly chunk, beside the rest (measured: no gain, see DESIGN.md)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-cells', type=int, default=1024)
     ap.add_argument('--layout', default='aos', choices=['aos', 'soa'])
@@ -267,6 +269,9 @@ def main():
         ip, ix = plan.csr_pattern()
         ex = ExchangePlan(rm, ip, ix)
         ex.prepare()
+        if args.overlap_exchange:
+            ex.attach(plan)              # interface exchange starts after the first assembly chunk, beside the rest
+    exchange = (lambda r, c: ex.exchange_overlapped(r, c)) if (ex is not None and args.overlap_exchange) else (lambda r, c: ex.exchange(r, c))
     status_u = plan.new_status()
     status_a = plan.new_status()
     norm_buf = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -277,7 +282,7 @@ def main():
     def do_assembly():
         plan.newton_update(mat, sol, state, DT, res=res, csr_data=csr, status=status_a, layout=layout)
         if ex is not None:
-            ex.exchange(res, csr)
+            exchange(res, csr)
             s = ex.owned_sumsq(res, norm_buf)
             dist.all_reduce(s, op=dist.ReduceOp.SUM)
         else:
@@ -415,7 +420,7 @@ def main():
                 d.copy_(h, non_blocking=True)
             plan.newton_update(mat, dsol, state, DT, res=res, csr_data=csr, layout=layout)
             if ex is not None:
-                ex.exchange(res, csr)
+                exchange(res, csr)
             hres.copy_(res, non_blocking=True)
             te[k][2].record()
         barrier()
@@ -506,7 +511,7 @@ def main():
         'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': t_tot / K, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(N),
-                   'partition': f'{world} slab(s)', 'state_layout': args.layout,
+                   'partition': f'{world} slab(s)' + (', interface exchange overlapped with the assembly (starts after the first chunk)' if (world > 1 and args.overlap_exchange) else ''), 'state_layout': args.layout,
                    'l2': 'inputs (>= 2 GB of state per pass) are larger than the 126 MB L2; no flush needed'},
         'update_ms': t_upd / K, 'assembly_ms': t_asm / K, 'assembly_metric': 'ms per Newton-iteration assembly '
         '(stress+tangent, hex8 integration, residual scatter, CSR fill, interface exchange, norm allreduce)',

@@ -100,6 +100,13 @@ int cpfem_plan_csr_copy(const cpfem_plan* plan, int64_t* indptr_out, int32_t* in
  * n_active = 0 (a rank that owns no cell) is legal: the state pointers may then be NULL, residual / CSR values come
  * back zeroed and nothing is launched. */
 int cpfem_plan_set_active_cells(cpfem_plan* plan, int64_t n_active);
+/* Element-partitioned runs, overlap of the interface exchange with the assembly: `event` is a caller-owned cudaEvent_t
+ * (NULL switches the feature off).  Every later cpfem_newton_update records it once the contributions of the cells
+ * [0, cell_prefix) - and the zero-fill of res / csr_data - are complete (at the end of the first assembly chunk that
+ * covers them), so that a communication stream waiting on it can ship the interface rows those cells feed (the
+ * reduction of SURVEY 8(e), which the reference - single device - does not have) while the remaining chunks compute.
+ * Contributions that arrive from peers may be added to res / csr_data with atomics from that point on. */
+int cpfem_plan_set_progress_event(cpfem_plan* plan, int64_t cell_prefix, void* event);
 /* Sizes: nc, nnodes, ns, nnz, max node valence, cells per assembly chunk. out[6]. */
 int cpfem_plan_info(const cpfem_plan* plan, int64_t* out);
 

@@ -45,6 +45,7 @@ SIGNATURES = {
     'cpfem_plan_csr': (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)]),
     'cpfem_plan_csr_copy': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     'cpfem_plan_set_active_cells': (ctypes.c_int, [c_vp, c_i64]),
+    'cpfem_plan_set_progress_event': (ctypes.c_int, [c_vp, c_i64, c_vp]),
     'cpfem_plan_info': (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
     'cpfem_update_state': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State),
                                           ctypes.POINTER(StateOut), c_dbl, c_vp, c_vp]),

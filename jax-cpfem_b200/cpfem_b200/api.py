@@ -87,6 +87,13 @@ class Plan:
         self.nc_active = int(n_active)
         self.np = 8 * self.nc_active
 
+    def set_progress_event(self, cell_prefix, event: Optional[torch.cuda.Event]):
+        """cpfem_plan_set_progress_event: newton_update records `event` once cells [0, cell_prefix) are assembled
+        (None switches it off).  The event must have been recorded once already (torch creates the handle lazily)."""
+        handle = None if event is None else ctypes.c_void_p(event.cuda_event)
+        check(_lib.lib().cpfem_plan_set_progress_event(self._h, int(cell_prefix), handle), 'cpfem_plan_set_progress_event')
+        self._progress_event = event                     # keep it alive as long as the plan may record it
+
     # ---- CSR pattern -------------------------------------------------------------------------
     def csr_pattern(self):
         """(indptr int64 (ndof+1), indices int32 (nnz)) as device tensors (copied once from the plan)."""

@@ -258,6 +258,52 @@ class ExchangePlan:
             if csr_data is not None:
                 self._scatter_add(csr_data, self.recv_slots[p], cb)
 
+    # ---- overlap with the assembly (CUDA only) -----------------------------------------------------------------
+    def send_cell_prefix(self):
+        """Number of leading owned cells after which every row this rank sends is complete (the last owned cell that
+        touches a node owned by a peer, + 1; one layer of cells for a z-slab)."""
+        rm = self.rm
+        if not rm.send_nodes:
+            return 0
+        mark = onp.zeros(len(rm.node_gid), dtype=bool)
+        for nodes in rm.send_nodes.values():
+            mark[onp.asarray(nodes)] = True
+        touch = onp.nonzero(mark[rm.cells[:rm.n_owned_cells]].any(axis=1))[0]
+        return int(touch[-1]) + 1 if len(touch) else 0
+
+    def attach(self, plan):
+        """Overlap the exchange with the assembly: `plan.newton_update` signals (cpfem_plan_set_progress_event) when the
+        cells feeding this rank's send rows are done - for a slab that is its first layer of cells, i.e. the end of the
+        first assembly chunk - and `exchange_overlapped` then runs send / receive / add on a high-priority stream
+        beside the remaining chunks.  Contributions of peers are added with atomics (cpfem_scatter_add), like the
+        element kernel's own, so the two may interleave."""
+        self.prepare()
+        self._plan = plan
+        with torch.cuda.device(self.device):
+            self._comm = torch.cuda.Stream(device=self.device, priority=-1)
+            self._ready = torch.cuda.Event()
+            self._ready.record()                          # creates the handle the library records from now on
+            self._done = torch.cuda.Event()
+        plan.set_progress_event(max(1, self.send_cell_prefix()), self._ready)
+
+    def detach(self):
+        if getattr(self, '_plan', None) is not None:
+            self._plan.set_progress_event(0, None)
+            self._plan = None
+
+    def exchange_overlapped(self, res: torch.Tensor, csr_data: Optional[torch.Tensor]):
+        """Call right after `plan.newton_update(..., res=res, csr_data=csr_data)` of the attached plan was enqueued on
+        the current stream; when this returns the current stream is ordered after the exchange."""
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(self._ready)
+            self.exchange(res, csr_data)
+            self._done.record(self._comm)
+        res.record_stream(self._comm)
+        if csr_data is not None:
+            csr_data.record_stream(self._comm)
+        cur.wait_event(self._done)
+
     def owned_sumsq(self, res: torch.Tensor, out: Optional[torch.Tensor] = None):
         """sum of squares of the residual over the rows this rank owns (device scalar)."""
         if not hasattr(self, '_s0'):

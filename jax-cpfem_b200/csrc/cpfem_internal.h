@@ -41,6 +41,10 @@ struct cpfem_plan {
     int64_t chunk_cells = 0;                   // cells per assembly chunk
     cudaStream_t elem_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_point[2] = {nullptr, nullptr}, ev_elem[2] = {nullptr, nullptr};
+    // multi-GPU overlap: cpfem_newton_update records `progress_event` (caller-owned) on its stream once the contributions
+    // of cells [0, progress_cells) are complete, so that the interface exchange can start while later chunks compute
+    cudaEvent_t progress_event = nullptr;
+    int64_t progress_cells = 0;
     CpSlip slip;
     int device = 0;
     int sm_count = 148;

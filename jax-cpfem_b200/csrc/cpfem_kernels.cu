@@ -301,6 +301,13 @@ extern "C" int cpfem_plan_set_active_cells(cpfem_plan* p, int64_t n_active) {
     p->nc_active = n_active;
     return 0;
 }
+extern "C" int cpfem_plan_set_progress_event(cpfem_plan* p, int64_t cell_prefix, void* event) {
+    if (!p) return set_err(-1, "cpfem_plan_set_progress_event: null plan");
+    if (cell_prefix < 0 || cell_prefix > p->nc) return set_err(-1, "cpfem_plan_set_progress_event: out of range");
+    p->progress_event = (cudaEvent_t)event;
+    p->progress_cells = cell_prefix;
+    return 0;
+}
 extern "C" int cpfem_plan_info(const cpfem_plan* p, int64_t* o) {
     if (!p || !o) return set_err(-1, "cpfem_plan_info: null argument");
     o[0] = p->nc; o[1] = p->nn; o[2] = p->ns; o[3] = p->nnz; o[4] = p->max_valence; o[5] = p->chunk_cells;
@@ -1234,7 +1241,11 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
     cudaStream_t stream = (cudaStream_t)stream_;
     CU_TRY(cudaMemsetAsync(res, 0, plan->nn * 3 * sizeof(double), stream));
     if (csr_data) CU_TRY(cudaMemsetAsync(csr_data, 0, plan->nnz * sizeof(double), stream));
-    if (plan->nc_active == 0) return 0;
+    if (plan->nc_active == 0) {
+        if (plan->progress_event) CU_TRY(cudaEventRecord(plan->progress_event, stream));
+        return 0;
+    }
+    bool progress_due = plan->progress_event != nullptr;
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
     const KMat km = make_kmat(m);
@@ -1279,6 +1290,10 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
                                                                                 plan->rank, res, csr_data, coo_V);
         CU_TRY(cudaGetLastError());
         if (piped) CU_TRY(cudaEventRecord(plan->ev_elem[buf], estream));
+        if (progress_due && (c0 + ncc >= plan->progress_cells || c0 + ncc >= plan->nc_active)) {
+            CU_TRY(cudaEventRecord(plan->progress_event, estream));    // cells [0, progress_cells) are in res / csr_data
+            progress_due = false;
+        }
     }
     if (piped) {                                                      // join: the caller's stream owns the results
         CU_TRY(cudaStreamWaitEvent(stream, plan->ev_elem[0], 0));

@@ -70,6 +70,15 @@ def _worker(rank, world, port, N, structured, ret):
         data = torch.as_tensor(A.data.copy())
         res_t = torch.as_tensor(res)
         ex = partition.ExchangePlan(rm, indptr, indices)
+        # the overlap trigger: every cell that feeds a row sent to a peer lies in [0, send_cell_prefix)
+        pre = ex.send_cell_prefix()
+        sent = np.zeros(nl, dtype=bool)
+        for nodes in rm.send_nodes.values():
+            sent[nodes] = True
+        feeds = sent[rm.cells[:rm.n_owned_cells]].any(axis=1)
+        assert not feeds[pre:].any() and (pre == 0 or feeds[pre - 1])
+        if structured and rank > 0:
+            assert pre == N * N                      # one layer of cells of a z-slab
         ex.exchange(res_t, data)
         nrm = ex.global_res_norm(res_t).item()
         # global truth
