@@ -140,20 +140,23 @@ def cpu_reference(n_mesh, sample_cells, steps, warmup):
     for s in range(1, PRE_STEPS + 1):
         params = fe.update_int_vars_gp(disp(s), params, DT)
     sol = disp(PRE_STEPS + 1)
-    t_upd, t_asm = [], []
+    t_upd, t_asm, t_csr = [], [], []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         fe.update_int_vars_gp(sol, params, DT)
         t1 = time.perf_counter()
         res, V = fe.newton_update(sol, params, DT)
-        A = O.csr_from_coo(V, fe.I, fe.J, fe.nn * 3)
+        tc = time.perf_counter()
+        A = O.csr_from_coo(V, fe.I, fe.J, fe.nn * 3)       # the reference's own get_A line (solver.py:281): scipy, one core
         t2 = time.perf_counter()
         if it >= warmup:
             t_upd.append(t1 - t0)
             t_asm.append(t2 - t1)
+            t_csr.append(t2 - tc)
     npts = sample_cells * 8
     return {'updates_per_s': npts * len(t_upd) / sum(t_upd), 'assembly_ms_sample': 1e3 * sum(t_asm) / len(t_asm),
             'assembly_us_per_cell': 1e6 * sum(t_asm) / len(t_asm) / sample_cells, 'sample_points': npts,
+            'coo_to_csr_us_per_cell': 1e6 * sum(t_csr) / len(t_csr) / sample_cells,
             'ms_per_step': 1e3 * (sum(t_upd) + sum(t_asm)) / len(t_upd), 'cores': torch.get_num_threads()}
 
 
@@ -173,7 +176,8 @@ def run_reference(args):
                        'sample_cells': sample_cells, 'l2': 'n/a (CPU arm)'},
             'assembly_ms': None, 'assembly_us_per_cell': r['assembly_us_per_cell'],
             'cpu_baseline': {'value': r['updates_per_s'], 'unit': 'quad-point updates/s', 'cores': r['cores'], 'kind': 'port',
-                             'sample': sample, 'assembly_us_per_cell': r['assembly_us_per_cell']},
+                             'sample': sample, 'assembly_us_per_cell': r['assembly_us_per_cell'],
+                             'coo_to_csr_us_per_cell': r['coo_to_csr_us_per_cell']},
             'e2e': {'value': r['updates_per_s'], 'unit': 'quad-point updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -504,7 +508,13 @@ def main():
         cpu = {'value': r['updates_per_s'], 'unit': 'quad-point updates/s', 'cores': r['cores'], 'kind': 'port',
                'sample': f'first {args.cpu_sample_cells} cells ({r["sample_points"]} points) of the same {N}^3 workload, oracle port '
                          f'(torch fp64 + torch.func.jacfwd, restatement - JAX is not installable here)',
-               'assembly_us_per_cell': r['assembly_us_per_cell']}
+               'assembly_us_per_cell': r['assembly_us_per_cell'],
+               'coo_to_csr_us_per_cell': r['coo_to_csr_us_per_cell'],
+               'extrapolated_to_workload': {'update_s': npts_global / r['updates_per_s'],
+                                            'assembly_s': r['assembly_us_per_cell'] * 1e-6 * (npts_global // 8),
+                                            'note': 'per-point / per-cell sample rates x the full mesh (the reference cannot hold '
+                                                    'it: ~110 GB of COO triplets at 200^3); assembly includes the scipy '
+                                                    'COO->CSR step of solver.py:281 (coo_to_csr_us_per_cell, one core)'}}
 
     line = {
         'metric': 'cp_quad_point_updates_per_s', 'value': npts_global * K / (t_upd * 1e-3), 'unit': 'quad-point updates/s',
