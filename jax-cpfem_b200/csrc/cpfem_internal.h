@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/cpfem.h"
 #include "cp_point.cuh"
@@ -39,6 +40,7 @@ struct cpfem_plan {
     // chunk i (load/store- and atomics-bound, plan-owned high-priority stream); two scratch buffers alternate
     double* scratch[2] = {nullptr, nullptr};   // each (90, pitch): P JxW and dP/dH JxW, component-major
     int64_t chunk_cells = 0;                   // cells per assembly chunk
+    std::vector<int64_t> zero_end;             // per chunk: first CSR slot behind the rows that chunks 0..k can touch
     cudaStream_t elem_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_point[2] = {nullptr, nullptr}, ev_elem[2] = {nullptr, nullptr};
     // multi-GPU overlap: cpfem_newton_update records `progress_event` (caller-owned) on its stream once the contributions

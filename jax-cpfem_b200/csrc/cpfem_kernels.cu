@@ -58,6 +58,14 @@ extern "C" int cpfem_version(void) { return 101; }
 // plus an odd number of rows' worth of padding so that the 90 component rows do not sit a power of two apart.
 static inline int64_t scratch_pitch(int64_t chunk_cells) { return ((chunk_cells * 8 + 31) / 32) * 32 + 73 * 32; }
 
+// largest node id among the cells of every assembly chunk (plan set-up: bounds the CSR rows a chunk can touch)
+__global__ void k_chunk_maxnode(const int32_t* __restrict__ cells, int64_t nc, int64_t chunk_cells, int* out) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    const int4 a = *reinterpret_cast<const int4*>(cells + c * 8), b = *reinterpret_cast<const int4*>(cells + c * 8 + 4);
+    atomicMax(&out[c / chunk_cells], max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b.x, b.y), max(b.z, b.w))));
+}
+
 __global__ void k_count_valence(const int32_t* __restrict__ cells, int64_t n, int64_t nn, int64_t* cnt, int* err) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -271,6 +279,28 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
         if (t2 != tmp) cudaFree(t2);
         cudaFree(dmax);
         p->max_valence = (int32_t)maxv;
+    }
+    {
+        // zero_end[k] = first CSR slot behind the rows that the cells of chunks 0..k can touch: the point kernel of chunk
+        // k zero-fills [zero_end[k-1], zero_end[k]) of the values, so the fill is spread over all launches of an assembly
+        // when the cell order follows the node order (structured meshes) and falls back to "everything in chunk 0"
+        // when it does not
+        const int64_t nch = (nc + p->chunk_cells - 1) / p->chunk_cells;
+        int* dmx = nullptr;
+        PLAN_TRY(dev_alloc(&dmx, (size_t)nch));
+        PLAN_TRY(cudaMemsetAsync(dmx, 0, nch * sizeof(int), stream));
+        k_chunk_maxnode<<<blocks(nc), T, 0, stream>>>(p->cells, nc, p->chunk_cells, dmx);
+        std::vector<int> hmx((size_t)nch);
+        cudaError_t e = cudaMemcpyAsync(hmx.data(), dmx, nch * sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(dmx);
+        PLAN_TRY(e);
+        p->zero_end.assign((size_t)nch, 0);
+        int run = 0;
+        for (int64_t k = 0; k < nch; ++k) {
+            run = hmx[(size_t)k] > run ? hmx[(size_t)k] : run;
+            PLAN_TRY(cudaMemcpy(&p->zero_end[(size_t)k], p->indptr + 3 * ((int64_t)run + 1), sizeof(int64_t), cudaMemcpyDeviceToHost));
+        }
     }
     PLAN_TRY(cudaGetLastError());
     p->nbr_ptr = nbr_ptr; p->nbr = nbr;
@@ -704,14 +734,21 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
     const int64_t pl = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;      // point within the chunk
-    // Zero-fill of the CSR values, folded into the first chunk's launch (zero_ptr 16-byte aligned, zero_n doubles): this
-    // kernel is FP64-bound and leaves the HBM write path idle, so the 8 B/entry go out for free instead of as a separate
-    // memset in front of the assembly (2.1 ms of 114 ms at 200^3).  The element kernel of the chunk starts after this grid.
+    // Zero-fill of the CSR values, folded into the point kernels (zero_n doubles from zero_ptr: the slots of the rows this
+    // chunk is the first to touch, plan->zero_end): this kernel is FP64-bound and leaves the HBM write path idle, so the
+    // 8 B/entry go out for free instead of as a separate memset in front of the assembly (2.1 ms of 114 ms at 200^3).
+    // The element kernel of the chunk starts after this grid.
     if (zero_n > 0) {
-        double2* z = reinterpret_cast<double2*>(zero_ptr);
-        const int64_t n2 = zero_n >> 1, T = (int64_t)gridDim.x * PT_BLOCK;
+        double* zp = zero_ptr;
+        int64_t n = zero_n;
+        if (reinterpret_cast<uintptr_t>(zp) & 8u) {            // odd leading entry: the body stores 16 bytes at a time
+            if (pl == 0) zp[0] = 0.0;
+            ++zp; --n;
+        }
+        double2* z = reinterpret_cast<double2*>(zp);
+        const int64_t n2 = n >> 1, T = (int64_t)gridDim.x * PT_BLOCK;
         for (int64_t j = pl; j < n2; j += T) __stcs(z + j, make_double2(0.0, 0.0));
-        if ((zero_n & 1) && pl == 0) zero_ptr[zero_n - 1] = 0.0;
+        if ((n & 1) && pl == 0) zp[n - 1] = 0.0;
     }
     const CpSlipRef slp = stage_slip(slip, s_slip, NS);
     const bool valid = pl < npc;
@@ -1253,9 +1290,9 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
     if (!sol || !res) return set_err(-1, "cpfem_newton_update: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     CU_TRY(cudaMemsetAsync(res, 0, plan->nn * 3 * sizeof(double), stream));
-    // the CSR values are zeroed by the first chunk's point kernel (see k_point_tangent) when the buffer allows 16-byte stores
-    // and there is at least one full block of points to do it; otherwise by a memset
-    const bool fuse_zero = CPFEM_FUSE_ZERO && csr_data && ((uintptr_t)csr_data & 15u) == 0 && plan->nc_active >= 16;
+    // the CSR values are zeroed by the point kernels, chunk by chunk (see k_point_tangent, plan->zero_end), when there is at
+    // least one full block of points to do it; otherwise by a memset
+    const bool fuse_zero = CPFEM_FUSE_ZERO && csr_data && plan->nc_active >= 16;
     if (csr_data && !fuse_zero) CU_TRY(cudaMemsetAsync(csr_data, 0, plan->nnz * sizeof(double), stream));
     if (plan->nc_active == 0) {
         if (plan->progress_event) CU_TRY(cudaEventRecord(plan->progress_event, stream));
@@ -1293,8 +1330,14 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
     k_point_tangent<NS, PW, PPV><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, km, plan->slip, \
                                                                           dt, np, c0 * 8, npc, pitch, PJ, TA, (long long*)status,  \
                                                                           zptr, zn)
-        double* zptr = (fuse_zero && ichunk == 0) ? csr_data : nullptr;
-        const int64_t zn = (fuse_zero && ichunk == 0) ? plan->nnz : 0;
+        // slots [z0, z1): rows first touched by this chunk; the last active chunk takes everything that is left (rows of
+        // ghost-only nodes are never touched but must not hold garbage)
+        // (with a progress event set, peers' contributions may arrive after the first chunk: everything is zeroed there)
+        const bool spread = plan->progress_event == nullptr;
+        const int64_t z0 = (ichunk == 0) ? 0 : (spread ? plan->zero_end[(size_t)ichunk - 1] : plan->nnz);
+        const int64_t z1 = (!spread || c0 + ncc >= plan->nc_active) ? plan->nnz : plan->zero_end[(size_t)ichunk];
+        double* zptr = (fuse_zero && z1 > z0) ? csr_data + z0 : nullptr;
+        const int64_t zn = (fuse_zero && z1 > z0) ? z1 - z0 : 0;
         CP_DISPATCH(plan->ns, pown, per_point(v), CALL);
 #undef CALL
         CU_TRY(cudaGetLastError());
