@@ -4,7 +4,8 @@
 //   k_update_state      K1  one thread per quadrature point: u_grad gather, local Newton, new state
 //   k_residual          K2  one warp per 4 hex8 cells: 32 points (stress) into shared memory, then lane (cell, node a)
 //                           integrates its residual rows and scatter-adds them
-//   k_point_tangent     K3a one thread per point: stress + consistent tangent (x JxW) into a component-major scratch
+//   k_point_tangent     K3a one thread per point: stress + consistent tangent (x JxW) into a component-major scratch;
+//                           also zero-fills the CSR values of the rows its chunk is the first to touch
 //   k_element_tangent   K3b one warp per 4 cells: stages the 32 points of the scratch in shared memory, lane
 //                           (cell, node a) integrates 3 rows of K_e and scatters them into the CSR pattern /
 //                           residual with fp64 atomics (optional COO V)
@@ -40,7 +41,7 @@ int cpfem_set_err(int code, const char* what, cudaError_t e) {
 }
 
 extern "C" const char* cpfem_last_error(void) { return g_last_error.c_str(); }
-extern "C" int cpfem_version(void) { return 101; }
+extern "C" int cpfem_version(void) { return 102; }
 
 #define MAX_VALENCE 16
 // two-stream overlap of the point and element kernels: measured on B200 (r1c), no gain (38.1 vs 37.3 ms at 128^3) - off
