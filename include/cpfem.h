@@ -19,6 +19,7 @@
  *   cpfem_update_state_avg_stress        the two calls above fused (driver order singlecrystal_copper.py:205,227)
  *   cpfem_point_stress_tangent           get_tensor_map()'s tensor_map under vmap, and its jacfwd
  *                                        (models_copper.py:135-137,155-162,251-265)
+ *   cpfem_point_update_state             get_maps()'s update_int_vars_map under vmap (models_copper.py:164-169,267-269)
  *   cpfem_apply_dirichlet                apply_bc_vec + zeroRows                (solver.py:119-133,290-293)
  */
 #ifndef CPFEM_H
@@ -148,6 +149,18 @@ int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* mat, const do
 int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads,
                                int64_t np, const cpfem_state* st, double dt, double* P, double* tangent,
                                int64_t* status, void* stream);
+
+/* update_int_vars_map under vmap (models_copper.py:164-169,267-269): u_grads (np, 9) given explicitly -> new state of
+ * every point (AoS arrays of np points).  The point-wise counterpart of cpfem_update_state. */
+int cpfem_point_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
+                             const cpfem_state* st, const cpfem_state_out* out, double dt, int64_t* status, void* stream);
+
+/* Input validation for the DP-steel form of the state (models_DPsteel_inhomo.py:121-147,185-186): counts the points of a
+ * (np, 81) elastic-tensor array that are NOT of the cubic pattern in the crystal frame (C11 on iiii, C12 on iijj, C44 on
+ * ijij / ijji, zero elsewhere; tolerance rtol x the largest constant).  *bad_count is a device int64 that is accumulated
+ * atomically (zero it first); callers treat a non-zero count as a hard error - the kernels read only C[0,0,0,0],
+ * C[0,0,1,1], C[1,2,1,2]. */
+int cpfem_check_cubic(const double* C, int64_t np, double rtol, int64_t* bad_count, void* stream);
 
 /* Row-elimination Dirichlet conditions on device: res[row] = sol[row] - val  (apply_bc_vec) and, if
  * csr_data != NULL, row := unit row (zeroRows with diag 1).  rows: device int64 (nbc) dof indices. */

@@ -59,6 +59,9 @@ SIGNATURES = {
     'cpfem_avg_stress': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State), c_dbl, c_vp, c_vp, c_vp]),
     'cpfem_point_stress_tangent': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, c_i64, ctypes.POINTER(State),
                                                   c_dbl, c_vp, c_vp, c_vp, c_vp]),
+    'cpfem_point_update_state': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, c_i64, ctypes.POINTER(State),
+                                                ctypes.POINTER(StateOut), c_dbl, c_vp, c_vp]),
+    'cpfem_check_cubic': (ctypes.c_int, [c_vp, c_i64, c_dbl, c_vp, c_vp]),
     'cpfem_apply_dirichlet': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'cpfem_spmv': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     'cpfem_csr_diagonal': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_vp]),

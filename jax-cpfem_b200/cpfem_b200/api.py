@@ -123,7 +123,7 @@ class Plan:
         cache[key] = (weakref.ref(t), val)
         return val
 
-    def _state(self, params: Sequence[torch.Tensor], layout=LAYOUT_AOS, mat: Optional[Material] = None):
+    def _state(self, params: Sequence[torch.Tensor], layout=LAYOUT_AOS, mat: Optional[Material] = None, validate=True):
         """cpfem_state from the reference's internal_vars list (4, 9 or 10 arrays).  With `mat` given, per-point parameter
         arrays that hold one value everywhere (the calibration drivers scale whole arrays, calibration_case4_...py:238-251;
         DP steel shares the rate sensitivity between its phases) are demoted to scalars of a copy of the material, so the
@@ -146,9 +146,34 @@ class Plan:
                 else:
                     setattr(m, name, v)
         if n == 10:
+            if validate:
+                self._check_cubic(ts[9])
             st.C = ts[9].data_ptr()
         st.layout = layout
         return (st, ts) if mat is None else (st, ts, m)
+
+    def _check_cubic(self, C: torch.Tensor, rtol=1e-12):
+        """The kernels read three entries of every point's (3,3,3,3) elastic tensor and assume the cubic pattern in the
+        crystal frame (what the reference builds, models_DPsteel_inhomo.py:121-147).  Anything else - a pre-rotated or a
+        lower-symmetry tensor - would give wrong answers silently, so it is refused: one reduction per distinct tensor
+        (identity + version counter), remembered afterwards."""
+        key = (id(C), C._version)
+        cache = self.__dict__.setdefault('_cubic_cache', {})
+        hit = cache.get(key)
+        if hit is not None and hit() is C:
+            return
+        if C.numel() % 81 != 0:
+            raise ValueError('C_gp must have shape (..., 3, 3, 3, 3)')
+        bad = torch.zeros(1, dtype=torch.int64, device=self.device)
+        check(_lib.lib().cpfem_check_cubic(_ptr(C), int(C.numel() // 81), float(rtol), _ptr(bad), _stream()), 'cpfem_check_cubic')
+        nbad = int(bad.item())
+        if nbad:
+            raise ValueError(f'C_gp: {nbad} of {C.numel() // 81} points hold an elastic tensor that is not cubic in the crystal '
+                             'frame (C11 on iiii, C12 on iijj, C44 on ijij/ijji, zero elsewhere); the crystal-plasticity kernels '
+                             'support the cubic form of the reference only (models_DPsteel_inhomo.py:121-147)')
+        if len(cache) > 16:
+            cache.clear()
+        cache[key] = weakref.ref(C)
 
     def new_status(self):
         return torch.zeros(4, dtype=torch.int64, device=self.device)
@@ -182,9 +207,15 @@ class Plan:
                   'cpfem_update_state_avg_stress')
         return out, sigma
 
-    def update_state_cells(self, mat: Material, sol, params, dt, cell0, ncells, out, status=None, layout=LAYOUT_AOS):
-        """cpfem_update_state_cells: `params` / `out` hold only the points of cells [cell0, cell0+ncells)."""
-        st, ts = self._state(params, layout)
+    def update_state_cells(self, mat: Material, sol, params, dt, cell0, ncells, out, status=None, layout=LAYOUT_AOS,
+                           demote=True):
+        """cpfem_update_state_cells: `params` / `out` hold only the points of cells [cell0, cell0+ncells).  `demote`:
+        per-point parameter arrays of the chunk that hold one value everywhere become scalars of the material (as in
+        update_state); update_state_host resolves that once for the whole state and passes demote=False."""
+        if demote:
+            st, ts, mat = self._state(params, layout, mat)
+        else:
+            st, ts = self._state(params, layout)
         so = StateOut(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), layout)
         check(_lib.lib().cpfem_update_state_cells(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st), ctypes.byref(so),
                                                   float(dt), int(cell0), int(ncells), _ptr(status), _stream()),
@@ -223,6 +254,19 @@ class Plan:
                 self._host_out = [[torch.empty((cc,) + tuple(h.shape[1:]), dtype=torch.float64, device=self.device) for h in hs[:3]]
                                   for _ in range(nbuf)]
                 self._host_key = key
+            # per-point parameter arrays (DP / calibration forms) that hold one value everywhere: demote them to scalars
+            # of the material ONCE, on the host tensors, and stream only the arrays that really vary - every chunk then
+            # runs the same (uniform-parameter / compile-time exponent) kernels as the device-resident path
+            skip = set()
+            if len(hs) >= 9:
+                names = ('gss_a', 'h', 't_sat', 'xm', 'r')
+                vals = [self._uniform_value(h) for h in hs[4:9]]
+                if any(v is not None for v in vals):
+                    mat = Material.from_buffer_copy(mat)
+                    for j, (name, v) in enumerate(zip(names, vals)):
+                        if v is not None:
+                            setattr(mat, name, v)
+                            skip.add(4 + j)
             rot_dev = None
             if cache_rot:
                 rk = getattr(self, '_rot_key', None)             # (weak reference to the host tensor, its version counter)
@@ -230,6 +274,7 @@ class Plan:
                     self._rot_dev = hs[3].to(self.device, non_blocking=True)
                     self._rot_key = (weakref.ref(hs[3]), hs[3]._version)
                 rot_dev = self._rot_dev
+            self._host_bad = torch.zeros(1, dtype=torch.int64, device=self.device)
             ev_in = [torch.cuda.Event() for _ in range(nbuf)]
             ev_cmp = [torch.cuda.Event() for _ in range(nbuf)]
             ev_out = [torch.cuda.Event() for _ in range(nbuf)]
@@ -247,8 +292,8 @@ class Plan:
                     if k >= nbuf:
                         s_in.wait_event(ev_cmp[b])            # the update that read this input buffer is done
                     for j, (d, h) in enumerate(zip(din, hs)):
-                        if j == 3 and rot_dev is not None:
-                            continue                          # resident on the device already
+                        if (j == 3 and rot_dev is not None) or j in skip:
+                            continue                          # resident on the device already / demoted to a scalar
                         d.copy_(h[c0:c0 + n], non_blocking=True)
                     ev_in[b].record(s_in)
                 if rot_dev is not None:
@@ -256,7 +301,7 @@ class Plan:
                 cur.wait_event(ev_in[b])
                 if k >= nbuf:
                     cur.wait_event(ev_out[b])                 # the D2H copy that read this output buffer is done
-                self.update_state_cells(mat, sol_d, din, dt, c0, n, dout, status=status)
+                self._update_cells_demoted(mat, sol_d, din, dt, c0, n, dout, status, skip)
                 ev_cmp[b].record(cur)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_cmp[b])
@@ -267,7 +312,23 @@ class Plan:
             for b in range(min(k, nbuf)):
                 cur.wait_event(ev_out[b])
             cur.synchronize()
+            if len(hs) == 10 and int(self._host_bad.item()):
+                raise ValueError(f'C_gp: {int(self._host_bad.item())} points hold an elastic tensor that is not cubic in the '
+                                 'crystal frame (see Plan._check_cubic); the returned state is invalid')
         return out
+
+    def _update_cells_demoted(self, mat, sol_d, din, dt, c0, n, dout, status, skip):
+        """One chunk of update_state_host: the arrays in `skip` were demoted to scalars of `mat` (NULL pointers)."""
+        st, ts = self._state(din, LAYOUT_AOS, validate=False)
+        if len(din) == 10:          # C_gp of this chunk: violations are counted on the device, read once at the end of the pass
+            check(_lib.lib().cpfem_check_cubic(_ptr(ts[9]), int(n) * 8, 1e-12, _ptr(self._host_bad), _stream()), 'cpfem_check_cubic')
+        for j, name in enumerate(('gss_a', 'h', 't_sat', 'xm', 'r')):
+            if 4 + j in skip:
+                setattr(st, name, None)
+        so = StateOut(dout[0].data_ptr(), dout[1].data_ptr(), dout[2].data_ptr(), LAYOUT_AOS)
+        check(_lib.lib().cpfem_update_state_cells(self._h, ctypes.byref(mat), _ptr(sol_d), ctypes.byref(st), ctypes.byref(so),
+                                                  float(dt), int(c0), int(n), _ptr(status), _stream()),
+              'cpfem_update_state_cells')
 
     def _host_streams(self):
         if getattr(self, '_s_in', None) is None:
@@ -323,6 +384,19 @@ class Plan:
                                                         _ptr(P), _ptr(A), _ptr(status), _stream()),
                   'cpfem_point_stress_tangent')
         return P, A
+
+    def point_update_state(self, mat: Material, u_grads, params, dt, status=None):
+        """update_int_vars_map under vmap (models_copper.py:164-169,267-269): explicit u_grads (np, 3, 3) + state arrays
+        of np points -> (Fp_inv_new, g_new, slip_new)."""
+        with torch.cuda.device(self.device):
+            st, ts, mat = self._state(params, LAYOUT_AOS, mat)
+            ug = _dev_f64(u_grads, self.device)
+            n = int(ug.numel() // 9)
+            out = [torch.empty_like(ts[0]), torch.empty_like(ts[1]), torch.empty_like(ts[2])]
+            so = StateOut(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), LAYOUT_AOS)
+            check(_lib.lib().cpfem_point_update_state(self._h, ctypes.byref(mat), _ptr(ug), n, ctypes.byref(st), ctypes.byref(so),
+                                                      float(dt), _ptr(status), _stream()), 'cpfem_point_update_state')
+        return out
 
     def apply_dirichlet(self, rows, vals, sol, res=None, csr_data=None):
         with torch.cuda.device(self.device):

@@ -214,6 +214,7 @@ class Problem:
     def newton_update(self, sol_list):
         sol = api._dev_f64(sol_list[0], self.device)
         self._last_sol = sol
+        self._drop_fused()
         st = self.plan.new_status()
         res, self.csr_data, V = self.plan.newton_update(self.material, sol, self.internal_vars, self.dt,
                                                         want_csr=True, want_V=self.keep_V, status=st)
@@ -231,6 +232,10 @@ class Problem:
     def set_params(self, params):
         """models_copper.py:284-285."""
         self.internal_vars = [api._dev_f64(v, self.device) for v in params]
+        self._drop_fused()
+
+    def _drop_fused(self):
+        pass
 
 
 class CrystalPlasticityBase(Problem):
@@ -274,12 +279,25 @@ class CrystalPlasticityBase(Problem):
         def tensor_map(u_grad, *state):
             ug = api._dev_f64(u_grad, self.device)
             lead = ug.shape[:-2]
-            flat = [api._dev_f64(s, self.device) for s in state]
+            flat = []
+            for s in state:
+                t = api._dev_f64(s, self.device)
+                flat.append(t.reshape((-1,) + tuple(t.shape[len(lead):])))
             P, _ = self.plan.point_stress_tangent(self.material, ug.reshape(-1, 3, 3), flat, self.dt, want_tangent=False)
             return P.reshape(*lead, 3, 3)
 
         def update_int_vars_map(u_grad, *state):
-            raise NotImplementedError('use update_int_vars_gp (the reference only calls the map through it)')
+            """models_copper.py:164-169,267-269: (u_grad, *state) -> (Fp_inv_new, slip_resistance_new, slip_new); a single
+            point (u_grad (3,3), state arrays without batch axes) or any batch of points."""
+            ug = api._dev_f64(u_grad, self.device)
+            lead = ug.shape[:-2]
+            flat = []
+            for k, s in enumerate(state):
+                t = api._dev_f64(s, self.device)
+                tail = t.shape[len(lead):]
+                flat.append(t.reshape((-1,) + tuple(tail)))
+            new = self.plan.point_update_state(self.material, ug.reshape(-1, 3, 3), flat, self.dt)
+            return tuple(n.reshape(tuple(lead) + tuple(n.shape[1:])) for n in new)
         return tensor_map, update_int_vars_map
 
     def tensor_map_jacobian(self, u_grad, *state):
@@ -293,7 +311,11 @@ class CrystalPlasticityBase(Problem):
     # The drivers call compute_avg_stress(sol, params) and then update_int_vars_gp(sol, params) with the SAME arguments
     # (singlecrystal_copper.py:205,227): both need the same converged local solve.  With fuse_avg_stress (default) the
     # first of the two calls runs the fused kernel and keeps the other result for the second call; the key is the
-    # identity + version counter of every argument tensor and dt, so any change of the inputs falls back to a fresh run.
+    # identity + version counter of every argument tensor, dt and the bytes of the material, so any change of the inputs
+    # falls back to a fresh run.  The kept result is dropped by the second call of the pair and by set_params /
+    # newton_update (the next things a driver loop does), so a lone call does not pin a second copy of the state for long.
+    # The library's own kernels write through raw pointers without bumping torch's version counter: callers that update a
+    # params tensor IN PLACE through api.Plan(..., out=...) between the two calls must set fuse_avg_stress = False.
     fuse_avg_stress = True
 
     @staticmethod
@@ -303,6 +325,9 @@ class CrystalPlasticityBase(Problem):
             return None
         return (float(dt),) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
 
+    def _drop_fused(self):
+        self._fuse_cache = None
+
     def _fused(self, sol, params):
         """Runs (or recalls) the fused update + average stress for these arguments: returns (new_state, sigma) or None."""
         if not self.fuse_avg_stress:
@@ -310,6 +335,7 @@ class CrystalPlasticityBase(Problem):
         key = self._fuse_key(sol, params, self.dt)
         if key is None:
             return None
+        key = key + (bytes(self.material),)       # a changed parameter set is a different computation
         hit = getattr(self, '_fuse_cache', None)
         if hit is not None and hit[0] == key:
             self._fuse_cache = None               # second call of the pair: hand over and forget (holds no extra memory)

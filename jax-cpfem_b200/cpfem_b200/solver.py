@@ -36,6 +36,12 @@ def _bc_rows_vals(problem):
             rows = onp.concatenate([onp.asarray(n, dtype=onp.int64) * fe.vec + onp.asarray(v, dtype=onp.int64) + problem.offset[0]
                                     for n, v in zip(fe.node_inds_list, fe.vec_inds_list)])
             vals = onp.concatenate([onp.asarray(v, dtype=onp.float64) for v in fe.vals_list])
+            # A dof named by several Dirichlet sets: the reference applies the sets one after the other (solver.py:125-131),
+            # so the LAST one wins.  One kernel thread per entry would race on such a dof - keep its last occurrence only.
+            _, first_rev = onp.unique(rows[::-1], return_index=True)
+            if len(first_rev) != len(rows):
+                keep = onp.sort(len(rows) - 1 - first_rev)
+                rows, vals = rows[keep], vals[keep]
         else:
             rows, vals = onp.zeros(0, onp.int64), onp.zeros(0, onp.float64)
         dev = problem.device
@@ -61,15 +67,16 @@ def get_A(problem, solver_options=None):
     return problem.csr_data
 
 
-def jax_solve(problem, A, b, x0, precond, restarts=3):
+def jax_solve(problem, A, b, x0, precond, restarts=0):
     """solver.py:19-48: Jacobi-preconditioned BiCGStab (tol = atol = 1e-10, maxiter = 10000) + acceptance test.
 
-    One deliberate difference, `restarts`: BiCGStab can break down (JAX's codes -10 / -11: rho or omega vanish - it
-    happens on the tangents of the drivers whose boundary conditions leave a rigid rotation free).  The
-    reference then returns the stagnated iterate, which passes its `err < 0.1` test however poor it is, and the Newton loop
-    absorbs the damage.  Here the solve is restarted from that iterate (at most `restarts` times) while it is still above
-    the requested tolerance, so the increment - and with it the run-to-run reproducibility of the Newton path - does not
-    depend on where a breakdown happens to strike.  `restarts=0` is the reference's behaviour."""
+    `restarts` (default 0 = the reference's behaviour): BiCGStab can break down (JAX's codes -10 / -11: rho or omega
+    vanish - it happens on the tangents of the drivers whose boundary conditions leave a rigid rotation free, SURVEY
+    App. H.1).  The reference then returns the stagnated iterate, which passes its `err < 0.1` test however poor it is, and
+    the Newton loop absorbs the damage.  With `restarts` > 0 (solver_options['jax_solver']['restarts']) the solve is
+    restarted from that iterate (at most `restarts` times) while it is still above the requested tolerance, so the
+    increment - and with it the run-to-run reproducibility of the Newton path - does not depend on where a breakdown
+    happens to strike.  problem.last_linear_restarts records how many restarts a solve took."""
     x, k, err = problem.plan.bicgstab(A, b, x0=x0, precond=precond, tol=1e-10, atol=1e-10, maxiter=10000)
     total = max(k, 0)
     tries = 0
@@ -80,6 +87,7 @@ def jax_solve(problem, A, b, x0, precond, restarts=3):
         tries += 1
     logger.debug('device BiCGStab: %d iterations, res = %g', total, err)
     problem.last_linear_iterations = total if k >= 0 else k
+    problem.last_linear_restarts = tries
     assert err < 0.1, f'linear solver failed to converge with err = {err}'
     return x
 
@@ -98,7 +106,7 @@ def linear_solver(problem, A, b, x0, solver_options):
         solver_options['jax_solver'] = {}
     if 'jax_solver' in solver_options:
         precond = solver_options['jax_solver'].get('precond', True)
-        return jax_solve(problem, A, b, x0, precond, restarts=solver_options['jax_solver'].get('restarts', 3))
+        return jax_solve(problem, A, b, x0, precond, restarts=solver_options['jax_solver'].get('restarts', 0))
     if 'umfpack_solver' in solver_options:
         return umfpack_solve(problem, A, b)
     if 'custom_solver' in solver_options:

@@ -44,6 +44,18 @@
 #endif
 
 #define CP_MAX_NS 24
+// Two tuning switches, both measured on B200 at 200^3 (profiles/r2/a_variants_n200.txt):
+#ifndef CP_FAST_RCP
+#define CP_FAST_RCP 1     // reciprocals as MUFU.RCP64H + two Newton steps (cp_rcp) instead of the IEEE division sequence:
+                          // update 61.07 -> 59.52 ms, assembly 114.19 -> 109.48 ms
+#endif
+#ifndef CP_TAIL2
+#define CP_TAIL2 1        // active slip set padded to a multiple of 2 instead of 4 (groups of 4, then one group of 2):
+                          // update 61.07 -> 58.56 ms, assembly 114.19 -> 113.18 ms
+#endif
+#ifndef CP_NM_ODD1
+#define CP_NM_ODD1 0      // experiment: single-system tail in cp_newton_matrix instead of a half-empty pair
+#endif
 #ifndef CP_TRACE_X
 #define CP_TRACE_X(a, ax)      // test hook (tests only): observe |tau/g| of every residual evaluation
 #endif
@@ -106,6 +118,21 @@ inline bool cp_slip_init(CpSlip* sl, const double* slip6, int ns) {
     return true;
 }
 
+// 1/x for a normal, finite x.  CP_FAST_RCP: hardware seed (about 20 bits) + two Newton steps = within 1 ulp, without the
+// range checks and the correction step of the correctly rounded division.
+CP_HD double cp_rcp(double x) {
+#if CP_FAST_RCP && defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
+
 struct CpPointParams {   // per-point values actually used at one quadrature point
     double C11, C12, C44, n_exp /* = 1/xm */;     // needed inside the local Newton solve
     double S11, S12, S44h;                        // cubic compliance: (C11+C12)/den, -C12/den, 1/(2 C44)
@@ -120,10 +147,10 @@ CP_HD double cp_x_lo(double n_exp) {
     return (n_exp > 1.0) ? exp(-46.051701859880914 / (n_exp - 1.0)) : 0.0;     // 1e-20 ^ (1/(n-1))
 }
 CP_HD void cp_params_elastic(CpPointParams& pm, double C11, double C12, double C44, double xm, double x_lo = -1.0) {
-    pm.C11 = C11; pm.C12 = C12; pm.C44 = C44; pm.n_exp = 1.0 / xm;
+    pm.C11 = C11; pm.C12 = C12; pm.C44 = C44; pm.n_exp = 1.0 / xm;     // exact: 1/(1/120) must be the integer 120
     pm.x_lo = (x_lo >= 0.0) ? x_lo : cp_x_lo(pm.n_exp);
-    const double iden = 1.0 / ((C11 - C12) * (C11 + 2.0 * C12));
-    pm.S11 = (C11 + C12) * iden; pm.S12 = -C12 * iden; pm.S44h = 0.5 / C44;
+    const double iden = cp_rcp((C11 - C12) * (C11 + 2.0 * C12));
+    pm.S11 = (C11 + C12) * iden; pm.S12 = -C12 * iden; pm.S44h = 0.5 * cp_rcp(C44);
 }
 
 // Per-thread array of one double per slip system.  STRIDE = 1 on the host; on the device the kernels point it at
@@ -164,7 +191,7 @@ CP_HD double m3_det(const double* M) {
 CP_HD void m3_inv(const double* M, double* Mi, double* det_out) {
     double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
     double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
-    double id = 1.0 / det;
+    double id = cp_rcp(det);
     Mi[0] = c00 * id; Mi[1] = (M[2] * M[7] - M[1] * M[8]) * id; Mi[2] = (M[1] * M[5] - M[2] * M[4]) * id;
     Mi[3] = c01 * id; Mi[4] = (M[0] * M[8] - M[2] * M[6]) * id; Mi[5] = (M[2] * M[3] - M[0] * M[5]) * id;
     Mi[6] = c02 * id; Mi[7] = (M[1] * M[6] - M[0] * M[7]) * id; Mi[8] = (M[0] * M[4] - M[1] * M[3]) * id;
@@ -276,6 +303,31 @@ CP_HD int cp_popc(unsigned m) {
 #endif
 }
 
+// Power law, w and the Lp accumulation for the next U systems of the set `m` (lowest bits first; they are removed from m).
+template <int POWN, int U, class Arr>
+CP_HD void cp_slip_group(const CpSlipRef& sl, const CpPointParams& pm, double cdt, double cn, double n1, const Arr& ginv,
+                         const Arr& w, unsigned& m, double* Lp) {
+    int a[U];
+    double x[U], ax[U], pw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        a[u] = cp_ffs0(m);
+        m &= m - 1u;
+        x[u] = w[a[u]];
+        ax[u] = fabs(x[u]);
+    }
+    cp_rate_pow<POWN, U>(ax, n1, pw);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const CpSlipSys& y = sl.d->sys[a[u]];
+        if (!(ax[u] >= pm.x_lo)) pw[u] = 0.0;
+        const double dg = (cdt * pw[u]) * x[u];
+        w[a[u]] = (cn * pw[u]) * ginv[a[u]];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Lp[i] += dg * y.M[i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One residual evaluation at s (crystal frame).  Also leaves what the next Newton matrix needs (w, Fe).
 //   tau_a  = d_a . S n_a = etilde_a . (D s)            (models_copper.py:173)
@@ -319,9 +371,10 @@ CP_HD double cp_residual(const CpSlipRef& sl, const CpPointParams& pm, double cd
         }
         unsigned m = cp_warp_or(act);
         mact = m;
-        // pad the set to a multiple of U with inactive systems (they are evaluated honestly: tiny values)
+        // pad the set to a multiple of U (CP_TAIL2: of 2) with inactive systems (they are evaluated honestly: tiny values)
         {
-            const int k = (U - (cp_popc(m) & (U - 1))) & (U - 1);
+            constexpr int PADTO = CP_TAIL2 ? 2 : U;
+            const int k = (PADTO - (cp_popc(m) & (PADTO - 1))) & (PADTO - 1);
             for (int i = 0; i < k; ++i) {
                 const unsigned z = ~m & ((NS == 32) ? 0xffffffffu : ((1u << NS) - 1u));
                 m |= z & (0u - z);
@@ -329,25 +382,13 @@ CP_HD double cp_residual(const CpSlipRef& sl, const CpPointParams& pm, double cd
         }
         mask = m;
         while (m) {
-            int a[U];
-            double x[U], ax[U], pw[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                a[u] = cp_ffs0(m);
-                m &= m - 1u;
-                x[u] = w[a[u]];
-                ax[u] = fabs(x[u]);
+#if CP_TAIL2
+            if (cp_popc(m) == 2) {
+                cp_slip_group<POWN, 2>(sl, pm, cdt, cn, n1, ginv, w, m, Lp);
+                break;
             }
-            cp_rate_pow<POWN, U>(ax, n1, pw);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const CpSlipSys& y = sl.d->sys[a[u]];
-                if (!(ax[u] >= pm.x_lo)) pw[u] = 0.0;
-                const double dg = (cdt * pw[u]) * x[u];
-                w[a[u]] = (cn * pw[u]) * ginv[a[u]];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) Lp[i] += dg * y.M[i];
-            }
+#endif
+            cp_slip_group<POWN, U>(sl, pm, cdt, cn, n1, ginv, w, m, Lp);
         }
     }
     // Fe = G - G Lp
@@ -356,19 +397,21 @@ CP_HD double cp_residual(const CpSlipRef& sl, const CpPointParams& pm, double cd
 #pragma unroll
         for (int j = 0; j < 3; ++j)
             Fe[3 * i + j] = G[3 * i + j] - (G[3 * i] * Lp[j] + G[3 * i + 1] * Lp[3 + j] + G[3 * i + 2] * Lp[6 + j]);
-    // E = 1/2 (Fe^T Fe - I)
-    const double E0 = 0.5 * (Fe[0] * Fe[0] + Fe[3] * Fe[3] + Fe[6] * Fe[6] - 1.0);
-    const double E1 = 0.5 * (Fe[1] * Fe[1] + Fe[4] * Fe[4] + Fe[7] * Fe[7] - 1.0);
-    const double E2 = 0.5 * (Fe[2] * Fe[2] + Fe[5] * Fe[5] + Fe[8] * Fe[8] - 1.0);
-    const double E3 = 0.5 * (Fe[1] * Fe[2] + Fe[4] * Fe[5] + Fe[7] * Fe[8]);
-    const double E4 = 0.5 * (Fe[0] * Fe[2] + Fe[3] * Fe[5] + Fe[6] * Fe[8]);
-    const double E5 = 0.5 * (Fe[0] * Fe[1] + Fe[3] * Fe[4] + Fe[6] * Fe[7]);
-    r[0] = s[0] - (pm.C11 * E0 + pm.C12 * (E1 + E2));
-    r[1] = s[1] - (pm.C11 * E1 + pm.C12 * (E0 + E2));
-    r[2] = s[2] - (pm.C11 * E2 + pm.C12 * (E0 + E1));
-    r[3] = s[3] - 2.0 * pm.C44 * E3;
-    r[4] = s[4] - 2.0 * pm.C44 * E4;
-    r[5] = s[5] - 2.0 * pm.C44 * E5;
+    // E2x = 2 E = Fe^T Fe - I; the 1/2 rides on the elastic constants (a multiplication by 0.5 is exact, so
+    // (C/2) (2E) == C E bit for bit) and the 2 C44 (1/2) of the shear rows cancels
+    const double E0 = Fe[0] * Fe[0] + Fe[3] * Fe[3] + Fe[6] * Fe[6] - 1.0;
+    const double E1 = Fe[1] * Fe[1] + Fe[4] * Fe[4] + Fe[7] * Fe[7] - 1.0;
+    const double E2 = Fe[2] * Fe[2] + Fe[5] * Fe[5] + Fe[8] * Fe[8] - 1.0;
+    const double E3 = Fe[1] * Fe[2] + Fe[4] * Fe[5] + Fe[7] * Fe[8];
+    const double E4 = Fe[0] * Fe[2] + Fe[3] * Fe[5] + Fe[6] * Fe[8];
+    const double E5 = Fe[0] * Fe[1] + Fe[3] * Fe[4] + Fe[6] * Fe[7];
+    const double C11h = 0.5 * pm.C11, C12h = 0.5 * pm.C12;
+    r[0] = s[0] - (C11h * E0 + C12h * (E1 + E2));
+    r[1] = s[1] - (C11h * E1 + C12h * (E0 + E2));
+    r[2] = s[2] - (C11h * E2 + C12h * (E0 + E1));
+    r[3] = s[3] - pm.C44 * E3;
+    r[4] = s[4] - pm.C44 * E4;
+    r[5] = s[5] - pm.C44 * E5;
     return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + 2.0 * (r[3] * r[3] + r[4] * r[4] + r[5] * r[5]));
 }
 
@@ -403,8 +446,14 @@ CP_HD void cp_newton_matrix(const CpSlipRef& sl, const CpPointParams& pm, const 
             m &= m - 1u;
             w2[1] = w[a2[1]];
         }
+#if CP_NM_ODD1
+        const int nu = (w2[1] == 0.0 && a2[1] == a2[0]) ? 1 : 2;
+#pragma unroll 1
+        for (int u = 0; u < nu; ++u) {
+#else
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
+#endif
             const CpSlipSys& y = sl.d->sys[a2[u]];
             const double k0 = K[0] * y.d[0] + K[1] * y.d[1] + K[2] * y.d[2];
             const double k1 = K[3] * y.d[0] + K[4] * y.d[1] + K[5] * y.d[2];
@@ -422,7 +471,7 @@ CP_HD void cp_newton_matrix(const CpSlipRef& sl, const CpPointParams& pm, const 
     // in-place LU (Doolittle), no pivoting
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        const double ip = 1.0 / N[6 * k + k];
+        const double ip = cp_rcp(N[6 * k + k]);
         piv[k] = ip;
 #pragma unroll
         for (int i = k + 1; i < 6; ++i) {
@@ -567,7 +616,7 @@ CP_HD void cp_point_solve(const CpSlipRef& sl, const CpMaterial& mat, const CpPo
         m3_mul(Fc, Ac, ps.G);
     }
 #pragma unroll 4
-    for (int a = 0; a < NS; ++a) ps.ginv[a] = 1.0 / g[a];
+    for (int a = 0; a < NS; ++a) ps.ginv[a] = cp_rcp(g[a]);
     ps.cdt = mat.ao * dt;
     cp_newton<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp,
                         ps.mask, ps.mact, ps.info);
@@ -594,7 +643,7 @@ CP_HD void cp_point_state_update(const CpSlipRef& sl, const CpPointParams& pm, c
         cp_to_lab(R, Anc, A_new_lab);
     }
     const double s3 = ps.s[3] + ps.s[3], s4 = ps.s[4] + ps.s[4], s5 = ps.s[5] + ps.s[5];
-    const double inv_n = 1.0 / pm.n_exp, inv_tsat = 1.0 / pm.t_sat;
+    const double inv_n = cp_rcp(pm.n_exp), inv_tsat = cp_rcp(pm.t_sat);
     double tsum = 0.0;
 #pragma unroll 2
     for (int a = 0; a < NS; ++a) {
@@ -635,7 +684,7 @@ CP_HD void cp_point_stress(const CpPointState<Arr>& ps, const double* R, double*
         for (int i = 0; i < 9; ++i) ImL[i] = -ps.Lp[i];
         ImL[0] += 1.0; ImL[4] += 1.0; ImL[8] += 1.0;
         m3_mul(ps.Ac, ImL, Anc);
-        ax.idet = 1.0 / m3_det(Anc);
+        ax.idet = cp_rcp(m3_det(Anc));
         m3_mul(R, Anc, ax.RAn);
     }
     m3_mul(R, ps.Fe, ax.RFe);

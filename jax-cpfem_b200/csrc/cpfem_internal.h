@@ -38,7 +38,7 @@ struct cpfem_plan {
     int32_t* nbr = nullptr;       // (nnz / 9)
     // assembly pipeline: the point kernel of chunk i+1 (FP64-bound, caller's stream) overlaps the element kernel of
     // chunk i (load/store- and atomics-bound, plan-owned high-priority stream); two scratch buffers alternate
-    double* scratch[2] = {nullptr, nullptr};   // each (90, pitch): P JxW and dP/dH JxW, component-major
+    double* scratch[2] = {nullptr, nullptr};   // each (quads, 90, 32): P JxW and dP/dH JxW, quad-major (SCR_QUAD)
     int64_t chunk_cells = 0;                   // cells per assembly chunk
     std::vector<int64_t> zero_end;             // per chunk: first CSR slot behind the rows that chunks 0..k can touch
     cudaStream_t elem_stream = nullptr;

@@ -41,7 +41,7 @@ int cpfem_set_err(int code, const char* what, cudaError_t e) {
 }
 
 extern "C" const char* cpfem_last_error(void) { return g_last_error.c_str(); }
-extern "C" int cpfem_version(void) { return 102; }
+extern "C" int cpfem_version(void) { return 200; }
 
 #define MAX_VALENCE 16
 // two-stream overlap of the point and element kernels: measured on B200 (r1c), no gain (38.1 vs 37.3 ms at 128^3) - off
@@ -55,9 +55,12 @@ extern "C" int cpfem_version(void) { return 102; }
 #define CPFEM_CHUNK_CELLS (1 << 19)   // 4 Mi points per assembly chunk: 3.0 GB of scratch
 #endif
 
-// Row pitch (in doubles) of the component-major assembly scratch: the points of a chunk rounded up to a 256-byte row,
-// plus an odd number of rows' worth of padding so that the 90 component rows do not sit a power of two apart.
-static inline int64_t scratch_pitch(int64_t chunk_cells) { return ((chunk_cells * 8 + 31) / 32) * 32 + 73 * 32; }
+// Assembly scratch, quad-major: the 32 quadrature points of a quad of four cells (= one warp of the point kernel, one
+// warp trip of the element kernel) own SCR_QUAD = 90 x 32 contiguous doubles, [component][point]: components 0..8 = P JxW,
+// 9..89 = dP/dH JxW.  A warp of the point kernel writes 90 coalesced 256-byte rows inside one 23 kB region, and the
+// element kernel fetches a whole slice (27 components = 6912 contiguous bytes) with ONE bulk copy.
+#define SCR_QUAD (90 * 32)
+static inline size_t scratch_doubles(int64_t chunk_cells) { return (size_t)((chunk_cells + 3) / 4) * SCR_QUAD; }
 
 // largest node id among the cells of every assembly chunk (plan set-up: bounds the CSR rows a chunk can touch)
 __global__ void k_chunk_maxnode(const int32_t* __restrict__ cells, int64_t nc, int64_t chunk_cells, int* out) {
@@ -255,8 +258,8 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
         }
         {
             const bool two = p->chunk_cells < nc;
-            PLAN_TRY(dev_alloc(&p->scratch[0], (size_t)90 * scratch_pitch(p->chunk_cells)));
-            if (two && CPFEM_OVERLAP) PLAN_TRY(dev_alloc(&p->scratch[1], (size_t)90 * scratch_pitch(p->chunk_cells)));
+            PLAN_TRY(dev_alloc(&p->scratch[0], scratch_doubles(p->chunk_cells)));
+            if (two && CPFEM_OVERLAP) PLAN_TRY(dev_alloc(&p->scratch[1], scratch_doubles(p->chunk_cells)));
             int lo = 0, hi = 0;
             PLAN_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
             PLAN_TRY(cudaStreamCreateWithPriority(&p->elem_stream, cudaStreamNonBlocking, hi));
@@ -730,7 +733,7 @@ template <int NS, int POWN, bool PP>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
                 StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip, double dt, int64_t np, int64_t p0,
-                int64_t npc, int64_t pitch, double* __restrict__ PJ, double* __restrict__ TA, long long* status,
+                int64_t npc, double* __restrict__ scratch, long long* status,
                 double* __restrict__ zero_ptr, int64_t zero_n) {
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
@@ -772,10 +775,11 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
     CpStressAux ax;
     cp_point_stress(ps, R, P, ax);
     if (valid) {
+        double* sq = scratch + (pl >> 5) * SCR_QUAD + (pl & 31);          // this point's column of its quad's block
 #pragma unroll
-        for (int i = 0; i < 9; ++i) __stcs(PJ + i * pitch + pl, P[i] * JxW);
-        double* ta = TA + pl;
-        cp_point_tangent<NS>(slp, ps, ax, P, JxW, ps.ginv, [ta, pitch](int ij, int kl, double v) { __stcs(ta + (int64_t)(9 * ij + kl) * pitch, v); });
+        for (int i = 0; i < 9; ++i) __stcs(sq + i * 32, P[i] * JxW);
+        double* ta = sq + 9 * 32;
+        cp_point_tangent<NS>(slp, ps, ax, P, JxW, ps.ginv, [ta](int ij, int kl, double v) { __stcs(ta + (9 * ij + kl) * 32, v); });
     }
     warp_status(ps.info, valid, status);
 }
@@ -798,8 +802,19 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
 #define EL_GN (4 * GN_CELL)              // shape gradients [cell][q][b][3]
 #define EL_KE (32 * KE_ROW)              // K_e row tile [32 lanes][KE_ROW]; at quad start the same space holds the transposed
                                          // gradients GA[cell][a][q][3] (768 doubles) until every lane has its own in registers
-#define EL_MISC (32 + 32 * 4 + 2)        // ROWP int64[32], RB int[32][8], two mbarriers
-#define ELEM_WARP_DOUBLES (2 * EL_TS + EL_GN + EL_KE + EL_MISC)     // 3466 doubles = 27.7 kB per warp
+#define EL_MISC (32 + 32 * 4 + 2 + 32)   // ROWP int64[32], RB int[32][8], two mbarriers, LIVE uint8[256]
+#define ELEM_WARP_DOUBLES (2 * EL_TS + EL_GN + EL_KE + EL_MISC)     // 3498 doubles = 28.0 kB per warp
+// Warp-aggregated scatter (CPFEM_MERGE_ATOMICS): cells of a quad that share a face give (node a, node b) blocks twice
+// - 48 of the 256 blocks of four x-neighbours.  The duplicates are found once per quad (rows of the same node by
+// __match_any_sync, columns by their rank in that node's neighbour list), summed in the shared K_e tile, and the scatter
+// walks a compacted list of the distinct blocks: one fp64 atomic per distinct CSR slot (-19 % atomics on structured meshes).
+// Measured on B200 at 200^3 (profiles/r2/b_variants_n200.txt): assembly 108.2 ms with the merge against 107.4 ms without -
+// the kernel is bound on the SM side (shared-memory wavefronts and issue slots, see profiles/r2/a_element_source_lines.txt),
+// not by the L2 atomic units (profiles/r2/a_red_probe.txt: 200-530 G fp64 atomics/s), so the extra tile traffic of the
+// merge costs more than the 19 % fewer atomics return.  Kept as a build option, off by default.
+#ifndef CPFEM_MERGE_ATOMICS
+#define CPFEM_MERGE_ATOMICS 0
+#endif
 #ifndef ELEM_WARPS
 #define ELEM_WARPS 8                     // 222 kB and 256 x 255 registers per block: one block fills an SM (measured on B200 at
                                          // 64^3: 6 / 7 / 8 warps -> 1.46 / 1.27 / 1.14 ms; the previous LDG+STS-staged kernel: 1.19 ms)
@@ -829,16 +844,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
-// warp-collective: rows [0, nrows) of `src` (row pitch `pitch` doubles, 32 doubles each) -> dst, completion on `bar`
-__device__ __forceinline__ void el_fill(uint32_t dst, uint32_t bar, const double* src, int64_t pitch, int nrows, int lane) {
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)nrows * 256u);
-    __syncwarp();
-    if (lane < nrows) bulk_g2s(dst + (uint32_t)lane * 256u, src + (int64_t)lane * pitch, 256u, bar);
+// warp-collective: `nrows` consecutive component rows (32 doubles each) of a quad's scratch block -> dst, one bulk copy,
+// completion on `bar`
+__device__ __forceinline__ void el_fill(uint32_t dst, uint32_t bar, const double* src, int nrows, int lane) {
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)nrows * 256u);
+        bulk_g2s(dst, src, (uint32_t)nrows * 256u, bar);
+    }
 }
 
 __global__ void __launch_bounds__(ELEM_WARPS * 32, 1)
 k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, int64_t c0, int64_t ncc,
-                  int64_t pitch, const double* __restrict__ PJg, const double* __restrict__ TAg,
+                  const double* __restrict__ scratch,
                   const int64_t* __restrict__ indptr, const uint8_t* __restrict__ rank, double* __restrict__ res,
                   double* __restrict__ csr_data, double* __restrict__ coo_V) {
     extern __shared__ __align__(128) double smem_el[];
@@ -849,6 +866,7 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
     long long* ROWP = reinterpret_cast<long long*>(KE + EL_KE);       // [32] CSR slot of the row start (or -1)
     int* RB = reinterpret_cast<int*>(ROWP + 32);                      // [32][8] column-block offsets
     unsigned long long* BAR = reinterpret_cast<unsigned long long*>(RB + 32 * 8);
+    uint8_t* LIVE = reinterpret_cast<uint8_t*>(BAR + 2);               // [256] distinct (lane, b) blocks of the quad, compacted
     const uint32_t ts_a[2] = {smem_u32(TS), smem_u32(TS + EL_TS)};
     const uint32_t bar_a[2] = {smem_u32(BAR), smem_u32(BAR + 1)};
     if (lane == 0) {
@@ -858,12 +876,13 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
     }
     __syncwarp();
     const int cl = lane >> 3, a = lane & 7;
+    const int sc_m = lane / 3, sc_k = lane - 3 * (lane / 3);           // scatter role: block sc_m of ten, entry sc_k
     const int64_t nquads = (ncc + 3) >> 2;
     const int64_t stride = (int64_t)gridDim.x * ELEM_WARPS;
     int64_t quad = (int64_t)blockIdx.x * ELEM_WARPS + warp;
     if (quad < nquads) {                     // prologue: slice 0 -> buffer 0, P JxW -> buffer 1
-        el_fill(ts_a[0], bar_a[0], TAg + quad * 32, pitch, 27, lane);
-        el_fill(ts_a[1], bar_a[1], PJg + quad * 32, pitch, 9, lane);
+        el_fill(ts_a[0], bar_a[0], scratch + quad * SCR_QUAD + 9 * 32, 27, lane);
+        el_fill(ts_a[1], bar_a[1], scratch + quad * SCR_QUAD, 9, lane);
     }
     for (; quad < nquads; quad += stride) {
         const int64_t next = quad + stride;
@@ -907,6 +926,46 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
                 RB[lane * 8 + 4 + b] = 3 * (int)((rk.y >> (8 * b)) & 0xffu);
             }
         }
+#if CPFEM_MERGE_ATOMICS
+        // ---- duplicate (row node, column node) blocks inside the quad: found once, used by the three slices ----
+        int n_live3 = 0, lead = lane, frank = 0, maxrank = 0;
+        unsigned fol = 0x88888888u;          // nibble b: position of my column b in the leader row's list, 8 = none
+        if (csr_data) {
+            const unsigned grp = __match_any_sync(0xffffffffu, valid ? (int)na : -1 - lane);
+            lead = __ffs((int)grp) - 1;                                  // first lane of the quad with the same node
+            frank = __popc(grp & ((1u << lane) - 1u));                   // 0 = that lane, 1.. = the followers, in lane order
+            maxrank = __reduce_max_sync(0xffffffffu, (unsigned)frank);
+            __syncwarp();                                                // RB of every lane is visible
+            unsigned livemask = valid ? 0xffu : 0u;
+            if (frank > 0) {
+                int lb[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) lb[b] = RB[lead * 8 + b];
+#pragma unroll
+                for (int bp = 0; bp < 8; ++bp) {
+                    const int my = RB[lane * 8 + bp];
+                    unsigned f = 8u;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) f = (lb[b] == my) ? (unsigned)b : f;
+                    fol = (fol & ~(0xfu << (4 * bp))) | (f << (4 * bp));
+                    if (f < 8u) livemask &= ~(1u << bp);
+                }
+            }
+            int incl = __popc(livemask);
+            const int cnt = incl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            n_live3 = 3 * __shfl_sync(0xffffffffu, incl, 31);
+            int off = incl - cnt;
+#pragma unroll
+            for (int bp = 0; bp < 8; ++bp)
+                if ((livemask >> bp) & 1u) LIVE[off++] = (uint8_t)(lane * 8 + bp);
+            __syncwarp();
+        }
+#endif
         // ---- residual rows from P JxW (buffer 1, first fill of the quad) ----
         mbar_wait(bar_a[1], 0);
         if (res) {
@@ -928,7 +987,7 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
             }
         }
         __syncwarp();                               // buffer 1 is free
-        el_fill(ts_a[1], bar_a[1], TAg + 27 * pitch + quad * 32, pitch, 27, lane);          // slice 1 -> buffer 1
+        el_fill(ts_a[1], bar_a[1], scratch + quad * SCR_QUAD + (9 + 27) * 32, 27, lane);    // slice 1 -> buffer 1
 #pragma unroll 1
         for (int i = 0; i < 3; ++i) {
             const int buf = i & 1;
@@ -966,10 +1025,10 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
             }
             __syncwarp();                           // every lane is done reading this buffer
             if (i == 0) {
-                el_fill(ts_a[0], bar_a[0], TAg + 54 * pitch + quad * 32, pitch, 27, lane);      // slice 2 -> buffer 0
+                el_fill(ts_a[0], bar_a[0], scratch + quad * SCR_QUAD + (9 + 54) * 32, 27, lane);      // slice 2 -> buffer 0
             } else if (next < nquads) {             // next quad: P JxW -> buffer 1 (after slice 1), slice 0 -> buffer 0 (after slice 2)
-                if (i == 1) el_fill(ts_a[1], bar_a[1], PJg + next * 32, pitch, 9, lane);
-                else el_fill(ts_a[0], bar_a[0], TAg + next * 32, pitch, 27, lane);
+                if (i == 1) el_fill(ts_a[1], bar_a[1], scratch + next * SCR_QUAD, 9, lane);
+                else el_fill(ts_a[0], bar_a[0], scratch + next * SCR_QUAD + 9 * 32, 27, lane);
             }
             if (valid && coo_V) {
                 double* v = coo_V + c * 576 + (int64_t)(3 * a + i) * 24;
@@ -982,16 +1041,45 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
                 for (int j = 0; j < 24; ++j) ke[j] = acc[j];
                 ROWP[lane] = (i == 0) ? rp0 : (i == 1) ? rp1 : rp2;
                 __syncwarp();
-                // coalesced scatter: every lane parked its row in shared memory; the 32 x 24 values of the tile then go out as
-                // 24 warp instructions with all 32 lanes busy (1 1/3 rows each: consecutive lanes hit the 24-byte pieces of a
-                // CSR row, x-neighbour pairs are contiguous)
-#pragma unroll 4
-                for (int it = 0; it < 24; ++it) {
-                    const int v = it * 32 + lane;
-                    const int t = v / 24, j = v - 24 * t;
-                    const long long base = ROWP[t];
-                    if (base >= 0) atomicAdd(csr_data + base + RB[t * 8 + j / 3] + (j - 3 * (j / 3)), KE[t * KE_ROW + j]);
+#if CPFEM_MERGE_ATOMICS
+                // follower rows add their duplicate blocks to the first row of the same node (round r: the r-th follower of
+                // every node, so no two lanes update the same entry at once), then the distinct blocks go out: consecutive
+                // lanes take the three k of one block (24 contiguous bytes of a CSR row)
+                for (int rr = 1; rr <= maxrank; ++rr) {
+                    if (frank == rr) {
+#pragma unroll
+                        for (int bp = 0; bp < 8; ++bp) {
+                            const unsigned f = (fol >> (4 * bp)) & 0xfu;
+                            if (f < 8u) {
+                                double* dst = KE + lead * KE_ROW + 3 * (int)f;
+                                dst[0] += ke[3 * bp]; dst[1] += ke[3 * bp + 1]; dst[2] += ke[3 * bp + 2];
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
+#pragma unroll 4
+                for (int e = lane; e < n_live3; e += 32) {
+                    const int pbi = e / 3, k = e - 3 * pbi;
+                    const int pb = LIVE[pbi];
+                    const int t = pb >> 3, b = pb & 7;
+                    atomicAdd(csr_data + ROWP[t] + RB[pb] + k, KE[t * KE_ROW + 3 * b + k]);
+                }
+#else
+                // coalesced scatter: every lane parked its row in shared memory; the 256 (row, neighbour) blocks of the tile
+                // then go out ten per warp instruction - lane = 3 m + k takes entry k of block it*10 + m, so three consecutive
+                // lanes cover the 24 contiguous bytes of a block (x-neighbour blocks are contiguous too) and the row / block
+                // indices are shifts (the former 32-entries-per-instruction walk spent 21 instructions per atomic on index
+                // arithmetic: 21 % of the kernel's instructions, profiles/r2/a_element_source_lines.txt)
+                if (lane < 30) {
+#pragma unroll 2
+                    for (int pb = sc_m; pb < 256; pb += 10) {
+                        const int t = pb >> 3;
+                        const long long base = ROWP[t];
+                        if (base >= 0) atomicAdd(csr_data + base + RB[pb] + sc_k, KE[t * KE_ROW + 3 * (pb & 7) + sc_k]);
+                    }
+                }
+#endif
                 __syncwarp();                       // KE / ROWP free again
             }
         }
@@ -1057,7 +1145,7 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
 template <int NS, int POWN, bool PP>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_point_eval(const double* __restrict__ u_grads, StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip,
-             double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, long long* status) {
+             double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, cpfem_state_out sout, long long* status) {
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
     const CpSlipRef slp = stage_slip(slip, s_slip, NS);
@@ -1082,14 +1170,49 @@ k_point_eval(const double* __restrict__ u_grads, StateView st, const __grid_cons
     CpStressAux ax;
     cp_point_stress(ps, R, P, ax);
     if (valid) {
+        if (Pout) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Pout[p * 9 + i] = P[i];
+            for (int i = 0; i < 9; ++i) Pout[p * 9 + i] = P[i];
+        }
         if (Aout) {
             double* ao = Aout + p * 81;
             cp_point_tangent<NS>(slp, ps, ax, P, 1.0, ps.ginv, [ao](int ij, int kl, double v) { ao[9 * ij + kl] = v; });
         }
+        if (sout.Fp_inv) {          // update_int_vars_map (models_copper.py:164-169,267-269): new state of this point (AoS)
+            double An[9];
+            if (PP) load_point_params_hard(mat, st, p, pmv);
+            cp_point_state_update<NS>(slp, pm, ps, gin(st.g, 0, p, NS, np), gin(st.slip, 0, p, NS, np), R, An,
+                                      gout(sout.g, 0, p, NS, np), gout(sout.slip, 0, p, NS, np));
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sout.Fp_inv[p * 9 + i] = An[i];
+        }
     }
     warp_status(ps.info, valid, status);
+}
+
+// C_gp validation (DP-steel form of the state): the kernels read C[0,0,0,0], C[0,0,1,1] and C[1,2,1,2] of every point's
+// (3,3,3,3) array and assume the rest follows the cubic pattern in the crystal frame (what the reference builds,
+// models_DPsteel_inhomo.py:121-147).  Counts the points where any of the 81 entries deviates from that pattern.
+__global__ void k_check_cubic(const double* __restrict__ C, int64_t np, double rtol, unsigned long long* bad) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int isbad = 0;
+    if (p < np) {
+        const double* c = C + p * 81;
+        const double C11 = c[0], C12 = c[4], C44 = c[50];
+        const double tol = rtol * fmax(fabs(C11), fmax(fabs(C12), fabs(C44)));
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                for (int k = 0; k < 3; ++k)
+                    for (int l = 0; l < 3; ++l) {
+                        double want = 0.0;
+                        if (i == j && k == l) want = (i == k) ? C11 : C12;
+                        else if (i != j && ((i == k && j == l) || (i == l && j == k))) want = C44;
+                        const double got = c[27 * i + 9 * j + 3 * k + l];
+                        if (!(fabs(got - want) <= tol)) isbad = 1;
+                    }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, isbad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(bad, (unsigned long long)__popc(m));
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -1321,15 +1444,13 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
         const int64_t ncc = (plan->nc_active - c0 < plan->chunk_cells) ? plan->nc_active - c0 : plan->chunk_cells;
         const int64_t npc = ncc * 8;
         const int buf = piped ? (int)(ichunk & 1) : 0;
-        const int64_t pitch = scratch_pitch(plan->chunk_cells);
-        double* PJ = plan->scratch[buf];
-        double* TA = plan->scratch[buf] + 9 * pitch;
+        double* scr = plan->scratch[buf];
         if (piped && ichunk >= 2) CU_TRY(cudaStreamWaitEvent(stream, plan->ev_elem[buf], 0));   // buffer free again
         const unsigned grid = (unsigned)((npc + PT_BLOCK - 1) / PT_BLOCK);
 #define CALL(NS, PW, PPV)                                                                                                   \
     CU_TRY(allow_smem(k_point_tangent<NS, PW, PPV>, tangent_smem<NS>()));                                                   \
     k_point_tangent<NS, PW, PPV><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, km, plan->slip, \
-                                                                          dt, np, c0 * 8, npc, pitch, PJ, TA, (long long*)status,  \
+                                                                          dt, np, c0 * 8, npc, scr, (long long*)status,            \
                                                                           zptr, zn)
         // slots [z0, z1): rows first touched by this chunk; the last active chunk takes everything that is left (rows of
         // ghost-only nodes are never touched but must not hold garbage)
@@ -1349,7 +1470,7 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
         const int64_t nquads = (ncc + 3) / 4;
         int64_t egrid = (nquads + ELEM_WARPS - 1) / ELEM_WARPS;
         if (egrid > (int64_t)plan->sm_count * ebps) egrid = (int64_t)plan->sm_count * ebps;
-        k_element_tangent<<<(unsigned)egrid, ELEM_WARPS * 32, esmem, estream>>>(plan->cells, plan->points, c0, ncc, pitch, PJ, TA, plan->indptr,
+        k_element_tangent<<<(unsigned)egrid, ELEM_WARPS * 32, esmem, estream>>>(plan->cells, plan->points, c0, ncc, scr, plan->indptr,
                                                                                 plan->rank, res, csr_data, coo_V);
         CU_TRY(cudaGetLastError());
         if (piped) CU_TRY(cudaEventRecord(plan->ev_elem[buf], estream));
@@ -1387,24 +1508,50 @@ extern "C" int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* ma
     return 0;
 }
 
-extern "C" int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads,
-                                          int64_t np, const cpfem_state* st, double dt, double* P, double* tangent,
-                                          int64_t* status, void* stream_) {
-    int rc = check_common(plan, mat, st, "cpfem_point_stress_tangent");
+static int point_eval_impl(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
+                           const cpfem_state* st, double dt, double* P, double* tangent, const cpfem_state_out* out,
+                           int64_t* status, void* stream_, const char* who) {
+    int rc = check_common(plan, mat, st, who);
     if (rc) return rc;
-    if (!u_grads || !P || np <= 0) return set_err(-1, "cpfem_point_stress_tangent: bad argument");
-    if (st->layout != CPFEM_LAYOUT_AOS) return set_err(-1, "cpfem_point_stress_tangent: AoS state only");
+    if (!u_grads || np <= 0) return set_err(-1, (std::string(who) + ": bad argument").c_str());
+    if (st->layout != CPFEM_LAYOUT_AOS || (out && out->layout != CPFEM_LAYOUT_AOS))
+        return set_err(-1, (std::string(who) + ": AoS state only").c_str());
     cudaStream_t stream = (cudaStream_t)stream_;
     const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
     StateView v = make_view(st);
     CpMaterial m = to_mat(mat);
     const KMat km = make_kmat(m);
+    cpfem_state_out so;
+    so.Fp_inv = nullptr; so.g = nullptr; so.slip = nullptr; so.layout = CPFEM_LAYOUT_AOS;
+    if (out) so = *out;
 #define CALL(NS, PW, PPV)                                                                                                   \
     CU_TRY(allow_smem(k_point_eval<NS, PW, PPV>, tangent_smem<NS>()));                                                      \
     k_point_eval<NS, PW, PPV><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(u_grads, v, km, plan->slip, dt, np, P, tangent,   \
-                                                                       (long long*)status)
+                                                                       so, (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
 #undef CALL
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads,
+                                          int64_t np, const cpfem_state* st, double dt, double* P, double* tangent,
+                                          int64_t* status, void* stream_) {
+    if (!P) return set_err(-1, "cpfem_point_stress_tangent: bad argument");
+    return point_eval_impl(plan, mat, u_grads, np, st, dt, P, tangent, nullptr, status, stream_, "cpfem_point_stress_tangent");
+}
+
+extern "C" int cpfem_point_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads,
+                                        int64_t np, const cpfem_state* st, const cpfem_state_out* out, double dt,
+                                        int64_t* status, void* stream_) {
+    if (!out || !out->Fp_inv || !out->g || !out->slip || !st || !st->slip)
+        return set_err(-1, "cpfem_point_update_state: null argument");
+    return point_eval_impl(plan, mat, u_grads, np, st, dt, nullptr, nullptr, out, status, stream_, "cpfem_point_update_state");
+}
+
+extern "C" int cpfem_check_cubic(const double* C, int64_t np, double rtol, int64_t* bad_count, void* stream_) {
+    if (!C || !bad_count || np <= 0 || !(rtol >= 0.0)) return set_err(-1, "cpfem_check_cubic: bad argument");
+    k_check_cubic<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(C, np, rtol, (unsigned long long*)bad_count);
     CU_TRY(cudaGetLastError());
     return 0;
 }

@@ -7,6 +7,10 @@ build container, where /root/reference exists; the GPU box only sees the committ
                              (consumer: calibration/calibration_case2_singleCrystalTa_GB.py:107-108,146)
   steel304_uq_zz_curve.txt<- calibration/data/csv/calibration_case4/UQ/stress_zz_curve_scenario0.txt
   quat_304.txt            <- polycrystal_304steel/data/csv/polycrystal_304steel/quat.txt
+  mesh2.msh               <- singlecrystal_copper/data/neper/singlecrystal_copper/mesh2.msh        (Neper, 2^3 cells, 1 grain)
+  domain0_mesh5.msh       <- polycrystal_304steel/data/neper/polycrystal_304steel/domain0_mesh5.msh (Neper, 5^3 cells, 8 grains)
+  box.msh                 <- calibration/data/msh/box.msh                                           (Gmsh, 1 hex + lower-dim. elements)
+                             (reader fixtures for cpfem_b200.generate_mesh.read_gmsh22_hex)
 """
 import os
 import shutil
@@ -18,6 +22,9 @@ FILES = {
     'tantalum_ss_curve.txt': 'calibration/data/csv/calibration_case2/ss_curve_e-2.txt',
     'steel304_uq_zz_curve.txt': 'calibration/data/csv/calibration_case4/UQ/stress_zz_curve_scenario0.txt',
     'quat_304.txt': 'polycrystal_304steel/data/csv/polycrystal_304steel/quat.txt',
+    'mesh2.msh': 'singlecrystal_copper/data/neper/singlecrystal_copper/mesh2.msh',
+    'domain0_mesh5.msh': 'polycrystal_304steel/data/neper/polycrystal_304steel/domain0_mesh5.msh',
+    'box.msh': 'calibration/data/msh/box.msh',
 }
 if __name__ == '__main__':
     for dst, src in FILES.items():

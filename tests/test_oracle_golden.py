@@ -38,7 +38,8 @@ def test_golden_curve_tantalum():
     """calibration_case2: BCC Ta, disps = linspace(0,-0.10,41), ts = linspace(0,10,41).  Tolerance 1e-10 relative:
     the reference's own outer Newton stops at rel 1e-8 on the residual, which leaves ~1e-12 on the stress here."""
     gold = np.loadtxt(os.path.join(GOLD, 'tantalum_ss_curve.txt'))
-    n = 8
+    n = len(gold)                      # all 40 committed load steps
+    assert n == 40
     got = _one_element_curve(O.tantalum(), np.linspace(0., -0.10, 41), np.linspace(0., 10., 41), n)
     assert np.abs(got / gold[:n] - 1).max() < 1e-10
 
@@ -47,7 +48,8 @@ def test_golden_curve_copper():
     """calibration_case1: FCC Cu, disps = linspace(0,0.025,21), ts = linspace(0,2.5,21).  The file holds the
     reference's BiCGStab/outer-Newton answer (tol 1e-7), good to ~3e-9 on the first step: tolerance 1e-8."""
     gold = np.loadtxt(os.path.join(GOLD, 'copper_ss_curve.txt'))
-    n = 8
+    n = 20                             # the 20 load steps the reference's driver consumes (stress_curve[:len(ts)-1],
+                                       # calibration_case1_singleCrystalCopper_GB.py:166-167); the file holds 80
     got = _one_element_curve(O.copper(), np.linspace(0., 0.025, 21), np.linspace(0., 2.5, 21), n)
     assert np.abs(got / gold[:n] - 1).max() < 1e-8
 
