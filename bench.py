@@ -29,19 +29,24 @@ import numpy as np
 import torch
 
 # ---- work model (DESIGN.md "Work model") ------------------------------------------------------------------------
-# algorithmic flops per point, SURVEY.md section 8(d) / Appendix G (hand-derived 9x9 formulation, FMA = 2 flops):
+# CONTRACT figure: algorithmic flops per point of SURVEY.md section 8(d) / Appendix G (hand-derived 9x9 formulation,
+# FMA = 2 flops).  Reported under roofline.contract only - the kernels run a leaner algorithm (6x6 symmetric
+# crystal-frame form, active slip set, factored tangent), so this figure over-states the work they do.
 F_UPDATE_FIXED = 1600.0     # set-up: Schmid rotation, B = F A M, hardening
 F_ITER = 5000.0             # one local Newton iteration incl. one line-search residual evaluation
 F_ASSEMBLY_FIXED = 16600.0  # set-up + consistent tangent (10 k) + element K_e share (5 k)
-# executed by this implementation (6x6 symmetric crystal-frame form, active-set slip processing, factored tangent):
-# 2 x FP64 thread instructions per point from ncu (profiles/r1/o_ncu_summary_n64.txt: dfma + dmul + dadd per cycle x cycles)
-X_UPDATE_FIXED = 3000.0     # kinematics, frame change, 1/g, first residual, state update (~1.5 k instructions)
-X_ITER = 1860.0             # per local Newton iteration: ~0.93 k instructions (matrix over the active systems + LU + solve
-                            # + 1.8 residual evaluations), x 2
-X_ASSEMBLY_FIXED = 12800.0  # update fixed part + factored tangent (2.5 k instr) + element K_e (2.4 k instr), x 2
-B_UPDATE = 610.0            # bytes/point: state in 336 + state out 264 + mesh/sol share 10
-B_ASSEMBLY = 2180.0         # bytes/point: state 240 + mesh/sol 10 + CSR memset 244 + CSR RMW 244 + scratch 2 x 720
-TRAFFIC_UPDATE_B_PER_POINT = 592.0   # ncu dram__bytes_read + write per point, k_update_state at 64^3 (profiles/r1/o_ncu_summary_n64.txt)
+# EXECUTED work = what `roofline.achieved` / `roofline.frac` are computed from: FP64 thread instructions per point
+# (DFMA + DMUL + DADD, each occupies one issue slot of the FP64 pipe) and DRAM bytes per point, measured by
+# `ncu --set full` on the timed step at 128^3 (same workload, same local-Newton iteration count) and committed as
+# profiles/fp64_instr.json (made by profiles/fp64_model.py from profiles/r2/*_ncu_summary_n128.txt).
+B_UPDATE = 610.0            # algorithmic bytes/point: state in 336 + state out 264 + mesh/sol share 10
+B_ASSEMBLY = 1940.0         # algorithmic bytes/point: state 240 + mesh/sol 10 + CSR zero-fill 244 + CSR RMW 244 (+244 read) + scratch 2 x 720
+
+
+def _fp64_model():
+    with open(os.path.join(ROOT, 'profiles', 'fp64_instr.json')) as f:
+        return json.load(f)
+
 
 MESH_N = 200
 D_EPS, DT, PRE_STEPS = 2e-4, 2e-3, 10
@@ -160,10 +165,65 @@ def cpu_reference(n_mesh, sample_cells, steps, warmup):
             'ms_per_step': 1e3 * (sum(t_upd) + sum(t_asm)) / len(t_upd), 'cores': torch.get_num_threads()}
 
 
+def _use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU arms run on rank 0 alone and use the box."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def same_algorithm_cpu(state, sol, rm, nthreads, sample_points=1 << 19):
+    """Second, labelled CPU baseline: the algorithm the GPU kernels run (csrc/cp_point.cuh: crystal-frame 6x6 form,
+    active slip set) compiled for the host (tests/hostcheck, g++ -O2 -fopenmp) on all host cores, on the first
+    `sample_points` quadrature points of the benchmark state - so that GPU / CPU compares hardware on the SAME algorithm,
+    while the oracle port above compares with the reference's own (autodiff) algorithm."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import hostcheck_build
+    import cpfem_oracle as O
+    lib = hostcheck_build.load()
+    nthreads = hostcheck_build.set_threads(lib, nthreads)
+    npts = int(min(sample_points, state[0].shape[0] * 8))
+    ncell = npts // 8
+    cells = rm.cells[:ncell]
+    X = rm.points[cells]                                        # (c, 8, 3)
+    g0, g1 = 0.21132486540518713, 0.7886751345948129
+    nodes = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]])
+    dN = np.zeros((8, 8, 3))
+    for q in range(8):
+        b = np.array([(q >> 2) & 1, (q >> 1) & 1, q & 1])
+        f = np.where(nodes == b[None, :], g1, g0)
+        sgn = np.where(nodes == 1, 1.0, -1.0)
+        dN[q, :, 0] = sgn[:, 0] * f[:, 1] * f[:, 2]
+        dN[q, :, 1] = sgn[:, 1] * f[:, 0] * f[:, 2]
+        dN[q, :, 2] = sgn[:, 2] * f[:, 0] * f[:, 1]
+    jac = np.einsum('cai,qaj->cqij', X, dN)
+    grads = np.einsum('qaj,cqji->cqai', dN, np.linalg.inv(jac))
+    u = sol.cpu().numpy()[cells]
+    H = np.einsum('cai,cqaj->cqij', u, grads).reshape(npts, 3, 3)
+    A, g, sl, R = (t[:ncell].reshape(npts, -1).cpu().numpy() for t in state[:4])
+    mat = O.steel304()
+    hostcheck_build.evaluate(lib, mat, DT, H[:4096], A[:4096], g[:4096], sl[:4096], R[:4096], tangent=False, pown=119)     # warm-up
+    t0 = time.perf_counter()
+    out = hostcheck_build.evaluate(lib, mat, DT, H, A, g, sl, R, tangent=False, pown=119)
+    t1 = time.perf_counter()
+    hostcheck_build.evaluate(lib, mat, DT, H, A, g, sl, R, tangent=True, pown=119)
+    t2 = time.perf_counter()
+    return {'value': npts / (t1 - t0), 'unit': 'quad-point updates/s', 'cores': nthreads,
+            'kind': 'port (the GPU path\'s own per-point algorithm, csrc/cp_point.cuh built for the host with g++ -O2 -fopenmp)',
+            'sample': f'first {npts} quadrature points of the benchmark state (stress + state update per point)',
+            'with_tangent_points_per_s': npts / (t2 - t1), 'mean_local_newton_iters': float(out[-1][:, 0].mean())}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    _use_all_host_threads()
     sample_cells = args.cpu_sample_cells
     r = cpu_reference(args.n, sample_cells, args.steps, args.warmup)
     sample = (f'first {sample_cells} cells ({r["sample_points"]} quad points) of the {args.n}^3 polycrystal, 10 load steps '
@@ -306,6 +366,7 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    launches0 = int(cpfem_b200.lib().cpfem_launch_count())         # kernels launched by libcpfem_b200.so so far (this rank)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     for k in range(K):
         ev[k][0].record()
@@ -313,6 +374,7 @@ def main():
         ev[k][1].record()
         do_assembly()
         ev[k][2].record()
+    launches = int(cpfem_b200.lib().cpfem_launch_count()) - launches0
     barrier()
     clocks = sampler.stop()
     t_upd = sum(e[0].elapsed_time(e[1]) for e in ev)
@@ -452,9 +514,10 @@ def main():
         return
 
     # ---- roofline (update kernel = the metric's kernel; assembly reported beside it) --------------------------------
-    # achieved = ALGORITHMIC flops of SURVEY 8(d) (hand-derived 9x9 form: 1.6 k + k 5.0 k per point, +15 k for the assembly)
-    # x points / CUDA-event duration; `executed` = the leaner 6x6 crystal-frame form this kernel actually runs
-    # (FP64 instructions counted on the ncu source page, profiles/r1) - DESIGN.md "Work model".
+    # `achieved` / `frac` = EXECUTED FP64 work: FP64 thread instructions per point (ncu at the bench state, 128^3,
+    # profiles/fp64_instr.json) x points of this rank / CUDA-event duration, as a share of the FP64 pipe's issue slots
+    # (SMs x 64 lanes x clock; written as TFLOP/s with 2 flops per slot so that it compares with the DFMA peak).  `true_flops`
+    # counts DFMA = 2, DMUL = DADD = 1.  `contract` is SURVEY 8(d)'s hand-derived 9x9 figure, which this algorithm undercuts.
     peaks = _peaks()
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     hbm_src = 'measured (MEASURED_PEAKS.json, burst copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
@@ -467,54 +530,70 @@ def main():
     upd_s = t_upd * 1e-3 / K
     asm_s = t_asm * 1e-3 / K
     pts_rank = npts_global / world
+    model = _fp64_model()
+    mk = model['kernels']
+    ku, kp, ke = mk['k_update_state'], mk['k_point_tangent'], mk['k_element_tangent']
+    tf = lambda f, t: pts_rank * f / t / 1e12
+    peak_src = ('max(DFMA microbenchmark of this run (cpfem_dfma_peak_kernel): %.2f TFLOP/s, nominal SMs x 64 DFMA/clk x '
+                'max SM clock: %.2f TFLOP/s); MEASURED_PEAKS.json has no FP64 entry' % (fp64_meas, fp64_nominal))
+    model_src = ('%s: %s' % (model['source'], model['what']))
     f_upd = F_UPDATE_FIXED + F_ITER * k_mean_u
     f_asm = F_ASSEMBLY_FIXED + F_ITER * k_mean_a
-    x_upd = X_UPDATE_FIXED + X_ITER * k_mean_u
-    x_asm = X_ASSEMBLY_FIXED + X_ITER * k_mean_a
-    tf = lambda f, t: pts_rank * f / t / 1e12
-    roof = {'bound': 'fp64', 'kernel': 'k_update_state<12,119>', 'achieved': tf(f_upd, upd_s), 'peak': fp64_peak,
-            'unit': 'TFLOP/s', 'frac': tf(f_upd, upd_s) / fp64_peak,
-            'traffic': TRAFFIC_UPDATE_B_PER_POINT * pts_rank,
-            'traffic_source': 'ncu --set full at 64^3 (profiles/r1/o_ncu_summary_n64.txt): dram read+write = 592 B/point, scaled to this launch; '
-                              'algorithmic bytes 610 B/point',
-            'peak_source': 'max(DFMA microbenchmark of this run (cpfem_dfma_peak_kernel): %.2f TFLOP/s, nominal SMs x 64 DFMA/clk x '
-                           'max SM clock: %.2f TFLOP/s); MEASURED_PEAKS.json has no FP64 entry' % (fp64_meas, fp64_nominal),
-            'flops_per_point': f_upd, 'flops_model': 'SURVEY 8(d): 1.6 k + k x 5.0 k, k = mean local Newton iterations (measured)',
-            'mean_local_newton_iters': k_mean_u,
-            'executed': {'flops_per_point': x_upd, 'achieved': tf(x_upd, upd_s), 'frac': tf(x_upd, upd_s) / fp64_peak,
-                         'model': '2 x FP64 instructions/point of the 6x6 crystal-frame form with active-set slip processing: '
-                                  '3.0 k + k x 1.86 k (ncu, profiles/r1/k_*); ncu sm__pipe_fp64_cycles_active = 60 % at 64^3'},
+    x_upd = 2.0 * ku['fp64_instr_per_point']
+    roof = {'bound': 'fp64', 'kernel': 'k_update_state<12,119>', 'achieved': tf(x_upd, upd_s), 'peak': fp64_peak,
+            'unit': 'TFLOP/s', 'frac': tf(x_upd, upd_s) / fp64_peak,
+            'what': 'executed FP64 issue slots: (DFMA + DMUL + DADD thread instructions per point, ncu) x 2 x points / '
+                    'CUDA-event duration of the kernel, against the DFMA peak = the share of the FP64 pipe the kernel keeps busy',
+            'fp64_instr_per_point': ku['fp64_instr_per_point'], 'model_source': model_src,
+            'ncu_pipe_fp64_cycles_active_pct_at_capture': ku['pipe_fp64_cycles_active_pct'],
+            'true_flops': {'flops_per_point': ku['flops_per_point'], 'achieved': tf(ku['flops_per_point'], upd_s),
+                           'frac': tf(ku['flops_per_point'], upd_s) / fp64_peak, 'what': 'DFMA = 2 flops, DMUL = DADD = 1'},
+            'contract': {'flops_per_point': f_upd, 'achieved': tf(f_upd, upd_s), 'frac_of_peak': tf(f_upd, upd_s) / fp64_peak,
+                         'model': 'SURVEY 8(d): 1.6 k + k x 5.0 k flops per point (hand-derived 9x9 form), k = mean local Newton '
+                                  'iterations measured live; the kernel runs a leaner algorithm (6x6 symmetric crystal-frame '
+                                  'form, active slip set), so this is NOT the work it does - a value above the peak only says so'},
+            'traffic': ku['dram_bytes_per_point'] * pts_rank,
+            'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum of the same capture = %.0f B/point, scaled to '
+                              'this launch; algorithmic bytes %.0f B/point' % (ku['dram_bytes_per_point'], B_UPDATE),
+            'peak_source': peak_src, 'mean_local_newton_iters': k_mean_u,
             'hbm': {'achieved': pts_rank * B_UPDATE / upd_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': pts_rank * B_UPDATE / upd_s / 1e9 / hbm_peak, 'bytes_per_point': B_UPDATE, 'peak_source': hbm_src},
             'note': 'arithmetic intensity ~%.0f flop/B >> B200 balance (~5.5): the FP64 pipe is the bound, not HBM or tensor '
-                    'cores (3x3 / 6x6 / 12-wide algebra per point).  `achieved` / `frac` use the contract figure of SURVEY 8(d) '
-                    '(hand-derived 9x9 form); the kernel runs a cheaper algorithm (6x6 symmetric crystal-frame form, active '
-                    'slip set), so that fraction exceeds 1 - `executed.frac` is the share of the FP64 pipe actually used '
-                    '(matches ncu sm__pipe_fp64_cycles_active)' % (f_upd / B_UPDATE)}
-    roof_asm = {'bound': 'fp64', 'kernel': 'k_point_tangent<12,119> + k_element_tangent', 'achieved': tf(f_asm, asm_s),
-                'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': tf(f_asm, asm_s) / fp64_peak, 'traffic': None,
-                'flops_per_point': f_asm, 'mean_local_newton_iters': k_mean_a,
-                'executed': {'flops_per_point': x_asm, 'achieved': tf(x_asm, asm_s), 'frac': tf(x_asm, asm_s) / fp64_peak},
+                    'cores (3x3 / 6x6 / 12-wide algebra per point)' % (ku['flops_per_point'] / B_UPDATE)}
+    x_asm = 2.0 * (kp['fp64_instr_per_point'] + ke['fp64_instr_per_point'])
+    fl_asm = kp['flops_per_point'] + ke['flops_per_point']
+    share = lambda k: k['ms'] / (kp['ms'] + ke['ms'])
+    roof_asm = {'bound': 'fp64', 'kernel': 'k_point_tangent<12,119> + k_element_tangent', 'achieved': tf(x_asm, asm_s),
+                'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': tf(x_asm, asm_s) / fp64_peak,
+                'what': 'executed FP64 issue slots of both kernels x 2 x points / duration of the whole assembly',
+                'fp64_instr_per_point': {'k_point_tangent': kp['fp64_instr_per_point'], 'k_element_tangent': ke['fp64_instr_per_point']},
+                'kernel_time_share_at_capture': {'k_point_tangent': share(kp), 'k_element_tangent': share(ke)},
+                'true_flops': {'flops_per_point': fl_asm, 'achieved': tf(fl_asm, asm_s), 'frac': tf(fl_asm, asm_s) / fp64_peak},
+                'contract': {'flops_per_point': f_asm, 'achieved': tf(f_asm, asm_s), 'frac_of_peak': tf(f_asm, asm_s) / fp64_peak},
+                'traffic': (kp['dram_bytes_per_point'] + ke['dram_bytes_per_point']) * pts_rank,
+                'mean_local_newton_iters': k_mean_a,
                 'hbm': {'achieved': pts_rank * B_ASSEMBLY / asm_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                         'frac': pts_rank * B_ASSEMBLY / asm_s / 1e9 / hbm_peak, 'bytes_per_point': B_ASSEMBLY},
-                'note': 'duration includes the CSR memset, both kernels and (multi-GPU) the interface exchange'}
+                'note': 'duration includes both kernels of every chunk, the residual memset and (multi-GPU) the interface exchange'}
 
     if solver_info is not None and 'spmv_gbs' in solver_info:
         solver_info['spmv_roofline'] = {'bound': 'hbm', 'achieved': solver_info['spmv_gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
                                         'frac': solver_info['spmv_gbs'] / hbm_peak, 'peak_source': hbm_src}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        nthreads = _use_all_host_threads()
         r = cpu_reference(N, args.cpu_sample_cells, 2, 1)
         cpu = {'value': r['updates_per_s'], 'unit': 'quad-point updates/s', 'cores': r['cores'], 'kind': 'port',
                'sample': f'first {args.cpu_sample_cells} cells ({r["sample_points"]} points) of the same {N}^3 workload, oracle port '
-                         f'(torch fp64 + torch.func.jacfwd, restatement - JAX is not installable here)',
+                         f'(torch fp64 + torch.func.jacfwd, restatement of the reference\'s algorithm - JAX is not installable here)',
                'assembly_us_per_cell': r['assembly_us_per_cell'],
                'coo_to_csr_us_per_cell': r['coo_to_csr_us_per_cell'],
                'extrapolated_to_workload': {'update_s': npts_global / r['updates_per_s'],
                                             'assembly_s': r['assembly_us_per_cell'] * 1e-6 * (npts_global // 8),
                                             'note': 'per-point / per-cell sample rates x the full mesh (the reference cannot hold '
                                                     'it: ~110 GB of COO triplets at 200^3); assembly includes the scipy '
-                                                    'COO->CSR step of solver.py:281 (coo_to_csr_us_per_cell, one core)'}}
+                                                    'COO->CSR step of solver.py:281 (coo_to_csr_us_per_cell, one core)'},
+               'same_algorithm': same_algorithm_cpu(state, sol, rm, nthreads)}
 
     line = {
         'metric': 'cp_quad_point_updates_per_s', 'value': npts_global * K / (t_upd * 1e-3), 'unit': 'quad-point updates/s',
@@ -522,7 +601,10 @@ def main():
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(N),
                    'partition': f'{world} slab(s)' + (', interface exchange overlapped with the assembly (starts after the first chunk)' if (world > 1 and args.overlap_exchange) else ''), 'state_layout': args.layout,
-                   'l2': 'inputs (>= 2 GB of state per pass) are larger than the 126 MB L2; no flush needed'},
+                   'l2': 'inputs (>= 2 GB of state per pass) are larger than the 126 MB L2; no flush needed',
+                   'layout_ab': 'SoA (component-major) state measured slower than the reference AoS layout on B200 (update 66.8 vs '
+                                '61.1 ms at 200^3, profiles/r2/a_layout_ab.txt): 42 component streams 0.5 GB apart per warp '
+                                'against one contiguous 2.3 kB record block; --layout soa reproduces it'},
         'update_ms': t_upd / K, 'assembly_ms': t_asm / K, 'assembly_metric': 'ms per Newton-iteration assembly '
         '(stress+tangent, hex8 integration, residual scatter, CSR fill, interface exchange, norm allreduce)',
         'update_avg_stress_fused_ms': t_fused, 'avg_stress_ms': t_avg, 'solver': solver_info,
@@ -532,7 +614,10 @@ def main():
         'mean_local_newton_iters': k_mean_u, 'points_at_iter_cap': int(st_u[0]) + int(st_a[0]),
         'nonfinite_points': int(st_u[1]) + int(st_a[1]), 'residual_norm': res_norm,
         'roofline': roof, 'roofline_assembly': roof_asm, 'cpu_baseline': cpu, 'e2e': e2e,
-        'gpu_launches': K * (1 + 2 * (-(-nc // plan.chunk_cells)) + (1 if world == 1 else 2 + 2 * len(rm.recv_nodes))), 'clocks': clocks,
+        'gpu_launches': launches,
+        'gpu_launches_what': 'kernels launched by libcpfem_b200.so inside the timed region on rank 0 (cpfem_launch_count(): '
+                             'update 1 + assembly 2 per chunk + norm / exchange helpers per step; memsets and NCCL kernels not counted)',
+        'clocks': clocks,
     }
     print(json.dumps(line))
     if world > 1:

@@ -197,6 +197,10 @@ int cpfem_soa_to_aos(const double* soa, int64_t np, int32_t comps, double* aos, 
  * DFMA rounds on every SM and returns the flop count in *flops (time it with CUDA events). */
 int cpfem_dfma_peak_kernel(int64_t iters, double* sink, double* flops, void* stream);
 
+/* Number of kernels this library has launched since it was loaded (hot-path entry points; memsets / copies excluded):
+ * bench.py reads it around its timed region for the `gpu_launches` figure. */
+int64_t cpfem_launch_count(void);
+
 const char* cpfem_last_error(void);
 int cpfem_version(void);
 

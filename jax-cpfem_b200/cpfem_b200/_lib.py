@@ -73,6 +73,7 @@ SIGNATURES = {
     'cpfem_aos_to_soa': (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'cpfem_soa_to_aos': (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'cpfem_dfma_peak_kernel': (ctypes.c_int, [c_i64, c_vp, ctypes.POINTER(c_dbl), c_vp]),
+    'cpfem_launch_count': (c_i64, []),
     'cpfem_last_error': (ctypes.c_char_p, []),
     'cpfem_version': (ctypes.c_int, []),
 }

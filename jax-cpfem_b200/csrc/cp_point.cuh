@@ -373,7 +373,7 @@ CP_HD double cp_residual(const CpSlipRef& sl, const CpPointParams& pm, double cd
         mact = m;
         // pad the set to a multiple of U (CP_TAIL2: of 2) with inactive systems (they are evaluated honestly: tiny values)
         {
-            constexpr int PADTO = CP_TAIL2 ? 2 : U;
+            constexpr int PADTO = (CP_TAIL2 == 2) ? 1 : (CP_TAIL2 ? 2 : U);
             const int k = (PADTO - (cp_popc(m) & (PADTO - 1))) & (PADTO - 1);
             for (int i = 0; i < k; ++i) {
                 const unsigned z = ~m & ((NS == 32) ? 0xffffffffu : ((1u << NS) - 1u));
@@ -383,8 +383,12 @@ CP_HD double cp_residual(const CpSlipRef& sl, const CpPointParams& pm, double cd
         mask = m;
         while (m) {
 #if CP_TAIL2
-            if (cp_popc(m) == 2) {
-                cp_slip_group<POWN, 2>(sl, pm, cdt, cn, n1, ginv, w, m, Lp);
+            const int left = cp_popc(m);
+            if (left < 4) {
+                if (left >= 2) cp_slip_group<POWN, 2>(sl, pm, cdt, cn, n1, ginv, w, m, Lp);
+#if CP_TAIL2 == 2
+                if (left & 1) cp_slip_group<POWN, 1>(sl, pm, cdt, cn, n1, ginv, w, m, Lp);
+#endif
                 break;
             }
 #endif

@@ -12,6 +12,7 @@
 // error plumbing
 // -----------------------------------------------------------------------------------------------
 int cpfem_set_err(int code, const char* what, cudaError_t e = cudaSuccess);
+void cpfem_count_launches(int n);     // feeds cpfem_launch_count()
 static inline int set_err(int code, const char* what, cudaError_t e = cudaSuccess) { return cpfem_set_err(code, what, e); }
 #define CU_TRY(x)                                                  \
     do {                                                           \

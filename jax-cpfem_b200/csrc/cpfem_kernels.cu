@@ -22,6 +22,7 @@
 #include <string.h>
 #include <string>
 #include <new>
+#include <atomic>
 
 #include "cpfem_internal.h"
 
@@ -41,6 +42,11 @@ int cpfem_set_err(int code, const char* what, cudaError_t e) {
 }
 
 extern "C" const char* cpfem_last_error(void) { return g_last_error.c_str(); }
+// kernels launched by the entry points of this library since it was loaded (all threads; memsets and copies not counted)
+static std::atomic<long long> g_launches{0};
+void cpfem_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t cpfem_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+#define LAUNCHED(n) cpfem_count_launches(n)
 extern "C" int cpfem_version(void) { return 200; }
 
 #define MAX_VALENCE 16
@@ -815,6 +821,12 @@ k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ po
 #ifndef CPFEM_MERGE_ATOMICS
 #define CPFEM_MERGE_ATOMICS 0
 #endif
+#ifndef CPFEM_SCATTER_DIRECT
+#define CPFEM_SCATTER_DIRECT 0           // experiment: scatter from registers, no shared K_e tile
+#endif
+#if CPFEM_SCATTER_DIRECT && CPFEM_MERGE_ATOMICS
+#error "CPFEM_MERGE_ATOMICS needs the shared K_e tile"
+#endif
 #ifndef ELEM_WARPS
 #define ELEM_WARPS 8                     // 222 kB and 256 x 255 registers per block: one block fills an SM (measured on B200 at
                                          // 64^3: 6 / 7 / 8 warps -> 1.46 / 1.27 / 1.14 ms; the previous LDG+STS-staged kernel: 1.19 ms)
@@ -918,12 +930,21 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
         // CSR row starts of this lane's three rows: requested here, a whole slice of arithmetic before the scatter needs them
         long long rp0 = -1, rp1 = -1, rp2 = -1;
         if (csr_data && valid) { rp0 = indptr[na * 3]; rp1 = indptr[na * 3 + 1]; rp2 = indptr[na * 3 + 2]; }
+        const bool quad_all_valid = __all_sync(0xffffffffu, valid);
+#if CPFEM_SCATTER_DIRECT
+        int rbr[8];
+#endif
         if (csr_data) {
             const uint2 rk = *reinterpret_cast<const uint2*>(rank + (c * 8 + a) * 8);
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
+#if CPFEM_SCATTER_DIRECT
+                rbr[b] = 3 * (int)((rk.x >> (8 * b)) & 0xffu);
+                rbr[4 + b] = 3 * (int)((rk.y >> (8 * b)) & 0xffu);
+#else
                 RB[lane * 8 + b] = 3 * (int)((rk.x >> (8 * b)) & 0xffu);
                 RB[lane * 8 + 4 + b] = 3 * (int)((rk.y >> (8 * b)) & 0xffu);
+#endif
             }
         }
 #if CPFEM_MERGE_ATOMICS
@@ -1035,6 +1056,21 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
 #pragma unroll
                 for (int j = 0; j < 24; ++j) v[j] = acc[j];
             }
+#if CPFEM_SCATTER_DIRECT
+            // direct scatter: every lane adds the 24 entries of its row straight from its accumulators - no tile, no
+            // index arithmetic beyond one 64-bit address per (row, neighbour) block; a warp instruction touches 32
+            // different CSR rows (the three k of a block go out as three instructions)
+            if (csr_data && valid) {
+                double* row = csr_data + ((i == 0) ? rp0 : (i == 1) ? rp1 : rp2);
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    double* dst = row + rbr[b];
+                    atomicAdd(dst, acc[3 * b]);
+                    atomicAdd(dst + 1, acc[3 * b + 1]);
+                    atomicAdd(dst + 2, acc[3 * b + 2]);
+                }
+            }
+#else
             if (csr_data) {
                 double* ke = KE + lane * KE_ROW;
 #pragma unroll
@@ -1071,17 +1107,26 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
                 // lanes cover the 24 contiguous bytes of a block (x-neighbour blocks are contiguous too) and the row / block
                 // indices are shifts (the former 32-entries-per-instruction walk spent 21 instructions per atomic on index
                 // arithmetic: 21 % of the kernel's instructions, profiles/r2/a_element_source_lines.txt)
+                // (KE index: 25 t + 3 b + k = 3 pb + k + (pb >> 3) for pb = 8 t + b)
                 if (lane < 30) {
+                    if (quad_all_valid) {
 #pragma unroll 2
-                    for (int pb = sc_m; pb < 256; pb += 10) {
-                        const int t = pb >> 3;
-                        const long long base = ROWP[t];
-                        if (base >= 0) atomicAdd(csr_data + base + RB[pb] + sc_k, KE[t * KE_ROW + 3 * (pb & 7) + sc_k]);
+                        for (int pb = sc_m; pb < 256; pb += 10) {
+                            const int t = pb >> 3;
+                            atomicAdd(csr_data + ROWP[t] + (RB[pb] + sc_k), KE[3 * pb + sc_k + t]);
+                        }
+                    } else {
+                        for (int pb = sc_m; pb < 256; pb += 10) {
+                            const int t = pb >> 3;
+                            const long long base = ROWP[t];
+                            if (base >= 0) atomicAdd(csr_data + base + (RB[pb] + sc_k), KE[3 * pb + sc_k + t]);
+                        }
                     }
                 }
 #endif
                 __syncwarp();                       // KE / ROWP free again
             }
+#endif
         }
     }
 }
@@ -1355,6 +1400,7 @@ static int update_state_impl(const cpfem_plan* plan, const cpfem_material* mat, 
                                                                           plan->slip, dt, np, cell0, sigma_cell,       \
                                                                           (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
+    LAUNCHED(1);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
@@ -1401,6 +1447,7 @@ extern "C" int cpfem_residual(const cpfem_plan* plan, const cpfem_material* mat,
     k_residual<NS, PW, PPV><<<grid, PT_BLOCK, residual_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, km, plan->slip, \
                                                                         dt, plan->nc_active, res, (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
+    LAUNCHED(1);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
@@ -1461,6 +1508,7 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
         double* zptr = (fuse_zero && z1 > z0) ? csr_data + z0 : nullptr;
         const int64_t zn = (fuse_zero && z1 > z0) ? z1 - z0 : 0;
         CP_DISPATCH(plan->ns, pown, per_point(v), CALL);
+    LAUNCHED(1);
 #undef CALL
         CU_TRY(cudaGetLastError());
         if (piped) {
@@ -1472,6 +1520,7 @@ extern "C" int cpfem_newton_update(const cpfem_plan* plan, const cpfem_material*
         if (egrid > (int64_t)plan->sm_count * ebps) egrid = (int64_t)plan->sm_count * ebps;
         k_element_tangent<<<(unsigned)egrid, ELEM_WARPS * 32, esmem, estream>>>(plan->cells, plan->points, c0, ncc, scr, plan->indptr,
                                                                                 plan->rank, res, csr_data, coo_V);
+    LAUNCHED(1);
         CU_TRY(cudaGetLastError());
         if (piped) CU_TRY(cudaEventRecord(plan->ev_elem[buf], estream));
         if (progress_due && (c0 + ncc >= plan->progress_cells || c0 + ncc >= plan->nc_active)) {
@@ -1503,6 +1552,7 @@ extern "C" int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* ma
     k_avg_stress<NS, PW, PPV><<<grid, PT_BLOCK, point_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, km, plan->slip, dt, \
                                                                        np, sigma_cell, (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
+    LAUNCHED(1);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
@@ -1529,6 +1579,7 @@ static int point_eval_impl(const cpfem_plan* plan, const cpfem_material* mat, co
     k_point_eval<NS, PW, PPV><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(u_grads, v, km, plan->slip, dt, np, P, tangent,   \
                                                                        so, (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
+    LAUNCHED(1);
 #undef CALL
     CU_TRY(cudaGetLastError());
     return 0;
@@ -1552,6 +1603,7 @@ extern "C" int cpfem_point_update_state(const cpfem_plan* plan, const cpfem_mate
 extern "C" int cpfem_check_cubic(const double* C, int64_t np, double rtol, int64_t* bad_count, void* stream_) {
     if (!C || !bad_count || np <= 0 || !(rtol >= 0.0)) return set_err(-1, "cpfem_check_cubic: bad argument");
     k_check_cubic<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(C, np, rtol, (unsigned long long*)bad_count);
+    LAUNCHED(1);
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -1562,6 +1614,7 @@ extern "C" int cpfem_apply_dirichlet(const cpfem_plan* plan, const int64_t* rows
     if (nbc <= 0) return 0;
     k_dirichlet<<<(unsigned)((nbc + 127) / 128), 128, 0, (cudaStream_t)stream_>>>(rows, vals, nbc, sol, res, csr_data,
                                                                                  plan->indptr, plan->indices);
+    LAUNCHED(1);
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -1570,6 +1623,7 @@ extern "C" int cpfem_scatter_add(const double* src, const int64_t* map, int64_t 
     if (n <= 0) return 0;
     if (!src || !map || !dst) return set_err(-1, "cpfem_scatter_add: null argument");
     k_scatter_add<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, map, n, dst);
+    LAUNCHED(1);
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -1577,6 +1631,7 @@ extern "C" int cpfem_gather(const double* src, const int64_t* map, int64_t n, do
     if (n <= 0) return 0;
     if (!src || !map || !dst) return set_err(-1, "cpfem_gather: null argument");
     k_gather<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, map, n, dst);
+    LAUNCHED(1);
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -1586,6 +1641,7 @@ extern "C" int cpfem_sumsq(const double* x, int64_t n, double* out, void* stream
     int64_t blocks = (n + 1023) / 1024;
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_sumsq<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, n, out);
+    LAUNCHED(1);
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -1593,6 +1649,7 @@ extern "C" int cpfem_aos_to_soa(const double* aos, int64_t np, int32_t comps, do
     if (!aos || !soa || np <= 0 || comps <= 0) return set_err(-1, "cpfem_aos_to_soa: bad argument");
     dim3 grid((unsigned)((np + 31) / 32), (unsigned)((comps + 31) / 32));
     k_transpose<<<grid, dim3(32, 8), 0, (cudaStream_t)stream_>>>(aos, np, comps, soa, 1);
+    LAUNCHED(1);
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -1600,6 +1657,7 @@ extern "C" int cpfem_soa_to_aos(const double* soa, int64_t np, int32_t comps, do
     if (!aos || !soa || np <= 0 || comps <= 0) return set_err(-1, "cpfem_soa_to_aos: bad argument");
     dim3 grid((unsigned)((np + 31) / 32), (unsigned)((comps + 31) / 32));
     k_transpose<<<grid, dim3(32, 8), 0, (cudaStream_t)stream_>>>(soa, comps, np, aos, 0);
+    LAUNCHED(1);
     CU_TRY(cudaGetLastError());
     return 0;
 }
@@ -1611,6 +1669,7 @@ extern "C" int cpfem_dfma_peak_kernel(int64_t iters, double* sink, double* flops
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int blocks = sms * 8, threads = 256;
     k_dfma_peak<<<blocks, threads, 0, (cudaStream_t)stream_>>>(iters, sink);
+    LAUNCHED(1);
     CU_TRY(cudaGetLastError());
     *flops = (double)blocks * threads * 8.0 * 2.0 * (double)iters;
     return 0;

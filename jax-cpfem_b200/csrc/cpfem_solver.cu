@@ -385,6 +385,7 @@ static unsigned vec_grid(const cpfem_plan* p, int64_t n) {
 
 extern "C" int cpfem_spmv(const cpfem_plan* plan, const double* csr_data, const double* x, double* y, void* stream_) {
     if (!plan || !csr_data || !x || !y) return set_err(-1, "cpfem_spmv: null argument");
+    cpfem_count_launches(1);
     k_bicg_spmv<3><<<spmv_grid(plan), RED_BLOCK, 0, (cudaStream_t)stream_>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, nullptr,
                                                                            nullptr, nullptr, x, y, 0.0, 0.0, 0);
     CU_TRY(cudaGetLastError());
@@ -394,6 +395,7 @@ extern "C" int cpfem_spmv(const cpfem_plan* plan, const double* csr_data, const 
 extern "C" int cpfem_csr_diagonal(const cpfem_plan* plan, const double* csr_data, double* diag, int32_t invert, void* stream_) {
     if (!plan || !csr_data || !diag) return set_err(-1, "cpfem_csr_diagonal: null argument");
     const int64_t n = 3 * plan->nn;
+    cpfem_count_launches(1);
     k_csr_diag<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, diag, invert);
     CU_TRY(cudaGetLastError());
     return 0;
@@ -401,6 +403,7 @@ extern "C" int cpfem_csr_diagonal(const cpfem_plan* plan, const double* csr_data
 
 // one BiCGStab iteration = five kernels (body_fun of _bicgstab_solve)
 static void launch_iteration(const cpfem_plan* plan, cpfem_solver_ws* w, unsigned gs, unsigned gv, cudaStream_t stream) {
+    cpfem_count_launches(5);
     k_bicg_vec<0><<<gv, RED_BLOCK, 0, stream>>>(w->n, w->sc, w->partials, w->dV);
     k_bicg_spmv<1><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, nullptr, plan->nn, w->sc, w->partials, w->dV, nullptr, nullptr,
                                                 0.0, 0.0, 0);
@@ -452,8 +455,10 @@ extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const do
     CU_TRY(cudaMemcpyAsync(w->dV, w->hV, sizeof(BicgVecs), cudaMemcpyHostToDevice, stream));
     const unsigned gs = spmv_grid(plan), gv = vec_grid(plan, n);
     if (precond) {
+        cpfem_count_launches(1);
         k_csr_diag<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, minv, 1);
     }
+    cpfem_count_launches(1);
     k_bicg_spmv<0><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, nullptr, plan->nn, w->sc, w->partials, w->dV, nullptr, nullptr,
                                                 tol, atol, (long long)maxiter);
     CU_TRY(cudaGetLastError());
@@ -468,6 +473,7 @@ extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const do
         for (int bi = 0; bi < batches; ++bi, launched += BICG_GRAPH_ITERS) {
             if (graph) {
                 CU_TRY(cudaGraphLaunch(graph, stream));
+                cpfem_count_launches(5 * BICG_GRAPH_ITERS);
             } else {
                 for (int it = 0; it < BICG_GRAPH_ITERS; ++it) launch_iteration(plan, w, gs, gv, stream);
             }
@@ -485,6 +491,7 @@ extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const do
     }
     if (resid) {
         // ||A x - b|| as jax_solve checks it (solver.py:43-45): one more SpMV into the t vector
+        cpfem_count_launches(2);
         k_bicg_spmv<3><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, nullptr, nullptr, nullptr, x, V.t, 0.0, 0.0, 0);
         k_norm2_diff<<<gv, RED_BLOCK, 0, stream>>>(V.t, b, n, w->sc, w->partials);
         CU_TRY(cudaMemcpyAsync(w->host_sc, w->sc, sizeof(BicgScal), cudaMemcpyDeviceToHost, stream));

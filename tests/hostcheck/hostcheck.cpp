@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY: compiles the product's per-point header (jax-cpfem_b200/csrc/cp_point.cuh) for the
 // host so that the hand-derived algebra can be compared with the autodiff oracle on a machine without a GPU.
-// Nothing in the product path loads this library.
+// Nothing in the product path loads this library.  bench.py's `cpu_baseline.same_algorithm` leg times it (built with
+// -fopenmp) as "the GPU path's own algorithm on the host cores", next to the oracle port of the reference's algorithm.
 #include <stdint.h>
 #include <string.h>
 #include "../../jax-cpfem_b200/csrc/cp_point.cuh"
@@ -16,6 +17,8 @@ static void run(const double* slip6, const CpMaterial* mat, double dt, int64_t n
     CpSlip table;
     cp_slip_init(&table, slip6, NS);
     const CpSlipRef sl = {&table, &table};
+    // points are independent: the OpenMP build (bench.py's same-algorithm CPU baseline) spreads them over the host cores
+#pragma omp parallel for schedule(dynamic, 256)
     for (int64_t p = 0; p < np; ++p) {
         CpPointParams pm;
         if (pp) {
@@ -45,6 +48,13 @@ static void run(const double* slip6, const CpMaterial* mat, double dt, int64_t n
         if (A_new) cp_point_state_update<NS>(sl, pm, ps, g + NS * p, slip_old + NS * p, R + 9 * p, A_new + 9 * p, g_new + NS * p, slip_new + NS * p);
     }
 }
+
+#ifdef _OPENMP
+#include <omp.h>
+extern "C" int hostcheck_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+extern "C" int hostcheck_threads(int) { return 1; }
+#endif
 
 extern "C" int hostcheck_points(int ns, int pown, const double* slip6, const CpMaterial* mat, double dt, int64_t np, const double* H,
                                 const double* A, const double* g, const double* slip_old, const double* R, const double* pp,

@@ -19,8 +19,14 @@ class CMat(ctypes.Structure):
 
 def load():
     if (not os.path.exists(SO)) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
-        subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-x', 'c++', SRC, '-o', SO])
+        subprocess.check_call(['g++', '-O2', '-fopenmp', '-std=c++17', '-shared', '-fPIC', '-x', 'c++', SRC, '-o', SO])
     return ctypes.CDLL(SO)
+
+
+def set_threads(lib, n):
+    """OpenMP threads of the host build (0 = leave as is); returns the number in use."""
+    lib.hostcheck_threads.restype = ctypes.c_int
+    return int(lib.hostcheck_threads(ctypes.c_int(int(n))))
 
 
 def evaluate(lib, mat, dt, H, A, g, sl, R, pp=None, tangent=True, pown=0):
