@@ -155,6 +155,14 @@ int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_material* mat
 int cpfem_point_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
                              const cpfem_state* st, const cpfem_state_out* out, double dt, int64_t* status, void* stream);
 
+/* Everything the two calls above produce, from ONE local solve per point, plus the per-point account of that solve:
+ * any of P (np, 9), tangent (np, 81), out (new state) may be NULL; point_info, if not NULL, is a device int32 (np, 3)
+ * array receiving [local Newton iterations, residual evaluations, status bits (1: hit max_iter, 2: non-finite)] of every
+ * point - what the parity tests compare with the reference's control flow (models_copper.py:204-249), point by point. */
+int cpfem_point_eval(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
+                     const cpfem_state* st, double dt, double* P, double* tangent, const cpfem_state_out* out,
+                     int32_t* point_info, int64_t* status, void* stream);
+
 /* Input validation for the DP-steel form of the state (models_DPsteel_inhomo.py:121-147,185-186): counts the points of a
  * (np, 81) elastic-tensor array that are NOT of the cubic pattern in the crystal frame (C11 on iiii, C12 on iijj, C44 on
  * ijij / ijji, zero elsewhere; tolerance rtol x the largest constant).  *bad_count is a device int64 that is accumulated
@@ -181,6 +189,17 @@ int cpfem_csr_diagonal(const cpfem_plan* plan, const double* csr_data, double* d
  * synchronises the stream (it polls the device-side convergence flag) and owns a workspace inside the plan. */
 int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const double* b, double* x, int32_t precond, double tol,
                    double atol, int64_t maxiter, int64_t* info, double* resid, void* stream);
+
+/* The same solve, enqueue-only (what an XLA-FFI handler may call: no stream synchronisation, no host read-back):
+ * `iters_to_enqueue` iterations (rounded up to the plan's CUDA-graph batch of 8, capped by maxiter) are enqueued on the
+ * stream - iterations after convergence / breakdown are no-ops on the device - and the outcome is written to DEVICE
+ * memory: info_dev[0] = iterations taken (negative: JAX breakdown code), info_dev[1] = 1 if the tolerance was not reached
+ * within the enqueued iterations (the caller may call again with x as the start vector), *resid_dev = ||A x - b||_2 (may
+ * be NULL).  The first call on a plan allocates the plan's solver workspace and instantiates its CUDA graph: warm it up
+ * once outside any stream capture. */
+int cpfem_bicgstab_enqueue(cpfem_plan* plan, const double* csr_data, const double* b, double* x, int32_t precond, double tol,
+                           double atol, int64_t maxiter, int64_t iters_to_enqueue, int64_t* info_dev, double* resid_dev,
+                           void* stream);
 
 /* Interface exchange helper for element-partitioned runs: dst[map[i]] += src[i]. */
 int cpfem_scatter_add(const double* src, const int64_t* map, int64_t n, double* dst, void* stream);

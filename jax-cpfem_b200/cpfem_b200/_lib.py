@@ -61,12 +61,15 @@ SIGNATURES = {
                                                   c_dbl, c_vp, c_vp, c_vp, c_vp]),
     'cpfem_point_update_state': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, c_i64, ctypes.POINTER(State),
                                                 ctypes.POINTER(StateOut), c_dbl, c_vp, c_vp]),
+    'cpfem_point_eval': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, c_i64, ctypes.POINTER(State), c_dbl, c_vp, c_vp,
+                                        ctypes.POINTER(StateOut), c_vp, c_vp, c_vp]),
     'cpfem_check_cubic': (ctypes.c_int, [c_vp, c_i64, c_dbl, c_vp, c_vp]),
     'cpfem_apply_dirichlet': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'cpfem_spmv': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     'cpfem_csr_diagonal': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_vp]),
     'cpfem_bicgstab': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_dbl, c_dbl, c_i64, ctypes.POINTER(c_i64),
                                       ctypes.POINTER(c_dbl), c_vp]),
+    'cpfem_bicgstab_enqueue': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_dbl, c_dbl, c_i64, c_i64, c_vp, c_vp, c_vp]),
     'cpfem_scatter_add': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     'cpfem_gather': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     'cpfem_sumsq': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),

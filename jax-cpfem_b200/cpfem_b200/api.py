@@ -398,6 +398,23 @@ class Plan:
                                                       float(dt), _ptr(status), _stream()), 'cpfem_point_update_state')
         return out
 
+    def point_eval(self, mat: Material, u_grads, params, dt, want_tangent=True, want_state=True, status=None):
+        """cpfem_point_eval: stress, tangent, new state and the per-point solve account (iterations, residual
+        evaluations, status bits) from one local solve per point.  Returns (P, A or None, new_state or None, info (np, 3))."""
+        with torch.cuda.device(self.device):
+            st, ts, mat = self._state(params, LAYOUT_AOS, mat)
+            ug = _dev_f64(u_grads, self.device)
+            n = int(ug.numel() // 9)
+            P = torch.empty(n, 3, 3, dtype=torch.float64, device=self.device)
+            A = torch.empty(n, 3, 3, 3, 3, dtype=torch.float64, device=self.device) if want_tangent else None
+            out = [torch.empty_like(ts[0]), torch.empty_like(ts[1]), torch.empty_like(ts[2])] if want_state else None
+            so = StateOut(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), LAYOUT_AOS) if want_state else None
+            info = torch.zeros(n, 3, dtype=torch.int32, device=self.device)
+            check(_lib.lib().cpfem_point_eval(self._h, ctypes.byref(mat), _ptr(ug), n, ctypes.byref(st), float(dt), _ptr(P), _ptr(A),
+                                              ctypes.byref(so) if so is not None else None, _ptr(info), _ptr(status), _stream()),
+                  'cpfem_point_eval')
+        return P, A, out, info
+
     def apply_dirichlet(self, rows, vals, sol, res=None, csr_data=None):
         with torch.cuda.device(self.device):
             check(_lib.lib().cpfem_apply_dirichlet(self._h, _ptr(rows), _ptr(vals), int(rows.numel()), _ptr(sol), _ptr(res),
@@ -432,6 +449,20 @@ class Plan:
             check(_lib.lib().cpfem_bicgstab(self._h, _ptr(csr_data), _ptr(b), _ptr(x), int(bool(precond)), float(tol), float(atol),
                                             int(maxiter), info, ctypes.byref(resid), _stream()), 'cpfem_bicgstab')
         return x, int(info[0]), float(resid.value)
+
+
+    def bicgstab_enqueue(self, csr_data, b, x, iters, precond=True, tol=1e-10, atol=1e-10, maxiter=10000, info=None, resid=None):
+        """cpfem_bicgstab_enqueue: no host synchronisation.  `x` holds the start vector and receives the solution; `info`
+        (int64[2]) and `resid` (float64[1]) are device tensors written when the stream gets there.  Returns (x, info, resid)."""
+        with torch.cuda.device(self.device):
+            if info is None:
+                info = torch.zeros(2, dtype=torch.int64, device=self.device)
+            if resid is None:
+                resid = torch.zeros(1, dtype=torch.float64, device=self.device)
+            check(_lib.lib().cpfem_bicgstab_enqueue(self._h, _ptr(csr_data), _ptr(b), _ptr(x), int(bool(precond)), float(tol),
+                                                    float(atol), int(maxiter), int(iters), _ptr(info), _ptr(resid), _stream()),
+                  'cpfem_bicgstab_enqueue')
+        return x, info, resid
 
 
 # ---- free helpers ------------------------------------------------------------------------------

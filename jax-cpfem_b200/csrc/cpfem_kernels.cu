@@ -1190,7 +1190,8 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
 template <int NS, int POWN, bool PP>
 __global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
 k_point_eval(const double* __restrict__ u_grads, StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip,
-             double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, cpfem_state_out sout, long long* status) {
+             double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, cpfem_state_out sout,
+             int32_t* __restrict__ point_info, long long* status) {
     extern __shared__ double smem[];
     __shared__ CpSlip s_slip;
     const CpSlipRef slp = stage_slip(slip, s_slip, NS);
@@ -1215,6 +1216,9 @@ k_point_eval(const double* __restrict__ u_grads, StateView st, const __grid_cons
     CpStressAux ax;
     cp_point_stress(ps, R, P, ax);
     if (valid) {
+        if (point_info) {           // per-point account of the local solve: Newton iterations, residual evaluations, status bits
+            point_info[p * 3] = ps.info.iters; point_info[p * 3 + 1] = ps.info.evals; point_info[p * 3 + 2] = ps.info.status;
+        }
         if (Pout) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) Pout[p * 9 + i] = P[i];
@@ -1560,7 +1564,7 @@ extern "C" int cpfem_avg_stress(const cpfem_plan* plan, const cpfem_material* ma
 
 static int point_eval_impl(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
                            const cpfem_state* st, double dt, double* P, double* tangent, const cpfem_state_out* out,
-                           int64_t* status, void* stream_, const char* who) {
+                           int32_t* point_info, int64_t* status, void* stream_, const char* who) {
     int rc = check_common(plan, mat, st, who);
     if (rc) return rc;
     if (!u_grads || np <= 0) return set_err(-1, (std::string(who) + ": bad argument").c_str());
@@ -1577,7 +1581,7 @@ static int point_eval_impl(const cpfem_plan* plan, const cpfem_material* mat, co
 #define CALL(NS, PW, PPV)                                                                                                   \
     CU_TRY(allow_smem(k_point_eval<NS, PW, PPV>, tangent_smem<NS>()));                                                      \
     k_point_eval<NS, PW, PPV><<<grid, PT_BLOCK, tangent_smem<NS>(), stream>>>(u_grads, v, km, plan->slip, dt, np, P, tangent,   \
-                                                                       so, (long long*)status)
+                                                                       so, point_info, (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
     LAUNCHED(1);
 #undef CALL
@@ -1589,7 +1593,7 @@ extern "C" int cpfem_point_stress_tangent(const cpfem_plan* plan, const cpfem_ma
                                           int64_t np, const cpfem_state* st, double dt, double* P, double* tangent,
                                           int64_t* status, void* stream_) {
     if (!P) return set_err(-1, "cpfem_point_stress_tangent: bad argument");
-    return point_eval_impl(plan, mat, u_grads, np, st, dt, P, tangent, nullptr, status, stream_, "cpfem_point_stress_tangent");
+    return point_eval_impl(plan, mat, u_grads, np, st, dt, P, tangent, nullptr, nullptr, status, stream_, "cpfem_point_stress_tangent");
 }
 
 extern "C" int cpfem_point_update_state(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads,
@@ -1597,7 +1601,14 @@ extern "C" int cpfem_point_update_state(const cpfem_plan* plan, const cpfem_mate
                                         int64_t* status, void* stream_) {
     if (!out || !out->Fp_inv || !out->g || !out->slip || !st || !st->slip)
         return set_err(-1, "cpfem_point_update_state: null argument");
-    return point_eval_impl(plan, mat, u_grads, np, st, dt, nullptr, nullptr, out, status, stream_, "cpfem_point_update_state");
+    return point_eval_impl(plan, mat, u_grads, np, st, dt, nullptr, nullptr, out, nullptr, status, stream_, "cpfem_point_update_state");
+}
+
+extern "C" int cpfem_point_eval(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
+                                const cpfem_state* st, double dt, double* P, double* tangent, const cpfem_state_out* out,
+                                int32_t* point_info, int64_t* status, void* stream_) {
+    if (out && (!out->Fp_inv || !out->g || !out->slip || !st || !st->slip)) return set_err(-1, "cpfem_point_eval: null state array");
+    return point_eval_impl(plan, mat, u_grads, np, st, dt, P, tangent, out, point_info, status, stream_, "cpfem_point_eval");
 }
 
 extern "C" int cpfem_check_cubic(const double* C, int64_t np, double rtol, int64_t* bad_count, void* stream_) {

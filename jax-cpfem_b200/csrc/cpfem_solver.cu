@@ -500,3 +500,63 @@ extern "C" int cpfem_bicgstab(cpfem_plan* plan, const double* csr_data, const do
     }
     return 0;
 }
+
+// -----------------------------------------------------------------------------------------------
+// Enqueue-only BiCGStab (for XLA-FFI handlers, SURVEY 8(b) "re-entrant, enqueue-only"): nothing here waits for the
+// device.  The pointer block travels as a kernel argument (no pinned staging buffer that a second call could overwrite
+// before the first copy ran), a FIXED number of iterations is enqueued - iterations after convergence are no-ops on the
+// device - and the outcome is written to DEVICE memory by a last one-thread kernel.
+// -----------------------------------------------------------------------------------------------
+__global__ void k_bicg_set_vecs(BicgVecs* dst, const BicgVecs v) { *dst = v; }
+__global__ void k_bicg_finish(const BicgScal* sc, int64_t* info, double* resid, int with_resid) {
+    if (info) {
+        info[0] = sc->k;                                  // iterations taken (negative: breakdown code of JAX)
+        info[1] = (sc->rs > sc->atol2) ? 1 : 0;           // 1 = stopped / ran out of enqueued iterations above the tolerance
+    }
+    if (resid && with_resid) *resid = sqrt(sc->ss);
+}
+
+extern "C" int cpfem_bicgstab_enqueue(cpfem_plan* plan, const double* csr_data, const double* b, double* x, int32_t precond,
+                                      double tol, double atol, int64_t maxiter, int64_t iters_to_enqueue, int64_t* info_dev,
+                                      double* resid_dev, void* stream_) {
+    if (!plan || !csr_data || !b || !x) return set_err(-1, "cpfem_bicgstab_enqueue: null argument");
+    if (iters_to_enqueue <= 0 || maxiter <= 0) return set_err(-1, "cpfem_bicgstab_enqueue: iteration counts must be positive");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cpfem_solver_ws* w = nullptr;
+    int rc = ws_get(plan, &w);            // first call on a plan allocates the workspace (not enqueue-only: warm it up once)
+    if (rc) return rc;
+    const int64_t n = w->n;
+    BicgVecs V;
+    V.data = csr_data; V.b = b; V.x = x;
+    const int64_t vp = w->pitch;
+    V.r = w->vec; V.rhat = w->vec + vp; V.p = w->vec + 2 * vp; V.q = w->vec + 3 * vp; V.phat = w->vec + 4 * vp;
+    V.s = w->vec + 5 * vp; V.shat = w->vec + 6 * vp; V.t = w->vec + 7 * vp;
+    double* minv = w->vec + 8 * vp;
+    V.minv = precond ? minv : nullptr;
+    const unsigned gs = spmv_grid(plan), gv = vec_grid(plan, n);
+    k_bicg_set_vecs<<<1, 1, 0, stream>>>(w->dV, V);
+    if (precond) k_csr_diag<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, minv, 1);
+    k_bicg_spmv<0><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, nullptr, plan->nn, w->sc, w->partials, w->dV, nullptr, nullptr,
+                                                tol, atol, (long long)maxiter);
+    cpfem_count_launches(precond ? 3 : 2);
+    CU_TRY(cudaGetLastError());
+    cudaGraphExec_t graph = iteration_graph(plan, w, gs, gv);      // captured once per plan, on a plan-owned stream
+    const int64_t want = iters_to_enqueue < maxiter ? iters_to_enqueue : maxiter;
+    for (int64_t done = 0; done < want; done += BICG_GRAPH_ITERS) {
+        if (graph) {
+            CU_TRY(cudaGraphLaunch(graph, stream));
+            cpfem_count_launches(5 * BICG_GRAPH_ITERS);
+        } else {
+            for (int it = 0; it < BICG_GRAPH_ITERS; ++it) launch_iteration(plan, w, gs, gv, stream);
+        }
+    }
+    if (resid_dev) {
+        k_bicg_spmv<3><<<gs, RED_BLOCK, 0, stream>>>(plan->nbr_ptr, plan->nbr, csr_data, plan->nn, nullptr, nullptr, nullptr, x, V.t, 0.0, 0.0, 0);
+        k_norm2_diff<<<gv, RED_BLOCK, 0, stream>>>(V.t, b, n, w->sc, w->partials);
+        cpfem_count_launches(2);
+    }
+    k_bicg_finish<<<1, 1, 0, stream>>>(w->sc, info_dev, resid_dev, resid_dev != nullptr);
+    cpfem_count_launches(1);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}

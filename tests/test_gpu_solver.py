@@ -186,7 +186,7 @@ def test_golden_curves_through_gpu_path():
     n = len(gold)
     got = _gpu_one_element_curve(Cu, np.linspace(0., 0.1, 81), np.linspace(0., 10., 81), n)
     print('copper curve: max rel err steps 1-20 %.2e, steps 21-80 %.2e' % (np.abs(got[:20] / gold[:20] - 1).max(), np.abs(got[20:] / gold[20:] - 1).max()))
-    assert n == 80 and np.abs(got[:20] / gold[:20] - 1).max() < 1e-8 and np.abs(got / gold - 1).max() < 1e-7
+    assert n == 80 and np.abs(got[:20] / gold[:20] - 1).max() < 1e-8 and np.abs(got[20:] / gold[20:] - 1).max() < 1e-9
     gold = np.loadtxt(os.path.join(GOLD, 'tantalum_ss_curve.txt'))
     n = len(gold)                      # all 40 committed load steps
     got = _gpu_one_element_curve(Ta, np.linspace(0., -0.10, 41), np.linspace(0., 10., 41), n)
