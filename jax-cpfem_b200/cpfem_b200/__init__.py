@@ -7,4 +7,8 @@ Host-side mirror of the reference interface:
 All numerical work happens in libcpfem_b200.so (csrc/), called through the C ABI of include/cpfem.h.
 """
 from ._lib import build, lib, LIB_PATH, CpfemError  # noqa: F401
-from .api import Plan, make_material, LAYOUT_AOS, LAYOUT_SOA  # noqa: F401
+try:
+    from .api import Plan, make_material, LAYOUT_AOS, LAYOUT_SOA  # noqa: F401
+except ImportError as _e:          # a JAX-only box without torch: the XLA-FFI path (jax_ffi, jax_problem) still works
+    if getattr(_e, 'name', '') != 'torch':
+        raise
