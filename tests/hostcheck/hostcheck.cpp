@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "../../jax-cpfem_b200/csrc/cp_point.cuh"
+#include "../../jax-cpfem_b200/csrc/cp_adjoint.cuh"
 
 typedef CpArr<1> HArr;
 
@@ -68,4 +69,63 @@ extern "C" int hostcheck_points(int ns, int pown, const double* slip6, const CpM
     else return -1;
 #undef RUN
     return 0;
+}
+
+// jac_x / jac_y / explicit dP columns of the adjoint header at given (x, y): per point jac_x (9, nx), jac_y (9, 9),
+// dPdx (9, nx), dPdS (9, 9), row-major; nx = 27 + 2 ns (+5 with_params, +81 with_C).  pp: (np, 4) = C11 C12 C44 xm.
+template <int NS>
+static void run_jac(const double* slip6, double cdt, int64_t np, const double* H, const double* A, const double* g, const double* R,
+                    const double* pp, const double* S, int with_params, int with_C, double* jac_x, double* jac_y, double* dPdx,
+                    double* dPdS) {
+    CpSlip table;
+    cp_slip_init(&table, slip6, NS);
+    const int nd = 27 + 2 * NS + (with_params ? 5 : 0);
+    const int nx = nd + (with_C ? 81 : 0);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t p = 0; p < np; ++p) {
+        const double* q = pp + 4 * p;
+        for (int c = 0; c < nd; ++c) {
+            double dr[9], dP[9];
+            cp_jac_x_column<NS>(table, cdt, H + 9 * p, A + 9 * p, g + NS * p, R + 9 * p, q[3], q[0], q[1], q[2], S + 9 * p, c, dr, dP);
+            for (int i = 0; i < 9; ++i) { jac_x[(p * 9 + i) * nx + c] = dr[i]; dPdx[(p * 9 + i) * nx + c] = dP[i]; }
+        }
+        if (with_C) {
+            double r[9], E[9], Eh[9];
+            cp_ref_residual<NS, double>(table, cdt, H + 9 * p, A + 9 * p, g + NS * p, R + 9 * p, q[3], q[0], q[1], q[2], S + 9 * p, r, nullptr, E);
+            cp_jac_C_prepare(R + 9 * p, E, Eh);
+            for (int i = 0; i < 9; ++i)
+                for (int c = 0; c < 81; ++c) { jac_x[(p * 9 + i) * nx + nd + c] = cp_jac_C_entry(R + 9 * p, Eh, i, c); dPdx[(p * 9 + i) * nx + nd + c] = 0.0; }
+        }
+        for (int m = 0; m < 9; ++m) {
+            double dr[9], dP[9];
+            cp_jac_y_column<NS>(table, cdt, H + 9 * p, A + 9 * p, g + NS * p, R + 9 * p, q[3], q[0], q[1], q[2], S + 9 * p, m, dr, dP);
+            for (int i = 0; i < 9; ++i) { jac_y[(p * 9 + i) * 9 + m] = dr[i]; dPdS[(p * 9 + i) * 9 + m] = dP[i]; }
+        }
+    }
+}
+extern "C" int hostcheck_jac(int ns, const double* slip6, double cdt, int64_t np, const double* H, const double* A, const double* g,
+                             const double* R, const double* pp, const double* S, int with_params, int with_C, double* jac_x,
+                             double* jac_y, double* dPdx, double* dPdS) {
+    if (ns == 12) run_jac<12>(slip6, cdt, np, H, A, g, R, pp, S, with_params, with_C, jac_x, jac_y, dPdx, dPdS);
+    else if (ns == 24) run_jac<24>(slip6, cdt, np, H, A, g, R, pp, S, with_params, with_C, jac_x, jac_y, dPdx, dPdS);
+    else return -1;
+    return 0;
+}
+// per-point VJP (cp_point_vjp) for the differentiable columns; grad (np, nd)
+extern "C" int hostcheck_vjp(int ns, const double* slip6, double cdt, int64_t np, const double* H, const double* A, const double* g,
+                             const double* R, const double* pp, const double* S, const double* W, int with_params, double* grad) {
+    CpSlip table;
+    if (ns != 12 && ns != 24) return -1;
+    cp_slip_init(&table, slip6, ns);
+    const int nd = 27 + 2 * ns + (with_params ? 5 : 0);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t p = 0; p < np; ++p) {
+        const double* q = pp + 4 * p;
+        double lam[9];
+        bool ok = (ns == 12) ? cp_point_vjp<12>(table, cdt, H + 9 * p, A + 9 * p, g + ns * p, R + 9 * p, q[3], q[0], q[1], q[2], S + 9 * p, W + 9 * p, 0, nd, grad + nd * p, lam)
+                             : cp_point_vjp<24>(table, cdt, H + 9 * p, A + 9 * p, g + ns * p, R + 9 * p, q[3], q[0], q[1], q[2], S + 9 * p, W + 9 * p, 0, nd, grad + nd * p, lam);
+        if (!ok) bad = 1;
+    }
+    return bad ? -2 : 0;
 }

@@ -114,6 +114,37 @@ def test_bicgstab_vs_oracle():
     assert kz == 0 and np.array_equal(xz.cpu().numpy(), x_d)
 
 
+def test_bicgstab_enqueue_only():
+    """cpfem_bicgstab_enqueue (what the XLA-FFI handler calls): no host synchronisation, a fixed number of iterations
+    enqueued, outcome in device memory - the same iterates as the polling version (iterations after convergence are
+    no-ops), and a too-small budget reports 'not converged' and can be continued from the returned x."""
+    import torch
+    plan, data, A, res = _plan_and_matrix()
+    b = -res.reshape(-1)
+    x_ref, k_ref, err_ref = plan.bicgstab(data, b)
+    x = torch.zeros(plan.ndof, dtype=torch.float64, device='cuda')
+    x, info, resid = plan.bicgstab_enqueue(data, b, x, iters=k_ref + 40)
+    torch.cuda.synchronize()
+    assert int(info[0]) == k_ref and int(info[1]) == 0
+    assert torch.equal(x, x_ref) and abs(float(resid[0]) - err_ref) <= 1e-12 * max(err_ref, 1.0)
+    # two calls in a row on the same plan without any synchronisation in between (no shared pinned staging)
+    xa = torch.zeros_like(x)
+    xb = torch.zeros_like(x)
+    _, ia, ra = plan.bicgstab_enqueue(data, b, xa, iters=k_ref + 40)
+    _, ib, rb = plan.bicgstab_enqueue(data, 2.0 * b, xb, iters=k_ref + 40)
+    torch.cuda.synchronize()
+    assert torch.equal(xa, x_ref) and int(ia[1]) == 0 and int(ib[1]) == 0
+    assert float((xb - 2.0 * x_ref).abs().max()) < 1e-8 * float(x_ref.abs().max())
+    # budget exhausted: flagged, and the solve continues from x
+    xs = torch.zeros_like(x)
+    _, i1, _ = plan.bicgstab_enqueue(data, b, xs, iters=8)
+    torch.cuda.synchronize()
+    assert int(i1[1]) == 1 and int(i1[0]) == 8
+    _, i2, r2 = plan.bicgstab_enqueue(data, b, xs, iters=k_ref + 80)
+    torch.cuda.synchronize()
+    assert int(i2[1]) == 0 and float((xs - x_ref).abs().max()) < 1e-8 * float(x_ref.abs().max())
+
+
 def test_device_newton_solver_vs_oracle():
     """solver(problem) of the mirror (device assembly + Dirichlet rows + device BiCGStab) vs the oracle's load step
     (autodiff assembly + direct solve) over two load steps of the copper driver's boundary conditions."""
