@@ -21,6 +21,8 @@
  *                                        (models_copper.py:135-137,155-162,251-265)
  *   cpfem_point_update_state             get_maps()'s update_int_vars_map under vmap (models_copper.py:164-169,267-269)
  *   cpfem_apply_dirichlet                apply_bc_vec + zeroRows                (solver.py:119-133,290-293)
+ *   cpfem_point_jac_x / cpfem_point_vjp  f_jvp's jac_x, jac_y (models_copper.py:251-259) and their reverse mode
+ *   cpfem_vjp_params                     vjp_linear_fn of implicit_vjp          (solver.py:832-848)
  */
 #ifndef CPFEM_H
 #define CPFEM_H
@@ -163,6 +165,40 @@ int cpfem_point_eval(const cpfem_plan* plan, const cpfem_material* mat, const do
                      const cpfem_state* st, double dt, double* P, double* tangent, const cpfem_state_out* out,
                      int32_t* point_info, int64_t* status, void* stream);
 
+/* ---- adjoint columns --------------------------------------------------------------------
+ * x = ravel([u_grad, Fp_inv_old, slip_resistance_old, slip_old, rot_mat]) (models_copper.py:156; nx = 27 + 2 ns), followed by
+ * [gss_a, h, t_sat, xm, r] when nextra >= 5 (calibration form, calibration/case1.py:153) and by C (81) when nextra == 6 (DP
+ * form, models_DPsteel_inhomo.py:245; nx = 161 for ns = 24).  y = the nine entries of S.  Derivatives follow the reference's
+ * literal formulation (rot_mat's nine entries independent, like jax.jacfwd sees them). */
+/* f_jvp's Jacobians at the converged local solution (models_copper.py:256-257): jac_x (np, 9, nx) = d implicit_residual/dx,
+ * and, if not NULL, jac_y (np, 9, 9) = d implicit_residual/dy and S (np, 9) = y itself. */
+int cpfem_point_jac_x(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
+                      const cpfem_state* st, double dt, int32_t nextra, double* jac_x, double* jac_y, double* S,
+                      int64_t* status, void* stream);
+/* Reverse mode of tensor_map through the local solve: grad (np, nx) = W : dP/dx with dP/dx = dP/dx|_S - dP/dS J_y^-1 J_x,
+ * W (np, 9) the cotangent of P.  (The first nine columns are W : the consistent tangent.) */
+int cpfem_point_vjp(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
+                    const cpfem_state* st, double dt, int32_t nextra, const double* W, double* grad, int64_t* status, void* stream);
+/* vjp_linear_fn of implicit_vjp (crystal_plasticity_OR_design/solver.py:832-848): adjoint (nnodes, 3) contracted with
+ * d(residual vector)/d(internal_vars), i.e. per point W_ij = sum_a adjoint[node_a, i] dN_a/dX_j JxW pushed through
+ * cpfem_point_vjp, written into arrays shaped like the state (any pointer may be NULL).  Zero the adjoint on Dirichlet dofs
+ * first (their residual rows do not depend on the state, solver.py:119-133).  The caller applies implicit_vjp's final
+ * minus sign (solver.py:849). */
+typedef struct cpfem_state_grad {
+    double* Fp_inv;   /* (np, 9)  */
+    double* g;        /* (np, ns) */
+    double* slip;     /* (np, ns) - identically zero: P does not depend on the accumulated slip */
+    double* rot;      /* (np, 9)  */
+    double* gss_a;    /* (np) - zero: the hardening law does not enter P */
+    double* h;        /* (np) - zero */
+    double* t_sat;    /* (np) - zero */
+    double* xm;       /* (np) */
+    double* r;        /* (np) - zero */
+    double* C;        /* (np, 81) */
+} cpfem_state_grad;
+int cpfem_vjp_params(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* st, double dt,
+                     const double* adjoint, const cpfem_state_grad* out, int64_t* status, void* stream);
+
 /* Input validation for the DP-steel form of the state (models_DPsteel_inhomo.py:121-147,185-186): counts the points of a
  * (np, 81) elastic-tensor array that are NOT of the cubic pattern in the crystal frame (C11 on iiii, C12 on iijj, C44 on
  * ijij / ijji, zero elsewhere; tolerance rtol x the largest constant).  *bad_count is a device int64 that is accumulated
@@ -182,6 +218,9 @@ int cpfem_apply_dirichlet(const cpfem_plan* plan, const int64_t* rows, const dou
 int cpfem_spmv(const cpfem_plan* plan, const double* csr_data, const double* x, double* y, void* stream);
 /* diag(A) (solver.py:32 `A_sp_scipy.diagonal()`), or 1/diag(A) when invert != 0. */
 int cpfem_csr_diagonal(const cpfem_plan* plan, const double* csr_data, double* diag, int32_t invert, void* stream);
+/* Values of A^T on the same pattern (the pattern is structurally symmetric): what linear_solver(A.transpose(), ...) of
+ * implicit_vjp needs (solver.py:844).  csr_data_T must not alias csr_data. */
+int cpfem_csr_transpose(const cpfem_plan* plan, const double* csr_data, double* csr_data_T, void* stream);
 /* BiCGStab with the semantics of jax.scipy.sparse.linalg.bicgstab(A, b, x0=x, M=Jacobi if precond, tol, atol, maxiter)
  * as called at solver.py:34-40: x holds x0 on entry and the solution on return.  info[0] = iterations taken (JAX's
  * negative breakdown codes -10 / -11 are passed through), info[1] = 1 if the tolerance was not reached; *resid, if not

@@ -33,6 +33,11 @@ class State(ctypes.Structure):
     _fields_ = [(n, c_vp) for n in ('Fp_inv', 'g', 'slip', 'rot', 'gss_a', 'h', 't_sat', 'xm', 'r', 'C')] + [('layout', c_i32)]
 
 
+class StateGrad(ctypes.Structure):
+    """cpfem_state_grad."""
+    _fields_ = [(n, c_vp) for n in ('Fp_inv', 'g', 'slip', 'rot', 'gss_a', 'h', 't_sat', 'xm', 'r', 'C')]
+
+
 class StateOut(ctypes.Structure):
     """cpfem_state_out."""
     _fields_ = [('Fp_inv', c_vp), ('g', c_vp), ('slip', c_vp), ('layout', c_i32)]
@@ -63,10 +68,17 @@ SIGNATURES = {
                                                 ctypes.POINTER(StateOut), c_dbl, c_vp, c_vp]),
     'cpfem_point_eval': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, c_i64, ctypes.POINTER(State), c_dbl, c_vp, c_vp,
                                         ctypes.POINTER(StateOut), c_vp, c_vp, c_vp]),
+    'cpfem_point_jac_x': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, c_i64, ctypes.POINTER(State), c_dbl, c_i32, c_vp, c_vp,
+                                         c_vp, c_vp, c_vp]),
+    'cpfem_point_vjp': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, c_i64, ctypes.POINTER(State), c_dbl, c_i32, c_vp, c_vp,
+                                       c_vp, c_vp]),
+    'cpfem_vjp_params': (ctypes.c_int, [c_vp, ctypes.POINTER(Material), c_vp, ctypes.POINTER(State), c_dbl, c_vp,
+                                        ctypes.POINTER(StateGrad), c_vp, c_vp]),
     'cpfem_check_cubic': (ctypes.c_int, [c_vp, c_i64, c_dbl, c_vp, c_vp]),
     'cpfem_apply_dirichlet': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'cpfem_spmv': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     'cpfem_csr_diagonal': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_vp]),
+    'cpfem_csr_transpose': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     'cpfem_bicgstab': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_dbl, c_dbl, c_i64, ctypes.POINTER(c_i64),
                                       ctypes.POINTER(c_dbl), c_vp]),
     'cpfem_bicgstab_enqueue': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_dbl, c_dbl, c_i64, c_i64, c_vp, c_vp, c_vp]),
@@ -93,7 +105,7 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(_CSRC, 'cp_point.cuh'), os.path.join(_CSRC, 'cpfem_internal.h'), os.path.join(_INCLUDE, 'cpfem.h')]
+    deps = sources() + [os.path.join(_CSRC, 'cp_point.cuh'), os.path.join(_CSRC, 'cp_adjoint.cuh'), os.path.join(_CSRC, 'cpfem_internal.h'), os.path.join(_INCLUDE, 'cpfem.h')]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -11,7 +11,7 @@ import numpy as onp
 import torch
 
 from . import _lib
-from ._lib import Material, State, StateOut, check
+from ._lib import Material, State, StateGrad, StateOut, check
 
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 
@@ -414,6 +414,58 @@ class Plan:
                                               ctypes.byref(so) if so is not None else None, _ptr(info), _ptr(status), _stream()),
                   'cpfem_point_eval')
         return P, A, out, info
+
+    # ---- adjoint columns (F5) ----------------------------------------------------------------------
+    @staticmethod
+    def _nextra(params):
+        return {4: 0, 9: 5, 10: 6}[len(params)]
+
+    def point_jac_x(self, mat: Material, u_grads, params, dt, want_jac_y=True, status=None):
+        """f_jvp's jac_x (np, 9, nx), jac_y (np, 9, 9) and y = S (np, 9) at the converged local solution
+        (models_copper.py:251-259); x in the reference's ravel order, see include/cpfem.h."""
+        with torch.cuda.device(self.device):
+            st, ts = self._state(params, LAYOUT_AOS)
+            ug = _dev_f64(u_grads, self.device)
+            n, ne = int(ug.numel() // 9), self._nextra(params)
+            nx = 27 + 2 * self.ns + (5 if ne >= 5 else 0) + (81 if ne >= 6 else 0)
+            jx = torch.empty(n, 9, nx, dtype=torch.float64, device=self.device)
+            jy = torch.empty(n, 9, 9, dtype=torch.float64, device=self.device) if want_jac_y else None
+            S = torch.empty(n, 9, dtype=torch.float64, device=self.device)
+            check(_lib.lib().cpfem_point_jac_x(self._h, ctypes.byref(mat), _ptr(ug), n, ctypes.byref(st), float(dt), ne, _ptr(jx),
+                                               _ptr(jy), _ptr(S), _ptr(status), _stream()), 'cpfem_point_jac_x')
+        return jx, jy, S
+
+    def point_vjp(self, mat: Material, u_grads, params, dt, W, status=None):
+        """W : d tensor_map / dx through the local solve: (np, nx)."""
+        with torch.cuda.device(self.device):
+            st, ts = self._state(params, LAYOUT_AOS)
+            ug, W = _dev_f64(u_grads, self.device), _dev_f64(W, self.device)
+            n, ne = int(ug.numel() // 9), self._nextra(params)
+            nx = 27 + 2 * self.ns + (5 if ne >= 5 else 0) + (81 if ne >= 6 else 0)
+            grad = torch.empty(n, nx, dtype=torch.float64, device=self.device)
+            check(_lib.lib().cpfem_point_vjp(self._h, ctypes.byref(mat), _ptr(ug), n, ctypes.byref(st), float(dt), ne, _ptr(W), _ptr(grad),
+                                             _ptr(status), _stream()), 'cpfem_point_vjp')
+        return grad
+
+    def vjp_params(self, mat: Material, sol, params, dt, adjoint, status=None):
+        """vjp_linear_fn of implicit_vjp (solver.py:832-848): adjoint (nnodes, 3) . d(residual)/d(internal_vars) as a list of
+        arrays shaped like `params` (zero the adjoint on the Dirichlet dofs first; the caller applies the final minus sign)."""
+        with torch.cuda.device(self.device):
+            st, ts = self._state(params, LAYOUT_AOS)
+            sol, adj = _dev_f64(sol, self.device), _dev_f64(adjoint, self.device)
+            out = [torch.empty_like(t) for t in ts]
+            sg = StateGrad(*[o.data_ptr() for o in out], *([None] * (10 - len(out))))
+            check(_lib.lib().cpfem_vjp_params(self._h, ctypes.byref(mat), _ptr(sol), ctypes.byref(st), float(dt), _ptr(adj),
+                                              ctypes.byref(sg), _ptr(status), _stream()), 'cpfem_vjp_params')
+        return out
+
+    def csr_transpose(self, csr_data, out=None):
+        """Values of A^T on the plan's (structurally symmetric) pattern."""
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty_like(csr_data)
+            check(_lib.lib().cpfem_csr_transpose(self._h, _ptr(csr_data), _ptr(out), _stream()), 'cpfem_csr_transpose')
+        return out
 
     def apply_dirichlet(self, rows, vals, sol, res=None, csr_data=None):
         with torch.cuda.device(self.device):

@@ -372,6 +372,15 @@ class CrystalPlasticityBase(Problem):
         params = [api._dev_f64(v, self.device) for v in params]
         return self.plan.avg_stress(self.material, sol, params, self.dt)
 
+    def vjp_params(self, sol, params, adjoint):
+        """adjoint . d(compute_residual)/d(params): what jax.vjp of the constraint function gives inside implicit_vjp
+        (crystal_plasticity_OR_design/solver.py:832-848), as a list shaped like `params`."""
+        params = [api._dev_f64(v, self.device) for v in params]
+        st = self.plan.new_status()
+        out = self.plan.vjp_params(self.material, sol, params, self.dt, adjoint, status=st)
+        self.last_status = st
+        return out
+
     def inspect_interval_vars(self, params):
         """models_copper.py:287-295 (post-processing only)."""
         Fp_inv_gp, slip_resistance_gp, slip_gp = params[0], params[1], params[2]

@@ -10,7 +10,9 @@ BiCGStab (`cpfem_bicgstab`) where it lies instead of building a scipy/PETSc matr
     line_search                              solver.py:240-276
     apply_bc_vec / get_A                     solver.py:119-133, 279-293  (one kernel: cpfem_apply_dirichlet)
 
-Out of scope here: arc-length, dynamic relaxation, adjoint / implicit_vjp, PETSc, P_mat constraints.
+    implicit_vjp                             solver.py:801-853  (adjoint solve on A^T + the parameter VJP kernel, row F5)
+
+Out of scope here: arc-length, dynamic relaxation, PETSc, P_mat constraints.
 """
 from __future__ import annotations
 
@@ -182,3 +184,24 @@ def solver(problem, solver_options=None):
     problem.last_newton_iterations = its
     logger.info('Solve took %g [s]', time.time() - start)
     return problem.unflatten_fn_sol_list(dofs)
+
+
+def implicit_vjp(problem, sol_list, params, v_list, adjoint_solver_options=None):
+    """solver.py:801-853: the adjoint method.  Solves A^T lambda = v on the device (the tangent assembled at sol_list with
+    its Dirichlet rows, transposed values on the same pattern), then contracts lambda with d(constraint)/d(params) by the
+    per-point VJP kernel (cpfem_vjp_params) and returns MINUS that, as a list shaped like `params` - what the reference's
+    jax.vjp(partial_params_c_fn)(adjoint) followed by tree_map(-x) gives.  The constraint rows of Dirichlet dofs
+    (u - u_bc, apply_bc) do not depend on the parameters, so lambda is zeroed there before the contraction."""
+    adjoint_solver_options = {} if adjoint_solver_options is None else adjoint_solver_options
+    problem.set_params(params)
+    problem.newton_update(sol_list)
+    A = get_A(problem, adjoint_solver_options)
+    v_vec = torch.cat([api._dev_f64(v, problem.device).reshape(-1) for v in v_list])
+    AT = problem.plan.csr_transpose(A)
+    adjoint_vec = linear_solver(problem, AT, v_vec, torch.zeros_like(v_vec), adjoint_solver_options)
+    rows, _ = _bc_rows_vals(problem)
+    lam = adjoint_vec.clone()
+    if rows.numel():
+        lam[rows] = 0.0
+    grads = problem.vjp_params(sol_list[0], params, problem.unflatten_fn_sol_list(lam)[0])
+    return [-g for g in grads]

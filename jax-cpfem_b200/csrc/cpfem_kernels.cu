@@ -25,6 +25,7 @@
 #include <atomic>
 
 #include "cpfem_internal.h"
+#include "cp_adjoint.cuh"
 
 static_assert(sizeof(cpfem_material) == sizeof(CpMaterial), "material struct mismatch");
 
@@ -1265,6 +1266,151 @@ __global__ void k_check_cubic(const double* __restrict__ C, int64_t np, double r
 }
 
 // -----------------------------------------------------------------------------------------------
+// F5: adjoint columns (cp_adjoint.cuh).  One thread per point: the local solve (forward kernels' code), S back to the lab
+// frame, then the dual-number columns of the reference's literal residual.  Not a throughput path (it runs once per
+// load step of a backward pass): run-time rate exponent and per-point parameter loads only, to keep the number of
+// instantiations at two.
+//   MODE 0: jac_x (np, 9, nx) [+ jac_y (np, 9, 9)] [+ S (np, 9)]        f_jvp's Jacobians, models_copper.py:256-257
+//   MODE 1: grad (np, nx) = W : dP/dx through the implicit function          reverse mode of tensor_map
+//   MODE 2: like 1 with W_ij = sum_a adj[node_a, i] dN_a/dX_j JxW from a nodal adjoint vector, the u_grad columns skipped
+//           and the result scattered into arrays shaped like internal_vars  (vjp_linear_fn of implicit_vjp, solver.py:832-838)
+// -----------------------------------------------------------------------------------------------
+struct GradView {
+    double *Fp_inv, *g, *slip, *rot, *gss_a, *h, *t_sat, *xm, *r, *C;
+};
+
+template <int NS, int MODE>
+__global__ void __launch_bounds__(PT_BLOCK, 1)
+k_point_adjoint(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
+                const double* __restrict__ u_grads, StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip,
+                double dt, int64_t np, int nextra, const double* __restrict__ Win, double* __restrict__ jac_x,
+                double* __restrict__ jac_y, double* __restrict__ S_out, double* __restrict__ grad, GradView gv, long long* status) {
+    extern __shared__ double smem[];
+    __shared__ CpSlip s_slip;
+    const CpSlipRef slp = stage_slip(slip, s_slip, NS);
+    int64_t p = (int64_t)blockIdx.x * PT_BLOCK + threadIdx.x;
+    const bool valid = p < np;
+    if (!valid) p = np - 1;
+    CpPointState<SArr> ps;
+    point_arrays<NS>(smem, ps);
+    const CpMaterial& mat = km.m;
+    CpPointParams pm;
+    load_point_params(mat, st, p, pm);
+    double H[9], W[9];
+    if (MODE == 2) {
+        double gN[8][3], JxW;
+        const int64_t c = p >> 3;
+        point_kinematics(cells, points, sol, c, (int)(p & 7), H, gN, JxW);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) W[i] = 0.0;
+        for (int a = 0; a < 8; ++a) {
+            const int64_t nd = cells[c * 8 + a];
+            for (int i = 0; i < 3; ++i) {
+                const double l = Win[nd * 3 + i] * JxW;
+                for (int j = 0; j < 3; ++j) W[3 * i + j] += l * gN[a][j];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] = u_grads[p * 9 + i];
+        if (MODE == 1)
+            for (int i = 0; i < 9; ++i) W[i] = Win[p * 9 + i];
+    }
+    solve_point<NS, 0>(st, mat, slp, dt, p, np, H, pm, ps);
+    warp_status(ps.info, valid, status);
+    if (!valid) return;
+    double A[9], R[9], g[NS], S[9];
+    load9(st.Fp_inv, st.soa, p, np, A);
+    load9(st.rot, st.soa, p, np, R);
+    {
+        const GIn gi = gin(st.g, st.soa, p, NS, np);
+        for (int a = 0; a < NS; ++a) g[a] = gi[a];
+        double Sc[9], T[9];
+        sym6_to_m3(ps.s, Sc);
+        m3_mul(R, Sc, T);
+        m3_mul_nt(T, R, S);                       // S (lab) = R S_c R^T
+    }
+    const double xm = st.xm ? st.xm[p] : mat.xm;
+    const double cdt = mat.ao * dt;
+    const int nd = 27 + 2 * NS + (nextra >= 5 ? 5 : 0);           // differentiable columns; the C block follows
+    const int nx = nd + (nextra >= 6 ? 81 : 0);
+    const CpSlip& table = s_slip;
+    if (MODE == 0) {
+        double* jx = jac_x + p * 9 * (int64_t)nx;
+        for (int c = 0; c < nd; ++c) {
+            double dr[9];
+            cp_jac_x_column<NS>(table, cdt, H, A, g, R, xm, pm.C11, pm.C12, pm.C44, S, c, dr, nullptr);
+            for (int i = 0; i < 9; ++i) jx[i * nx + c] = dr[i];
+        }
+        if (nextra >= 6) {
+            double r[9], E[9], Eh[9];
+            cp_ref_residual<NS, double>(table, cdt, H, A, g, R, xm, pm.C11, pm.C12, pm.C44, S, r, nullptr, E);
+            cp_jac_C_prepare(R, E, Eh);
+            for (int i = 0; i < 9; ++i)
+                for (int c = 0; c < 81; ++c) jx[i * nx + nd + c] = cp_jac_C_entry(R, Eh, i, c);
+        }
+        if (jac_y) {
+            for (int m = 0; m < 9; ++m) {
+                double dr[9];
+                cp_jac_y_column<NS>(table, cdt, H, A, g, R, xm, pm.C11, pm.C12, pm.C44, S, m, dr, nullptr);
+                for (int i = 0; i < 9; ++i) jac_y[(p * 9 + i) * 9 + m] = dr[i];
+            }
+        }
+        if (S_out)
+            for (int i = 0; i < 9; ++i) S_out[p * 9 + i] = S[i];
+    } else {
+        const int c0 = (MODE == 2) ? 9 : 0;
+        double gr[27 + 2 * NS + 5], lam[9];
+        const bool ok = cp_point_vjp<NS>(table, cdt, H, A, g, R, xm, pm.C11, pm.C12, pm.C44, S, W, c0, nd, gr, lam);
+        if (!ok && status) atomicAdd((unsigned long long*)&status[1], 1ULL);
+        // C block: grad[abcd] = -lam . dr/dC_abcd = (R^T Lam R)_ab Ehat_cd
+        double GC[9], Eh[9];
+        if (nextra >= 6) {
+            double r[9], E[9], t[9];
+            cp_ref_residual<NS, double>(table, cdt, H, A, g, R, xm, pm.C11, pm.C12, pm.C44, S, r, nullptr, E);
+            cp_jac_C_prepare(R, E, Eh);
+            m3_mul_tn(R, lam, t);
+            m3_mul(t, R, GC);
+        }
+        if (MODE == 1) {
+            double* out = grad + p * (int64_t)nx;
+            for (int c = 0; c < nd; ++c) out[c] = gr[c];
+            if (nextra >= 6)
+                for (int ab = 0; ab < 9; ++ab)
+                    for (int cd = 0; cd < 9; ++cd) out[nd + 9 * ab + cd] = GC[ab] * Eh[cd];
+        } else {
+            const double* q = gr;                 // columns 9.. : Fp_inv (9), g (NS), slip (NS), rot (9), params (5)
+            if (gv.Fp_inv) for (int i = 0; i < 9; ++i) gv.Fp_inv[p * 9 + i] = q[i];
+            if (gv.g) for (int a = 0; a < NS; ++a) gv.g[p * NS + a] = q[9 + a];
+            if (gv.slip) for (int a = 0; a < NS; ++a) gv.slip[p * NS + a] = 0.0;
+            if (gv.rot) for (int i = 0; i < 9; ++i) gv.rot[p * 9 + i] = q[9 + 2 * NS + i];
+            if (gv.gss_a) gv.gss_a[p] = 0.0;
+            if (gv.h) gv.h[p] = 0.0;
+            if (gv.t_sat) gv.t_sat[p] = 0.0;
+            if (gv.r) gv.r[p] = 0.0;
+            if (gv.xm) {
+                double v = 0.0;
+                if (nextra >= 5) v = q[18 + 2 * NS + 3];
+                else { double dr[9], dP[9]; cp_jac_x_column<NS>(table, cdt, H, A, g, R, xm, pm.C11, pm.C12, pm.C44, S, 27 + 2 * NS + 3, dr, dP);
+                       for (int i = 0; i < 9; ++i) v += W[i] * dP[i] - lam[i] * dr[i]; }
+                gv.xm[p] = v;
+            }
+            if (gv.C) {
+                if (nextra < 6) {
+                    double r[9], E[9], t[9];
+                    cp_ref_residual<NS, double>(table, cdt, H, A, g, R, xm, pm.C11, pm.C12, pm.C44, S, r, nullptr, E);
+                    cp_jac_C_prepare(R, E, Eh);
+                    m3_mul_tn(R, lam, t);
+                    m3_mul(t, R, GC);
+                }
+                for (int ab = 0; ab < 9; ++ab)
+                    for (int cd = 0; cd < 9; ++cd) gv.C[p * 81 + 9 * ab + cd] = GC[ab] * Eh[cd];
+            }
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
 // small utility kernels
 // -----------------------------------------------------------------------------------------------
 __global__ void k_dirichlet(const int64_t* __restrict__ rows, const double* __restrict__ vals, int64_t nbc,
@@ -1609,6 +1755,63 @@ extern "C" int cpfem_point_eval(const cpfem_plan* plan, const cpfem_material* ma
                                 int32_t* point_info, int64_t* status, void* stream_) {
     if (out && (!out->Fp_inv || !out->g || !out->slip || !st || !st->slip)) return set_err(-1, "cpfem_point_eval: null state array");
     return point_eval_impl(plan, mat, u_grads, np, st, dt, P, tangent, out, point_info, status, stream_, "cpfem_point_eval");
+}
+
+// ---- F5 entry points ------------------------------------------------------------------------------------------------
+template <int MODE>
+static int adjoint_impl(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const double* u_grads, int64_t np,
+                        const cpfem_state* st, double dt, int32_t nextra, const double* Win, double* jac_x, double* jac_y,
+                        double* S_out, double* grad, const GradView& gv, int64_t* status, void* stream_, const char* who) {
+    int rc = check_common(plan, mat, st, who);
+    if (rc) return rc;
+    if (np <= 0) return set_err(-1, (std::string(who) + ": no points").c_str());
+    if (st->layout != CPFEM_LAYOUT_AOS) return set_err(-1, (std::string(who) + ": AoS state only").c_str());
+    if (nextra != 0 && nextra != 5 && nextra != 6) return set_err(-1, (std::string(who) + ": nextra must be 0, 5 or 6").c_str());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const unsigned grid = (unsigned)((np + PT_BLOCK - 1) / PT_BLOCK);
+    StateView v = make_view(st);
+    CpMaterial m = to_mat(mat);
+    const KMat km = make_kmat(m);
+    if (plan->ns == 12) {
+        CU_TRY(allow_smem(k_point_adjoint<12, MODE>, point_smem<12>()));
+        k_point_adjoint<12, MODE><<<grid, PT_BLOCK, point_smem<12>(), stream>>>(plan->cells, plan->points, sol, u_grads, v, km, plan->slip, dt,
+                                                                              np, nextra, Win, jac_x, jac_y, S_out, grad, gv, (long long*)status);
+    } else {
+        CU_TRY(allow_smem(k_point_adjoint<24, MODE>, point_smem<24>()));
+        k_point_adjoint<24, MODE><<<grid, PT_BLOCK, point_smem<24>(), stream>>>(plan->cells, plan->points, sol, u_grads, v, km, plan->slip, dt,
+                                                                              np, nextra, Win, jac_x, jac_y, S_out, grad, gv, (long long*)status);
+    }
+    LAUNCHED(1);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cpfem_point_jac_x(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
+                                 const cpfem_state* st, double dt, int32_t nextra, double* jac_x, double* jac_y, double* S,
+                                 int64_t* status, void* stream_) {
+    if (!u_grads || !jac_x) return set_err(-1, "cpfem_point_jac_x: null argument");
+    GradView gv = {};
+    return adjoint_impl<0>(plan, mat, nullptr, u_grads, np, st, dt, nextra, nullptr, jac_x, jac_y, S, nullptr, gv, status, stream_,
+                           "cpfem_point_jac_x");
+}
+
+extern "C" int cpfem_point_vjp(const cpfem_plan* plan, const cpfem_material* mat, const double* u_grads, int64_t np,
+                               const cpfem_state* st, double dt, int32_t nextra, const double* W, double* grad, int64_t* status,
+                               void* stream_) {
+    if (!u_grads || !W || !grad) return set_err(-1, "cpfem_point_vjp: null argument");
+    GradView gv = {};
+    return adjoint_impl<1>(plan, mat, nullptr, u_grads, np, st, dt, nextra, W, nullptr, nullptr, nullptr, grad, gv, status, stream_,
+                           "cpfem_point_vjp");
+}
+
+extern "C" int cpfem_vjp_params(const cpfem_plan* plan, const cpfem_material* mat, const double* sol, const cpfem_state* st,
+                                double dt, const double* adjoint, const cpfem_state_grad* out, int64_t* status, void* stream_) {
+    if (!plan || !sol || !adjoint || !out) return set_err(-1, "cpfem_vjp_params: null argument");
+    if (plan->nc_active == 0) return check_common(plan, mat, st, "cpfem_vjp_params", false);
+    GradView gv = {out->Fp_inv, out->g, out->slip, out->rot, out->gss_a, out->h, out->t_sat, out->xm, out->r, out->C};
+    const int32_t nextra = (st && st->C) ? 6 : ((st && (st->gss_a || st->h || st->t_sat || st->xm || st->r)) ? 5 : 0);
+    return adjoint_impl<2>(plan, mat, sol, nullptr, plan->nc_active * 8, st, dt, nextra, adjoint, nullptr, nullptr, nullptr, nullptr, gv,
+                           status, stream_, "cpfem_vjp_params");
 }
 
 extern "C" int cpfem_check_cubic(const double* C, int64_t np, double rtol, int64_t* bad_count, void* stream_) {

@@ -560,3 +560,43 @@ extern "C" int cpfem_bicgstab_enqueue(cpfem_plan* plan, const double* csr_data, 
     CU_TRY(cudaGetLastError());
     return 0;
 }
+
+// -----------------------------------------------------------------------------------------------
+// A^T on the plan's pattern (structurally symmetric: node adjacency is).  The adjoint solve of implicit_vjp is
+// linear_solver(A.transpose(), v) (crystal_plasticity_OR_design/solver.py:844): the transposed values are written once and
+// the ordinary node-block BiCGStab runs on them.  One thread per (node n, neighbour slot j): block (n, m) of A^T is the
+// transpose of block (m, n) of A, found by a binary search of n in m's sorted neighbour list.
+// -----------------------------------------------------------------------------------------------
+__global__ void k_csr_transpose(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr, int64_t nn, int64_t nblocks,
+                                const double* __restrict__ in, double* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nblocks) return;
+    // node n that owns block slot t: binary search in nbr_ptr
+    int64_t lo = 0, hi = nn - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (nbr_ptr[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int64_t n = lo, b0 = nbr_ptr[n], mn = nbr_ptr[n + 1] - b0, j = t - b0;
+    const int64_t m = nbr[t], c0 = nbr_ptr[m], mm = nbr_ptr[m + 1] - c0;
+    int64_t a = 0, b = mm - 1;
+    while (a < b) {
+        const int64_t mid = (a + b) >> 1;
+        if (nbr[c0 + mid] < (int32_t)n) a = mid + 1; else b = mid;
+    }
+    const int64_t r = a;                          // rank of n in m's list (present: the adjacency is symmetric)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) out[9 * b0 + i * 3 * mn + 3 * j + k] = in[9 * c0 + k * 3 * mm + 3 * r + i];
+}
+
+extern "C" int cpfem_csr_transpose(const cpfem_plan* plan, const double* csr_data, double* csr_data_T, void* stream_) {
+    if (!plan || !csr_data || !csr_data_T || csr_data == csr_data_T) return set_err(-1, "cpfem_csr_transpose: bad argument");
+    const int64_t nblocks = plan->nnz / 9;
+    cpfem_count_launches(1);
+    k_csr_transpose<<<(unsigned)((nblocks + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(plan->nbr_ptr, plan->nbr, plan->nn, nblocks,
+                                                                                         csr_data, csr_data_T);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}

@@ -30,7 +30,10 @@ Differences from the reference that are deliberate and do not change results:
   * `abs(x)**n * sign(x)` is guarded at x == 0 so that torch's batched forward-mode rule returns
     the same 0 that JAX returns there (torch would produce NaN from 0*inf).
   * Forward assembly only ever pushes tangents through `u_grad`; the 42 (152) other columns of
-    `jac_x` (`models_copper.py:256`) multiply zero tangents and are not formed.
+    `jac_x` (`models_copper.py:256`) multiply zero tangents and are not formed there.  The full `jac_x`
+    (all 51 / 56 / 161 columns) and what reverse mode makes of f_jvp inside `implicit_vjp`
+    (`crystal_plasticity_OR_design/solver.py:801-853`) are restated by `PointBatch.jac_x`, `PointBatch.dP_dx`
+    and `FEOracle.vjp_params` for the adjoint row.
 """
 from __future__ import annotations
 
@@ -375,6 +378,53 @@ class PointBatch:
         A = dP_du + dP_dy @ dy
         return A.reshape(n, 3, 3, 3, 3)
 
+    # ---- adjoint row F5: full jac_x and the total derivative of tensor_map ---------------------
+    def x_size(self, nextra=0):
+        """Entries of x = ravel([u_grad, Fp_inv_old, slip_resistance_old, slip_old, rot_mat]) (models_copper.py:156), then
+        [gss_a, h, t_sat, xm, r] when nextra >= 5 (calibration form) and C (81) when nextra == 6 (DP form,
+        models_DPsteel_inhomo.py:245)."""
+        return 27 + 2 * self.g.shape[1] + (5 if nextra >= 5 else 0) + (81 if nextra >= 6 else 0)
+
+    def _x_argnums(self, nextra):
+        return (0, 1, 2, 3, 4) + ((6, 7, 8, 9, 10) if nextra >= 5 else ()) + ((11,) if nextra >= 6 else ())
+
+    def jac_x(self, u_grad, y, dt, nextra=0):
+        """jax.jacfwd(implicit_residual, argnums=0)(x, y) of f_jvp (models_copper.py:256): (n, 9, nx), columns in the
+        reference's ravel order.  rot_mat's nine entries are independent variables, like jacfwd sees them."""
+        u_grad = torch.as_tensor(u_grad, dtype=torch.float64)
+        n = self.n
+        st, pm, C = self._args(slice(None))
+        if C.dim() == 4:
+            C = C[None].expand(n, 3, 3, 3, 3)
+
+        def f(u_grad, A, g, sl, R, y, a, h, ts, xm, r, C):
+            return implicit_residual(u_grad, A, g, sl, R, y, a, h, ts, xm, r, C, self.schmid, dt, self.ao)
+        J = vmap(jacfwd(f, argnums=self._x_argnums(nextra)))(u_grad, *st, y, *pm, C)
+        return torch.cat([j.reshape(n, 9, -1) for j in J], dim=2)
+
+    def dP_dx(self, u_grad, dt, y=None, nextra=0):
+        """Total derivative of tensor_map with respect to x through the local solve (n, 9, nx): what jacfwd / vjp of
+        first_PK_stress (models_copper.py:155-162) yields with newton_solver's custom f_jvp (:251-259):
+        dP/dx = dP/dx|_y + dP/dy . dy/dx,  dy/dx = solve(jac_y, -jac_x)."""
+        u_grad = torch.as_tensor(u_grad, dtype=torch.float64)
+        if y is None:
+            y = self.newton_solver(u_grad, dt)
+        n = self.n
+        jy = self.jac_y(u_grad, y, dt)
+        jx = self.jac_x(u_grad, y, dt, nextra)
+        dy = torch.linalg.solve(jy, -jx)                                # (n, 9, nx)
+
+        def f(u_grad, A, g, sl, R, y, a, h, ts, xm, r):
+            return _pk1_from_S(u_grad, A, g, sl, R, y, a, h, ts, xm, r, self.schmid, dt, self.ao)
+        st, pm, _ = self._args(slice(None))
+        argn = tuple(a for a in self._x_argnums(nextra) if a != 11)
+        Jp = vmap(jacfwd(f, argnums=argn))(u_grad, *st, y, *pm)
+        dP_x = torch.cat([j.reshape(n, 9, -1) for j in Jp], dim=2)
+        if nextra >= 6:
+            dP_x = torch.cat([dP_x, torch.zeros(n, 9, 81)], dim=2)      # P does not depend on C at fixed y
+        dP_dy = vmap(jacfwd(f, argnums=5))(u_grad, *st, y, *pm).reshape(n, 9, 9)
+        return dP_x + dP_dy @ dy
+
     # ---- models_copper.py:164-169 -----------------------------------------------------------
     def update_int_vars(self, u_grad, dt, y=None):
         u_grad = torch.as_tensor(u_grad, dtype=torch.float64)
@@ -509,6 +559,24 @@ class FEOracle:
         Ke = onp.einsum('cqaj,cqijkl,cqbl,cq->caibk', self.shape_grads, A, self.shape_grads, self.JxW)
         V = Ke.reshape(-1)
         return res, V
+
+    def vjp_params(self, sol, params, dt, adjoint):
+        """vjp_linear_fn of implicit_vjp (crystal_plasticity_OR_design/solver.py:832-838): adjoint (nn, 3) contracted with
+        d(compute_residual)/d(internal_vars), returned as a list shaped like `params`.  The residual is linear in P with the
+        cell weights shape_grads x JxW, so the cotangent of P at a point is W_ij = sum_a adjoint[node_a, i] dN_a/dX_j JxW
+        and the rest is the per-point total derivative `PointBatch.dP_dx`."""
+        pb = self.make_batch(params)
+        nextra = {4: 0, 9: 5, 10: 6}[len(params)]
+        lam = onp.asarray(adjoint, dtype=onp.float64).reshape(self.nn, 3)[self.cells]          # (nc, 8 nodes, 3)
+        W = onp.einsum('cai,cqaj,cq->cqij', lam, self.shape_grads, self.JxW).reshape(-1, 9)
+        D = pb.dP_dx(self.u_grads(sol), dt, nextra=nextra).numpy()                              # (np, 9, nx)
+        G = onp.einsum('pi,pic->pc', W, D)[:, 9:]                                               # drop the u_grad columns
+        out, o = [], 0
+        for a in params:
+            k = int(onp.prod(a.shape[2:])) if a.ndim > 2 else 1
+            out.append(G[:, o:o + k].reshape(a.shape))
+            o += k
+        return out
 
     def compute_avg_stress(self, sol, params, dt):
         """models_copper.py:297-319."""

@@ -1,0 +1,211 @@
+"""GPU suite for the adjoint row: cpfem_point_jac_x / cpfem_point_vjp / cpfem_vjp_params /
+cpfem_csr_transpose and the implicit_vjp mirror, called through the C ABI, against the oracle's autodiff and against
+finite differences of the GPU forward solve.
+
+Reference: f_jvp's jac_x, jac_y (singlecrystal_copper/models_copper.py:251-259; polycrystal_DPsteel/models_DPsteel_inhomo.py:245)
+and implicit_vjp (crystal_plasticity_OR_design/solver.py:801-853).  Tolerance: 1e-10 of each block's largest entry for the
+Jacobians (the local solution S itself is only converged to the reference's 1e-8 on both sides, but both sides stop at the
+same iterate - the iteration counts are identical); 1e-9 for the products that go through a 9x9 solve."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import cpfem_oracle as O
+from test_adjoint_oracle import assert_blocks
+from test_solver_oracle import _clamped_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _mat(m, tol=None):
+    from cpfem_b200 import make_material
+    return make_material(m.C11, m.C12, m.C44, m.h, m.t_sat, m.gss_a, m.xm, m.r, m.ao, m.tol if tol is None else tol, m.max_sub_step)
+
+
+def _dummy_plan(slip):
+    from cpfem_b200 import Plan
+    pts, cells = O.box_mesh(1, 1, 1)
+    return Plan(cells, pts, slip)
+
+
+@pytest.mark.parametrize('name', list(cases.MATERIALS))
+def test_point_jac_x_vs_oracle(name):
+    """All columns of jac_x (51, or 75 for BCC24), jac_y and y = S from the kernel's own local solve."""
+    plan = None
+    for step, mat, dt, H, A, g, sl, R in cases.point_history(name, n=40, steps=6, seed=2):
+        if step not in (1, 4, 6):
+            continue
+        plan = plan or _dummy_plan(mat.slip)
+        pb = O.PointBatch(A, g, sl, R, mat)
+        y = pb.newton_solver(H, dt)
+        st = plan.new_status()
+        jx, jy, S = plan.point_jac_x(_mat(mat), H, [A, g, sl, R], dt, status=st)
+        assert int(st[0]) == 0 and int(st[1]) == 0
+        ns = g.shape[1]
+        assert jx.shape == (len(H), 9, 27 + 2 * ns)
+        assert cases.relerr(S.cpu().numpy(), y.numpy()) < 1e-10
+        Hh = torch.as_tensor(H)
+        assert_blocks(jx.cpu().numpy(), pb.jac_x(Hh, y, dt).numpy(), ns, 0, what=f'{name} step {step}')
+        jy_o = pb.jac_y(Hh, y, dt).numpy()
+        assert np.abs(jy.cpu().numpy() - jy_o).max() < 1e-10 * np.abs(jy_o).max()
+
+
+def _dp_points(n, seed=5):
+    params, ph, quat, ori = cases.dp_params(n, seed=seed)
+    A, g, sl, R, ga, h, ts, xm, r, C = [a[:, 0] for a in params]
+    f = O.dp_ferrite()
+    mk = lambda A_, g_, s_: O.PointBatch(A_, g_, s_, R, gss_a=ga, h=h, t_sat=ts, xm=xm, r=r, C=C, slip_table=O.SLIP_BCC24, ao=f.ao,
+                                         max_sub_step=f.max_sub_step, tol=f.tol)
+    rng = np.random.default_rng(seed + 1)
+    H = np.zeros((n, 3, 3))
+    H[:, 2, 2] = 4e-3
+    H[:, 0, 0] = H[:, 1, 1] = -1.2e-3
+    H += rng.uniform(-1, 1, size=H.shape) * 2e-4
+    An, gn, sn = mk(A, g, sl).update_int_vars(H, 0.2)
+    An, gn, sn = An.numpy(), gn.numpy(), sn.numpy()
+    return f, mk(An, gn, sn), 1.5 * H, [An, gn, sn, R, ga, h, ts, xm, r, C]
+
+
+def test_point_jac_x_dp_form_161_columns():
+    """DP form of the state (10 arrays, per-point parameters and elastic tensor): nx = 161."""
+    n = 24
+    f, pb, H, params = _dp_points(n)
+    plan = _dummy_plan(O.SLIP_BCC24)
+    y = pb.newton_solver(H, 0.2)
+    jx, jy, S = plan.point_jac_x(_mat(f), H, params, 0.2)
+    assert jx.shape == (n, 9, 161)
+    assert cases.relerr(S.cpu().numpy(), y.numpy()) < 1e-10
+    assert_blocks(jx.cpu().numpy(), pb.jac_x(torch.as_tensor(H), y, 0.2, nextra=6).numpy(), 24, 6, what='dp jac_x')
+    # reverse mode over the same 161 columns
+    W = np.random.default_rng(3).normal(size=(n, 9))
+    grad = plan.point_vjp(_mat(f), H, params, 0.2, W)
+    want = np.einsum('pi,pic->pc', W, pb.dP_dx(torch.as_tensor(H), 0.2, y, nextra=6).numpy())
+    assert_blocks(grad.cpu().numpy(), want, 24, 6, tol=1e-9, what='dp vjp')
+
+
+@pytest.mark.parametrize('name', ['copper', '304steel', 'tantalum'])
+def test_point_vjp_vs_oracle(name):
+    """W : d tensor_map / dx through the local solve; the first nine columns are W : (the consistent tangent)."""
+    rng = np.random.default_rng(11)
+    plan = None
+    for step, mat, dt, H, A, g, sl, R in cases.point_history(name, n=40, steps=5, seed=4):
+        if step != 5:
+            continue
+        plan = plan or _dummy_plan(mat.slip)
+        pb = O.PointBatch(A, g, sl, R, mat)
+        y = pb.newton_solver(H, dt)
+        W = rng.normal(size=(len(H), 9))
+        grad = plan.point_vjp(_mat(mat), H, [A, g, sl, R], dt, W).cpu().numpy()
+        D = pb.dP_dx(torch.as_tensor(H), dt, y).numpy()
+        assert_blocks(grad, np.einsum('pi,pic->pc', W, D), g.shape[1], 0, tol=1e-9, what=f'{name} vjp')
+        T = pb.tangent(H, dt, y).numpy().reshape(len(H), 9, 9)
+        assert np.abs(grad[:, :9] - np.einsum('pi,pic->pc', W, T)).max() < 1e-9 * np.abs(T).max()
+
+
+@pytest.mark.parametrize('name', ['304steel', 'copper'])
+def test_vjp_params_vs_oracle(name):
+    """vjp_linear_fn of implicit_vjp on a small distorted polycrystal mesh: nodal adjoint . d(residual)/d(internal_vars)."""
+    from cpfem_b200 import Plan
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case(name, N=2, steps=5)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    lam = np.random.default_rng(5).normal(size=(fe.nn, 3))
+    got = plan.vjp_params(_mat(mat), sol, params, dt, lam)
+    want = fe.vjp_params(sol, params, dt, lam)
+    for k, (a, b) in enumerate(zip(got, want)):
+        a = a.cpu().numpy().reshape(b.shape)
+        if np.abs(b).max() == 0.0:
+            assert np.abs(a).max() == 0.0, k
+        else:
+            assert np.abs(a - b).max() < 1e-9 * np.abs(b).max(), (k, np.abs(a - b).max() / np.abs(b).max())
+
+
+def test_vjp_params_dp_form():
+    """The same with the 10-array DP form: gradients with respect to xm and C per point, zeros for gss_a, h, t_sat, r."""
+    from cpfem_b200 import Plan
+    pts, cells = O.box_mesh(2, 2, 2)
+    rng = np.random.default_rng(8)
+    pts = pts + rng.uniform(-1, 1, size=pts.shape) * 0.02
+    params, ph, quat, ori = cases.dp_params(len(cells), seed=2)
+    f = O.dp_ferrite()
+    fe = O.FEOracle(pts, cells, O.make_dp_batch_factory(f.max_sub_step))
+    u = lambda e: np.stack([-0.3 * e * pts[:, 0], -0.3 * e * pts[:, 1], e * pts[:, 2]], 1)
+    params = fe.update_int_vars_gp(u(4e-3), params, 0.2)
+    sol = u(6e-3) + rng.uniform(-1, 1, size=pts.shape) * 1e-5
+    plan = Plan(cells, pts, O.SLIP_BCC24)
+    lam = rng.normal(size=(fe.nn, 3))
+    got = plan.vjp_params(_mat(f), sol, params, 0.2, lam)
+    want = fe.vjp_params(sol, params, 0.2, lam)
+    assert len(got) == 10
+    for k, (a, b) in enumerate(zip(got, want)):
+        a = a.cpu().numpy().reshape(b.shape)
+        if np.abs(b).max() == 0.0:
+            assert np.abs(a).max() == 0.0, k
+        else:
+            assert np.abs(a - b).max() < 1e-9 * np.abs(b).max(), (k, np.abs(a - b).max() / np.abs(b).max())
+
+
+def test_csr_transpose_vs_scipy():
+    import scipy.sparse
+    from cpfem_b200 import Plan
+    fe, mat, dt, sol, params, quat, ori = cases.small_fe_case('304steel', N=3, steps=5)
+    plan = Plan(fe.cells, fe.points, mat.slip)
+    res, data, _ = plan.newton_update(_mat(mat), sol, params, dt)
+    rows = torch.arange(0, 12, device='cuda')                                 # a few Dirichlet rows make A unsymmetric
+    plan.apply_dirichlet(rows, torch.zeros(12, dtype=torch.float64, device='cuda'), torch.as_tensor(sol, device='cuda').reshape(-1),
+                         res=res.reshape(-1), csr_data=data)
+    ip, ix = plan.csr_pattern()
+    A = scipy.sparse.csr_array((data.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(plan.ndof, plan.ndof))
+    AT = scipy.sparse.csr_array(A.T)
+    AT.sort_indices()
+    dT = plan.csr_transpose(data).cpu().numpy()
+    assert np.array_equal(AT.indices, ix.cpu().numpy()) and np.array_equal(dT, AT.data)      # a permutation: bit-exact
+
+
+def test_implicit_vjp_vs_finite_differences():
+    """implicit_vjp (solver.py:801-853) end to end on the GPU path: d(v . sol)/d(internal_vars) from one adjoint solve
+    against central differences of the full forward solve (Newton + BiCGStab) along random directions in g, Fp_inv and
+    rot_mats.  Local and global tolerances are tightened so that the forward map is smooth at the finite-difference step."""
+    from cpfem_b200.generate_mesh import Mesh
+    from cpfem_b200.models_copper import CrystalPlasticity
+    from cpfem_b200.solver import implicit_vjp, solver
+
+    class Cu(CrystalPlasticity):
+        tol = 5e-10
+
+    fe, mat, dt, deps, params_o, pts, nodes, comps, bottom, top, quat, ori = _clamped_case(2)
+    zb = lambda p: np.isclose(p[2], 0., atol=1e-9)
+    zt = lambda p: np.isclose(p[2], 1., atol=1e-9)
+    d = deps * 6
+    bc = [[zb, zb, zb, zt, zt, zt], [0, 1, 2, 0, 1, 2], [lambda p: 0.] * 5 + [lambda p: d]]
+    problem = Cu(Mesh(pts, fe.cells), vec=3, dim=3, ele_type='HEX8', dirichlet_bc_info=bc, additional_info=(quat, ori))
+    problem.dt = dt
+    opts = lambda g: {'jax_solver': {}, 'initial_guess': [g], 'tol': 1e-10, 'rel_tol': 1e-12}
+    zero = torch.zeros(fe.nn, 3, dtype=torch.float64, device='cuda')
+    # a plastically deformed state to differentiate at: two load steps
+    params = [torch.as_tensor(np.asarray(p), device='cuda') for p in problem.internal_vars]
+    problem.set_params(params)
+    sol = solver(problem, opts(zero))[0]
+    params = problem.update_int_vars_gp(sol, params)
+    bc[2][5] = lambda p: 1.5 * d
+    problem.fes[0].update_Dirichlet_boundary_conditions(bc)
+
+    def forward(p):
+        problem.set_params(p)
+        return solver(problem, opts(sol))[0]
+    sol1 = forward(params)
+    assert int(problem.last_status[2]) > 2                                    # plastic flow
+    rng = np.random.default_rng(1)
+    v = torch.as_tensor(rng.normal(size=(fe.nn, 3)), device='cuda')
+    grads = implicit_vjp(problem, [sol1], params, [v], {'jax_solver': {}})
+    assert len(grads) == 4 and all(g.shape == p.shape for g, p in zip(grads, params))
+    assert float(grads[2].abs().max()) == 0.0                                  # accumulated slip does not enter the residual
+    for k, eps in ((1, 1e-4), (0, 1e-7), (3, 1e-7)):                           # g (MPa), Fp_inv, rot_mats
+        dirn = torch.as_tensor(rng.normal(size=tuple(params[k].shape)), device='cuda')
+        up, dn = list(params), list(params)
+        up[k] = params[k] + eps * dirn
+        dn[k] = params[k] - eps * dirn
+        fd = float(((forward(up) - forward(dn)) * v).sum()) / (2 * eps)
+        an = float((grads[k] * dirn).sum())
+        print(f'implicit_vjp block {k}: adjoint {an:.8e}  central difference {fd:.8e}')
+        assert abs(fd - an) < 2e-5 * abs(an), (k, fd, an)
