@@ -183,7 +183,7 @@ def test_implicit_vjp_vs_finite_differences():
     opts = lambda g: {'jax_solver': {}, 'initial_guess': [g], 'tol': 1e-10, 'rel_tol': 1e-12}
     zero = torch.zeros(fe.nn, 3, dtype=torch.float64, device='cuda')
     # a plastically deformed state to differentiate at: two load steps
-    params = [torch.as_tensor(np.asarray(p), device='cuda') for p in problem.internal_vars]
+    params = [torch.as_tensor(p, dtype=torch.float64, device='cuda') for p in problem.internal_vars]
     problem.set_params(params)
     sol = solver(problem, opts(zero))[0]
     params = problem.update_int_vars_gp(sol, params)
@@ -203,8 +203,17 @@ def test_implicit_vjp_vs_finite_differences():
     for k, eps in ((1, 1e-4), (0, 1e-7), (3, 1e-7)):                           # g (MPa), Fp_inv, rot_mats
         dirn = torch.as_tensor(rng.normal(size=tuple(params[k].shape)), device='cuda')
         up, dn = list(params), list(params)
-        up[k] = params[k] + eps * dirn
-        dn[k] = params[k] - eps * dirn
+        if k == 3:
+            # The forward kernels work in the crystal frame and use R^T R = I, so they agree with the reference's literal
+            # formulation ON the rotation group only (cp_adjoint.cuh header): differentiate along it, R(+-eps) = exp(+-eps W) R
+            # with a random skew W per point; the direction is W R.
+            W = dirn - dirn.transpose(-1, -2)
+            up[k] = torch.linalg.matrix_exp(eps * W) @ params[k]
+            dn[k] = torch.linalg.matrix_exp(-eps * W) @ params[k]
+            dirn = W @ params[k]
+        else:
+            up[k] = params[k] + eps * dirn
+            dn[k] = params[k] - eps * dirn
         fd = float(((forward(up) - forward(dn)) * v).sum()) / (2 * eps)
         an = float((grads[k] * dirn).sum())
         print(f'implicit_vjp block {k}: adjoint {an:.8e}  central difference {fd:.8e}')
