@@ -252,6 +252,8 @@ def main():
     ap.add_argument('--n', type=int, default=MESH_N, help='mesh cells per edge (default 200 = BASELINE config)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--exchange', choices=['peer', 'nccl'], default='peer',
+                    help='multi-GPU interface exchange: peer-memory mailboxes (CUDA IPC, cpfem_peer_put; default) or NCCL send/recv')
     ap.add_argument('--overlap-exchange', action='store_true',
                     help='multi-GPU: start the interface exchange after the first assembly chunk, beside the rest (measured: no gain, see DESIGN.md)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -335,7 +337,24 @@ def main():
         ex.prepare()
         if args.overlap_exchange:
             ex.attach(plan)              # interface exchange starts after the first assembly chunk, beside the rest
-    exchange = (lambda r, c: ex.exchange_overlapped(r, c)) if (ex is not None and args.overlap_exchange) else (lambda r, c: ex.exchange(r, c))
+        elif args.exchange == 'peer':
+            # peer-memory mailboxes (CUDA IPC + cpfem_peer_* kernels); if the box refuses IPC mappings every rank falls back
+            # to the NCCL send/recv transport TOGETHER (attach_peer is collective) and the line says which one ran
+            ok = torch.ones(1, device=dev)
+            try:
+                ex.attach_peer(with_csr=True)
+            except Exception as e:                                   # noqa: BLE001
+                print(f'rank {rank}: peer-memory exchange unavailable ({e}); using NCCL send/recv', file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if not bool(ok.item()):
+                args.exchange = 'nccl'
+    if ex is not None and args.overlap_exchange:
+        exchange = lambda r, c: ex.exchange_overlapped(r, c)
+    elif ex is not None and args.exchange == 'peer':
+        exchange = lambda r, c: ex.exchange_peer(r, c)
+    else:
+        exchange = lambda r, c: ex.exchange(r, c)
     status_u = plan.new_status()
     status_a = plan.new_status()
     norm_buf = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -507,6 +526,10 @@ def main():
                        'newton_update, D2H of the residual (the CSR stays on the device for the device linear solver)'}
         del hsol, hstate, hnew, hres, dsol
 
+    if ex is not None and getattr(ex, '_peer', None) is not None:
+        peer_timeouts = ex.peer_timeouts()
+        ex.detach_peer()                         # collective: unmap the neighbours' mailboxes, free this rank's
+        assert peer_timeouts == 0, f'rank {rank}: {peer_timeouts} peer-memory waits timed out'
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -601,6 +624,8 @@ def main():
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(N),
                    'partition': f'{world} slab(s)' + (', interface exchange overlapped with the assembly (starts after the first chunk)' if (world > 1 and args.overlap_exchange) else ''), 'state_layout': args.layout,
+                   'exchange': (None if world == 1 else ('nccl send/recv (overlapped)' if args.overlap_exchange else
+                                                         ('peer-memory mailbox (CUDA IPC, cpfem_peer_put)' if args.exchange == 'peer' else 'nccl send/recv'))),
                    'l2': 'inputs (>= 2 GB of state per pass) are larger than the 126 MB L2; no flush needed',
                    'layout_ab': 'SoA (component-major) state measured slower than the reference AoS layout on B200 (update 66.8 vs '
                                 '61.1 ms at 200^3, profiles/r2/a_layout_ab.txt): 42 component streams 0.5 GB apart per warp '

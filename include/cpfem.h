@@ -247,6 +247,26 @@ int cpfem_gather(const double* src, const int64_t* map, int64_t n, double* dst, 
 /* sum of squares of a device vector into out[0] (device double, accumulated atomically; zero it first). */
 int cpfem_sumsq(const double* x, int64_t n, double* out, void* stream);
 
+/* ---- peer-memory mailbox for the interface exchange (one process per GPU, one node; csrc/cpfem_peer.cu) ------------------
+ * The reduction of SURVEY 8(e) - the reference is single-device and has no counterpart.  A mailbox is device memory of the
+ * RECEIVER that senders map through CUDA IPC and write over NVLink; flags are 64-bit epochs that only grow.
+ *   owner:   cpfem_peer_alloc -> handle (CPFEM_PEER_HANDLE_BYTES, ship it to the peers by any host channel)
+ *   sender:  cpfem_peer_open(handle) -> pointer valid in the sender's process; cpfem_peer_put copies (gathers if map != NULL)
+ *            n doubles into it and then stores `epoch` to *flag_peer (NULL: no flag) with system-scope release semantics
+ *   owner:   cpfem_peer_wait(flag, epoch) makes the stream wait until the flag has reached `epoch` (bounded by timeout_s,
+ *            default 20 s: a miss is counted in status[1] instead of hanging the device), then consumes the data with
+ *            cpfem_scatter_add and acknowledges with cpfem_peer_signal into a flag in the sender's own mailbox.
+ * All calls but alloc / open / close / free are enqueue-only. */
+#define CPFEM_PEER_HANDLE_BYTES 64
+int cpfem_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle);
+int cpfem_peer_open(const uint8_t* handle, void** ptr);
+int cpfem_peer_close(void* ptr);
+int cpfem_peer_free(void* ptr);
+int cpfem_peer_put(double* dst_peer, const double* src, const int64_t* map, int64_t n, uint64_t* flag_peer, uint64_t epoch,
+                   void* stream);
+int cpfem_peer_signal(uint64_t* flag_peer, uint64_t epoch, void* stream);
+int cpfem_peer_wait(const uint64_t* flag_local, uint64_t epoch, double timeout_s, int64_t* status, void* stream);
+
 /* Layout conversion (np, comps) <-> (comps, np). */
 int cpfem_aos_to_soa(const double* aos, int64_t np, int32_t comps, double* soa, void* stream);
 int cpfem_soa_to_aos(const double* soa, int64_t np, int32_t comps, double* aos, void* stream);

@@ -85,6 +85,13 @@ SIGNATURES = {
     'cpfem_scatter_add': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     'cpfem_gather': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     'cpfem_sumsq': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
+    'cpfem_peer_alloc': (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp), c_vp]),
+    'cpfem_peer_open': (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    'cpfem_peer_close': (ctypes.c_int, [c_vp]),
+    'cpfem_peer_free': (ctypes.c_int, [c_vp]),
+    'cpfem_peer_put': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, ctypes.c_uint64, c_vp]),
+    'cpfem_peer_signal': (ctypes.c_int, [c_vp, ctypes.c_uint64, c_vp]),
+    'cpfem_peer_wait': (ctypes.c_int, [c_vp, ctypes.c_uint64, c_dbl, c_vp, c_vp]),
     'cpfem_aos_to_soa': (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'cpfem_soa_to_aos': (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'cpfem_dfma_peak_kernel': (ctypes.c_int, [c_i64, c_vp, ctypes.POINTER(c_dbl), c_vp]),
@@ -98,7 +105,7 @@ _lock = threading.Lock()
 
 
 def sources():
-    return [os.path.join(_CSRC, 'cpfem_kernels.cu'), os.path.join(_CSRC, 'cpfem_solver.cu')]
+    return [os.path.join(_CSRC, 'cpfem_kernels.cu'), os.path.join(_CSRC, 'cpfem_solver.cu'), os.path.join(_CSRC, 'cpfem_peer.cu')]
 
 
 def needs_build():

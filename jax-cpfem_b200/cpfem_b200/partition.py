@@ -304,6 +304,111 @@ class ExchangePlan:
             csr_data.record_stream(self._comm)
         cur.wait_event(self._done)
 
+    # ---- peer-memory path (CUDA, one node): the sender stores into the owner's mailbox over NVLink --------------------
+    def attach_peer(self, with_csr=True, timeout_s=20.0):
+        """Collective.  Allocates this rank's mailbox (cpfem_peer_alloc: room for what every neighbour sends, behind two
+        arrays of 64-bit epoch flags), ships its IPC handle to the neighbours and maps theirs.  After this
+        `exchange_peer` replaces `exchange`: no NCCL call, no rendezvous, no receive-side copy - the sender's copy kernel
+        (cpfem_peer_put) writes the rows into the owner's memory and releases a flag the owner's stream waits on."""
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        from ._lib import check
+        L = _lib.lib()
+        dev = self.device
+        me, world = self.rm.rank, self.rm.world
+        self.prepare()
+        peers_s, peers_r = sorted(self.send_rows), sorted(self.recv_rows)
+        head = ((2 * world * 8 + 255) // 256) * 256                      # data flags [src], ack flags [dst]
+        off, o = {}, head // 8
+        for q in peers_r:
+            off[q] = o
+            o += self.recv_rows[q].numel() + (self.recv_slots[q].numel() if with_csr else 0)
+            o = (o + 1) & ~1                                              # 16-byte aligned segments
+        nbytes = max(o * 8, head)
+        with torch.cuda.device(dev):
+            ptr = ctypes.c_void_p()
+            hb = (ctypes.c_uint8 * 64)()
+            check(L.cpfem_peer_alloc(nbytes, ctypes.byref(ptr), hb), 'cpfem_peer_alloc')
+            mine = torch.tensor(list(hb), dtype=torch.uint8, device=dev)
+            allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allh, mine, group=self.pg)
+            # the receiver tells every sender where its segment starts
+            offs_s = {q: torch.zeros(1, dtype=torch.int64, device=dev) for q in peers_s}
+            ops = [dist.P2POp(dist.isend, torch.tensor([off[q]], dtype=torch.int64, device=dev), q, group=self.pg) for q in peers_r]
+            ops += [dist.P2POp(dist.irecv, offs_s[q], q, group=self.pg) for q in peers_s]
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            torch.cuda.synchronize()
+            remote = {}
+            for q in sorted(set(peers_s) | set(peers_r)):
+                rp = ctypes.c_void_p()
+                hq = (ctypes.c_uint8 * 64)(*allh[q].cpu().tolist())
+                check(L.cpfem_peer_open(hq, ctypes.byref(rp)), 'cpfem_peer_open')
+                remote[q] = rp.value
+            self._peer = dict(ptr=ptr.value, remote=remote, off=off, off_s={q: int(offs_s[q].item()) for q in peers_s},
+                              with_csr=with_csr, world=world, me=me, timeout=float(timeout_s),
+                              status=torch.zeros(4, dtype=torch.int64, device=dev))
+            self._epoch = 0
+            dist.barrier(group=self.pg)          # every mailbox is mapped before anybody writes
+
+    def detach_peer(self):
+        pe = getattr(self, '_peer', None)
+        if pe is None:
+            return
+        import torch.distributed as dist
+        from . import _lib
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.pg)              # nobody still writes into a mailbox that is about to go
+        L = _lib.lib()
+        for rp in pe['remote'].values():
+            L.cpfem_peer_close(rp)
+        L.cpfem_peer_free(pe['ptr'])
+        self._peer = None
+
+    def peer_timeouts(self):
+        """Number of cpfem_peer_wait calls that gave up (must be 0)."""
+        return int(self._peer['status'][1])
+
+    def exchange_peer(self, res: torch.Tensor, csr_data: Optional[torch.Tensor]):
+        """Same result as `exchange` through the mailboxes of `attach_peer` (enqueue-only, current stream)."""
+        import ctypes
+        from . import _lib
+        from ._lib import check
+        from .api import _ptr, _stream
+        L, pe = _lib.lib(), self._peer
+        assert (csr_data is not None) <= pe['with_csr'], 'attach_peer(with_csr=True) needed to ship CSR rows'
+        r = res.reshape(-1)
+        self._epoch += 1
+        e, me, W = self._epoch, pe['me'], pe['world']
+        vp = ctypes.c_void_p
+        st, to, stat = _stream(), pe['timeout'], _ptr(pe['status'])
+        with torch.cuda.device(self.device):
+            for q in sorted(self.send_rows):
+                r0, rn, s0, sn = self._s0[q]
+                rc, sc = self.send_contig[q]
+                base = pe['remote'][q]
+                dst = base + 8 * pe['off_s'][q]
+                flag = vp(base + 8 * me)                                      # data flag [src = me] in q's mailbox
+                if e > 1:                                                     # q has consumed what the last put left there
+                    check(L.cpfem_peer_wait(vp(pe['ptr'] + 8 * (W + q)), e - 1, to, stat, st), 'cpfem_peer_wait')
+                last = csr_data is None
+                check(L.cpfem_peer_put(vp(dst), vp(r.data_ptr() + 8 * r0) if rc else _ptr(r), None if rc else _ptr(self.send_rows[q]), rn,
+                                       flag if last else None, e, st), 'cpfem_peer_put')
+                if not last:
+                    check(L.cpfem_peer_put(vp(dst + 8 * rn), vp(csr_data.data_ptr() + 8 * s0) if sc else _ptr(csr_data),
+                                           None if sc else _ptr(self.send_slots[q]), sn, flag, e, st), 'cpfem_peer_put')
+            for q in sorted(self.recv_rows):
+                src = pe['ptr'] + 8 * pe['off'][q]
+                nr = self.recv_rows[q].numel()
+                check(L.cpfem_peer_wait(vp(pe['ptr'] + 8 * q), e, to, stat, st), 'cpfem_peer_wait')
+                check(L.cpfem_scatter_add(vp(src), _ptr(self.recv_rows[q]), nr, _ptr(r), st), 'cpfem_scatter_add')
+                if csr_data is not None:
+                    check(L.cpfem_scatter_add(vp(src + 8 * nr), _ptr(self.recv_slots[q]), self.recv_slots[q].numel(), _ptr(csr_data), st),
+                          'cpfem_scatter_add')
+                check(L.cpfem_peer_signal(vp(pe['remote'][q] + 8 * (W + me)), e, st), 'cpfem_peer_signal')   # ack flag [dst = me] at q
+
     def owned_sumsq(self, res: torch.Tensor, out: Optional[torch.Tensor] = None):
         """sum of squares of the residual over the rows this rank owns (device scalar)."""
         if not hasattr(self, '_s0'):

@@ -36,6 +36,7 @@
 // them from the CUDA kernels in cpfem_kernels.cu.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define CP_HD __host__ __device__ __forceinline__
@@ -55,6 +56,26 @@
 #endif
 #ifndef CP_NM_ODD1
 #define CP_NM_ODD1 0      // experiment: single-system tail in cp_newton_matrix instead of a half-empty pair
+#endif
+#ifndef CP_PRUNE
+#define CP_PRUNE 0        // experiment, off: line-search trials whose rejection is certain from tau/g alone are not evaluated
+                          // (cp_prune_setup).  Bitwise-identical results and 5.8 % fewer FP64 instructions at the 304-steel
+                          // benchmark state, but every code shape tried costs more than it saves on sm_100a: the loop sits at
+                          // the register budget, and the extra exit makes ptxas spill Fe across the line-search decision or
+                          // hoist the slip table's constant-bank operands into spilled registers (update 57.7 -> 61.4 ... 71.3 ms
+                          // at 200^3, profiles/r2/h_prune_variants.txt).  tests/test_prune_option.py keeps the path honest.
+#endif
+// X_cap of the pruning in high-word terms: X_rej = 2^k (1 + m) is skipped up to 2^k (1.5 + m), i.e. X_cap / X_rej <= 1.5
+#define CP_PRUNE_SPAN 0x80000u
+#ifndef CP_LS_SMEM
+#define CP_LS_SMEM 0      // experiment, off: accepted iterate and Newton increment of the local solve in shared memory
+                          // (24 registers of loop state): 57.7 -> 58.8 ms at 200^3, ptxas fills the 168 registers either way
+#endif
+#ifndef CP_BLOCK_THREADS
+#define CP_BLOCK_THREADS 128   // threads per block of the kernels that call cp_newton (checked in cpfem_kernels.cu)
+#endif
+#ifndef CP_TRACE_PRUNE
+#define CP_TRACE_PRUNE()       // test hook (tests only): count the skipped evaluations
 #endif
 #ifndef CP_TRACE_X
 #define CP_TRACE_X(a, ax)      // test hook (tests only): observe |tau/g| of every residual evaluation
@@ -114,6 +135,9 @@ inline bool cp_slip_init(CpSlip* sl, const double* slip6, int ns) {
             for (int j = 0; j < 3; ++j) y.M[3 * i + j] = y.d[i] * y.n[j];
         y.Et[0] = y.M[0]; y.Et[1] = y.M[4]; y.Et[2] = y.M[8];
         y.Et[3] = 0.5 * (y.M[5] + y.M[7]); y.Et[4] = 0.5 * (y.M[2] + y.M[6]); y.Et[5] = 0.5 * (y.M[1] + y.M[3]);
+        // largest |d . n| of the table (0 up to rounding for a slip table): cp_prune_setup relies on tr(d n^T) = 0
+        const double dn_ = fabs(y.d[0] * y.n[0] + y.d[1] * y.n[1] + y.d[2] * y.n[2]);
+        if (dn_ > sl->sys[0].pad[0]) sl->sys[0].pad[0] = dn_;
     }
     return true;
 }
@@ -302,6 +326,25 @@ CP_HD int cp_popc(unsigned m) {
     return __builtin_popcount(m);
 #endif
 }
+// true if `p` holds on every lane of the warp that is executing together (host: one lane)
+CP_HD bool cp_warp_all(bool p) {
+#ifdef __CUDA_ARCH__
+    return __all_sync(__activemask(), p) != 0;
+#else
+    return p;
+#endif
+}
+// High word of |x|.  Non-negative doubles order like their bit patterns, so hi(|x|) >= hi(t) is x >= t exactly when the
+// low word of t is zero - comparisons on the integer pipe instead of the FP64 pipe.
+CP_HD int cp_hi_abs(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x) & 0x7fffffff;
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    return (int)((b >> 32) & 0x7fffffff);
+#endif
+}
 
 // Power law, w and the Lp accumulation for the next U systems of the set `m` (lowest bits first; they are removed from m).
 template <int POWN, int U, class Arr>
@@ -419,6 +462,97 @@ CP_HD double cp_residual(const CpSlipRef& sl, const CpPointParams& pm, double cd
     return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + 2.0 * (r[3] * r[3] + r[4] * r[4] + r[5] * r[5]));
 }
 
+#if CP_PRUNE || CP_LS_SMEM
+// ---- experimental code shape (CP_PRUNE / CP_LS_SMEM, both off by default): pass (1) split off, skip loop ----
+// Pass (1): x_a = tau_a / g_a for every system, parked in w[a]; returns this lane's set of active systems and, in `hmax`,
+// the high word of max_a |x_a| (what the pruning of certainly rejected line-search trials looks at, cp_prune_setup).
+template <int NS, class Arr>
+CP_HD unsigned cp_slip_ratios(const CpSlipRef& sl, const CpPointParams& pm, const Arr& ginv, const Arr& w, const double* s, int& hmax) {
+    const double s3 = s[3] + s[3], s4 = s[4] + s[4], s5 = s[5] + s[5];
+    unsigned act = 0u;
+    int h = 0;
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+        const CpSlipSys& y = sl.u->sys[a];
+        const double tau = y.Et[0] * s[0] + y.Et[1] * s[1] + y.Et[2] * s[2] + y.Et[3] * s3 + y.Et[4] * s4 + y.Et[5] * s5;
+        const double x = tau * ginv[a];
+        w[a] = x;
+        CP_TRACE_X(a, fabs(x));
+        act |= (fabs(x) >= pm.x_lo ? 1u : 0u) << a;
+#if CP_PRUNE
+        const int hx = cp_hi_abs(x);
+        h = hx > h ? hx : h;
+#endif
+    }
+    hmax = h;
+    return act;
+}
+
+// Pass (2) and the rest of the evaluation; `act` from cp_slip_ratios (ignored when s_is_zero).
+template <int NS, int POWN, class Arr>
+CP_HD double cp_residual_x(const CpSlipRef& sl, const CpPointParams& pm, double cdt, const double* G, const Arr& ginv,
+                         const Arr& w, const double* s, bool s_is_zero, unsigned act, double* r, double* Fe, double* Lp,
+                         unsigned& mask, unsigned& mact) {
+    constexpr int U = 4;
+    static_assert(NS % U == 0, "slip systems are processed four at a time");
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Lp[i] = 0.0;
+    mask = 0u;
+    mact = 0u;
+    if (!s_is_zero) {
+        const double n1 = pm.n_exp - 1.0;
+        const double cn = cdt * pm.n_exp;
+        unsigned m = cp_warp_or(act);
+        mact = m;
+        // pad the set to a multiple of U (CP_TAIL2: of 2) with inactive systems (they are evaluated honestly: tiny values)
+        {
+            constexpr int PADTO = (CP_TAIL2 == 2) ? 1 : (CP_TAIL2 ? 2 : U);
+            const int k = (PADTO - (cp_popc(m) & (PADTO - 1))) & (PADTO - 1);
+            for (int i = 0; i < k; ++i) {
+                const unsigned z = ~m & ((NS == 32) ? 0xffffffffu : ((1u << NS) - 1u));
+                m |= z & (0u - z);
+            }
+        }
+        mask = m;
+        while (m) {
+#if CP_TAIL2
+            const int left = cp_popc(m);
+            if (left < 4) {
+                if (left >= 2) cp_slip_group<POWN, 2>(sl, pm, cdt, cn, n1, ginv, w, m, Lp);
+#if CP_TAIL2 == 2
+                if (left & 1) cp_slip_group<POWN, 1>(sl, pm, cdt, cn, n1, ginv, w, m, Lp);
+#endif
+                break;
+            }
+#endif
+            cp_slip_group<POWN, U>(sl, pm, cdt, cn, n1, ginv, w, m, Lp);
+        }
+    }
+    // Fe = G - G Lp
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            Fe[3 * i + j] = G[3 * i + j] - (G[3 * i] * Lp[j] + G[3 * i + 1] * Lp[3 + j] + G[3 * i + 2] * Lp[6 + j]);
+    // E2x = 2 E = Fe^T Fe - I; the 1/2 rides on the elastic constants (a multiplication by 0.5 is exact, so
+    // (C/2) (2E) == C E bit for bit) and the 2 C44 (1/2) of the shear rows cancels
+    const double E0 = Fe[0] * Fe[0] + Fe[3] * Fe[3] + Fe[6] * Fe[6] - 1.0;
+    const double E1 = Fe[1] * Fe[1] + Fe[4] * Fe[4] + Fe[7] * Fe[7] - 1.0;
+    const double E2 = Fe[2] * Fe[2] + Fe[5] * Fe[5] + Fe[8] * Fe[8] - 1.0;
+    const double E3 = Fe[1] * Fe[2] + Fe[4] * Fe[5] + Fe[7] * Fe[8];
+    const double E4 = Fe[0] * Fe[2] + Fe[3] * Fe[5] + Fe[6] * Fe[8];
+    const double E5 = Fe[0] * Fe[1] + Fe[3] * Fe[4] + Fe[6] * Fe[7];
+    const double C11h = 0.5 * pm.C11, C12h = 0.5 * pm.C12;
+    r[0] = s[0] - (C11h * E0 + C12h * (E1 + E2));
+    r[1] = s[1] - (C11h * E1 + C12h * (E0 + E2));
+    r[2] = s[2] - (C11h * E2 + C12h * (E0 + E1));
+    r[3] = s[3] - pm.C44 * E3;
+    r[4] = s[4] - pm.C44 * E4;
+    r[5] = s[5] - pm.C44 * E5;
+    return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + 2.0 * (r[3] * r[3] + r[4] * r[4] + r[5] * r[5]));
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // Newton matrix in scaled form, LU-factorised in place (no pivoting, see header comment).
 //   N = C^-1 D^-1 + sum_a w_a e_a etilde_a^T,  e_a = voigt(sym(K d_a n_a^T)), K = Fe^T G,
@@ -509,6 +643,73 @@ CP_HD void cp_compliance_neg(const CpPointParams& pm, const double* r, double* b
     b[3] = -S44h * r[3]; b[4] = -S44h * r[4]; b[5] = -S44h * r[5];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Certain rejections of the line search.  The reference's 'cut-half' search (models_copper.py:231-243) evaluates the
+// residual at y + relax inc for relax = 1, 1/2, ... and rejects a trial whose norm is not below the accepted one.  With a
+// rate exponent of 20 ... 120 most rejected trials overshoot the flow stress by more than 10 %, where the power law makes
+// the residual astronomically large (median ||crt|| / ||r|| of the rejected trials of the 304-steel benchmark state:
+// 4e9).  For such a trial the decision follows from x_a = tau_a / g_a alone (the first 84 of the ~330 FP64 instructions
+// of an evaluation), by a chain of inequalities that holds for ANY signs and magnitudes of the other slip increments:
+//   S : Lp = sum_a dgamma_a tau_a = sum_a |dgamma_a| |tau_a|          (dgamma_a and tau_a have the same sign)
+//          >= cdt X^n . X g_min,                 X = max_a |x_a|, g_min = min_a g_a
+//   ||Lp||_F >= (S : Lp) / ||S||_F =: L                                (Cauchy-Schwarz)
+//   ||I - Lp||_F^2 = 3 + ||Lp||_F^2                                    (tr(d n^T) = 0)
+//   ||Fe||_F >= sigma_min(G) ||I - Lp||_F,  sigma_min(G) >= gamma = 1 - ||G - I||_F
+//   ||2E||_F = ||Fe^T Fe - I||_F >= ||Fe||_F^2 / sqrt(3) - sqrt(3)     (Fe^T Fe is positive semi-definite)
+//   ||C : E||_F >= c_min ||E||_F,  c_min = min(C11 + 2 C12, C11 - C12, 2 C44)   (eigenvalues of a cubic C on symmetric E)
+//   ||crt|| = ||S - C : E|| >= c_min (gamma^2 L^2 - 3 (1 - gamma^2)) / (2 sqrt(3)) - ||S||
+// so the trial is rejected (||crt|| >= ||r||) as soon as X^(n+1) >= T = L_req cap / (cdt g_min), where
+//   L_req^2 = (2 sqrt(3) . 1.5 . 3 cap / c_min + 3 (1 - gamma^2)) / gamma^2
+// and `cap` bounds both ||r|| of the accepted iterate (with a factor 2 to spare for the rounding of the literal
+// evaluation) and ||S|| of the trial (<= ||y|| + ||inc||).  cap = 4 ||r(0)|| is fixed per point, so the (n+1)-th root is
+// taken once per point, before the Newton loop (its code and registers stay out of the loop); the Newton loop checks the two conditions on `cap` once per iteration and compares the high word of
+// X with one integer per trial.  Trials beyond X_cap (about 1.5 X_rej) are evaluated as before: far enough out the literal
+// evaluation overflows to inf - inf = NaN, which the reference's comparison ACCEPTS.  A skipped trial changes nothing
+// but the time: the decision, the iterates and the evaluation count (`evals` still counts it) are the reference's.
+// At the 304-steel benchmark state 3.9 of the 17.1 evaluations per point are skipped (60 % of the rejected ones).
+// ---------------------------------------------------------------------------------------------------
+struct CpPrune {
+    int lo;         // high word of X_rej, rounded up; 0x7fffffff: nothing is skipped
+    int capw;       // high word of cap: hi(v) < capw implies v < cap
+};
+template <int NS, class Arr>
+CP_HD void cp_prune_setup(const CpSlipRef& sl, const CpPointParams& pm, double cdt, const double* G, const Arr& ginv, CpPrune& pr) {
+    pr.lo = 0x7fffffff; pr.capw = 0;
+#if CP_PRUNE
+    double gi = 0.0;
+#pragma unroll 4
+    for (int a = 0; a < NS; ++a) gi = ginv[a] > gi ? ginv[a] : gi;
+    const double d0 = G[0] - 1.0, d4 = G[4] - 1.0, d8 = G[8] - 1.0;
+    const double gam = 1.0 - sqrt(d0 * d0 + d4 * d4 + d8 * d8 + G[1] * G[1] + G[2] * G[2] + G[3] * G[3] + G[5] * G[5] + G[6] * G[6] + G[7] * G[7]);
+    double cmin = pm.C11 + 2.0 * pm.C12;
+    cmin = (pm.C11 - pm.C12) < cmin ? (pm.C11 - pm.C12) : cmin;
+    cmin = (2.0 * pm.C44) < cmin ? (2.0 * pm.C44) : cmin;
+    // ||r(0)|| = ||C : 1/2 (G^T G - I)|| (what the first evaluation of the solve returns; any value of that size will do here)
+    double rn0;
+    {
+        const double E0 = G[0] * G[0] + G[3] * G[3] + G[6] * G[6] - 1.0, E1 = G[1] * G[1] + G[4] * G[4] + G[7] * G[7] - 1.0;
+        const double E2 = G[2] * G[2] + G[5] * G[5] + G[8] * G[8] - 1.0;
+        const double E3 = G[1] * G[2] + G[4] * G[5] + G[7] * G[8], E4 = G[0] * G[2] + G[3] * G[5] + G[6] * G[8];
+        const double E5 = G[0] * G[1] + G[3] * G[4] + G[6] * G[7];
+        const double a = 0.5 * pm.C11, b = 0.5 * pm.C12;
+        const double r0 = a * E0 + b * (E1 + E2), r1 = a * E1 + b * (E0 + E2), r2 = a * E2 + b * (E0 + E1);
+        rn0 = sqrt(r0 * r0 + r1 * r1 + r2 * r2 + 2.0 * (pm.C44 * pm.C44) * (E3 * E3 + E4 * E4 + E5 * E5));
+    }
+    const double cap = 4.0 * rn0;
+    const double g2 = gam * gam;
+    const double Lreq2 = (15.588457268119896 * cap / cmin + 3.0 * (1.0 - g2)) / g2;       // 2 sqrt(3) . 1.5 . 3 = 15.588...
+    const double T = sqrt(Lreq2) * cap * gi / cdt;
+    // every quantity must be an ordinary positive number, the table a slip table (d . n = 0), and cdt (1.5 X_rej)^n far from
+    // overflow: cdt X_rej^n < T cdt <= 1e30 and 1.5^n <= 1e70 for n <= 400
+    if (!(gam >= 0.5) || !(cmin > 0.0) || !(cap > 0.0) || !(gi > 0.0) || !(T < 1e300) || !(T * cdt < 1e30) || !(pm.n_exp > 1.0) ||
+        !(pm.n_exp <= 400.0) || !(sl.u->sys[0].pad[0] < 1e-12))
+        return;
+    const double X = (T > 1.0) ? exp(log(T) / (pm.n_exp + 1.0)) * (1.0 + 1e-6) : 1.0;
+    pr.lo = cp_hi_abs(X) + 1;
+    pr.capw = cp_hi_abs(cap);
+#endif
+}
+
 struct CpSolveInfo {
     int iters;      // outer Newton iterations taken
     int evals;      // residual evaluations
@@ -579,6 +780,130 @@ CP_HD void cp_newton(const CpSlipRef& sl, const CpPointParams& pm, double cdt, d
         if (!((mask >> a) & 1u)) w[a] = 0.0;
 }
 
+#if CP_PRUNE || CP_LS_SMEM
+// The same solve with the experimental switches: certainly rejected trials skipped (CP_PRUNE), loop state in shared memory
+// (CP_LS_SMEM).  Results are bitwise those of cp_newton (tests/test_prune_option.py).
+template <int NS, int POWN, class Arr>
+CP_HD void cp_newton_x(const CpSlipRef& sl, const CpPointParams& pm, double cdt, double tol, int max_sub, int max_iter,
+                     const double* G, const Arr& ginv, const Arr& w, double* s, double* Fe, double* Lp,
+                     unsigned& mask, unsigned& mact, CpSolveInfo& info) {
+    // Loop state that is touched once per evaluation - the accepted iterate y, the Newton increment, the three integers of
+    // the pruning - lives in per-thread columns of shared memory on the device: the loop sits exactly at the register
+    // budget of 3 blocks per SM (168), and every further live value makes the compiler spill a dozen doubles around the
+    // Newton matrix (three more integers: 57.7 -> 61.4 ms at 200^3).
+#if defined(__CUDA_ARCH__) && CP_LS_SMEM
+    __shared__ double cp_ls_s[12 * CP_BLOCK_THREADS];
+    double* const lss = cp_ls_s + threadIdx.x;
+#define CP_Y(i) lss[(i) * CP_BLOCK_THREADS]
+#define CP_INC(i) lss[(6 + (i)) * CP_BLOCK_THREADS]
+#else
+    double lss[12];
+#define CP_Y(i) lss[i]
+#define CP_INC(i) lss[6 + (i)]
+#endif
+#if defined(__CUDA_ARCH__) && CP_PRUNE
+    __shared__ int cp_prune_s[3 * CP_BLOCK_THREADS];
+    int* const prs = cp_prune_s + threadIdx.x;
+#define CP_PRS(i) prs[(i) * CP_BLOCK_THREADS]
+#else
+    int prs[3];
+#define CP_PRS(i) prs[i]
+#endif
+    double r[6], st[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { CP_Y(i) = 0.0; st[i] = 0.0; CP_INC(i) = 0.0; }
+    const bool zero_ok = pm.n_exp > 1.0;
+    double rn = 0.0, relax = 1.0;
+    int sub = 0;
+    bool first = true;
+    info.iters = 0; info.evals = 0; info.status = 0;
+    {
+        CpPrune pr;
+        cp_prune_setup<NS>(sl, pm, cdt, G, ginv, pr);
+        CP_PRS(0) = pr.lo; CP_PRS(1) = pr.capw; CP_PRS(2) = 0x7fffffff;
+    }
+    for (;;) {
+        unsigned act = 0u;
+        if (!(first && zero_ok)) {
+            for (;;) {
+                int hmax;
+                act = cp_slip_ratios<NS>(sl, pm, ginv, w, st, hmax);
+#if CP_PRUNE
+                // A trial whose rejection is certain (cp_prune_setup) is not evaluated any further - unless it is the last one
+                // the search allows, which is accepted whatever its norm.  Decided per warp: the evaluation is shared.
+                const int plo = (sub + 1 < max_sub) ? CP_PRS(2) : 0x7fffffff;
+                if (!cp_warp_all((unsigned)(hmax - plo) < CP_PRUNE_SPAN)) break;
+                CP_TRACE_PRUNE();
+                ++info.evals;
+                relax *= 0.5;
+                ++sub;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) st[i] = CP_Y(i) + relax * CP_INC(i);
+#else
+                break;
+#endif
+            }
+        }
+        const double crtn = cp_residual_x<NS, POWN>(sl, pm, cdt, G, ginv, w, st, first && zero_ok, act, r, Fe, Lp, mask, mact);
+        ++info.evals;
+        if (!first) {
+            relax *= 0.5;
+            ++sub;
+            if (crtn >= rn && sub < max_sub) {           // line search: next trial y + relax inc
+#pragma unroll
+                for (int i = 0; i < 6; ++i) st[i] = CP_Y(i) + relax * CP_INC(i);
+                continue;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) CP_Y(i) = st[i];    // accept: y + 2 relax inc == the point just evaluated
+            ++info.iters;
+        }
+        rn = crtn;
+        if (!(rn > tol)) break;
+        if (info.iters >= max_iter) { info.status |= 1; break; }
+        double inc[6];
+        if (first && zero_ok) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) inc[i] = -r[i];
+        } else {
+            double N[36], piv[6];
+            cp_newton_matrix<NS>(sl, pm, G, Fe, w, mact, N, piv);
+            cp_compliance_neg(pm, r, inc);
+            cp_lu_solve(N, piv, inc);
+            inc[3] *= 0.5; inc[4] *= 0.5; inc[5] *= 0.5;          // inc = D^-1 z
+        }
+        first = false;
+        relax = 1.0;
+        sub = 0;
+        // y is the point just evaluated (st) or, before the first step, 0 (also st)
+#if CP_PRUNE
+        {
+            // ||y + relax inc||_F <= ||y||_F + ||inc||_F <= the weighted 1-norms below (sqrt(2) < 1.5)
+            const double sc = (fabs(st[0]) + fabs(st[1]) + fabs(st[2]) + fabs(inc[0]) + fabs(inc[1]) + fabs(inc[2])) +
+                              1.5 * (fabs(st[3]) + fabs(st[4]) + fabs(st[5]) + fabs(inc[3]) + fabs(inc[4]) + fabs(inc[5]));
+            const int capw = CP_PRS(1);
+            CP_PRS(2) = (cp_hi_abs(rn) < capw && cp_hi_abs(sc) < capw) ? CP_PRS(0) : 0x7fffffff;
+        }
+#endif
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            CP_INC(i) = inc[i];
+            st[i] += inc[i];
+        }
+    }
+    if (!(rn == rn)) info.status |= 2;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i] = st[i];            // the accepted iterate is the point of the last evaluation
+    // systems outside the last processed set: w = 0 (the output stages read w of every system)
+#pragma unroll 4
+    for (int a = 0; a < NS; ++a)
+        if (!((mask >> a) & 1u)) w[a] = 0.0;
+#undef CP_PRS
+#undef CP_Y
+#undef CP_INC
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // Frame change helpers
 // ---------------------------------------------------------------------------------------------------
@@ -622,8 +947,13 @@ CP_HD void cp_point_solve(const CpSlipRef& sl, const CpMaterial& mat, const CpPo
 #pragma unroll 4
     for (int a = 0; a < NS; ++a) ps.ginv[a] = cp_rcp(g[a]);
     ps.cdt = mat.ao * dt;
+#if CP_PRUNE || CP_LS_SMEM
+    cp_newton_x<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp,
+                          ps.mask, ps.mact, ps.info);
+#else
     cp_newton<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp,
                         ps.mask, ps.mact, ps.info);
+#endif
 }
 
 template <class Arr>

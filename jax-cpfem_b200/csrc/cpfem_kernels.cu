@@ -539,6 +539,7 @@ __device__ __forceinline__ CpSlipRef stage_slip(const CpSlip& param, CpSlip& sh,
 #ifndef PT_MIN_BLOCKS
 #define PT_MIN_BLOCKS 3      // 3 x 128 threads x 168 registers per SM
 #endif
+static_assert(PT_BLOCK == CP_BLOCK_THREADS, "cp_newton sizes its shared-memory columns for CP_BLOCK_THREADS threads");
 typedef CpArr<PT_BLOCK> SArr;
 // layout: [w: NS][1/g: NS][tangent kernels only: CP_TANGENT_PARK - NS more rows] x PT_BLOCK columns.  1/g is dead once the
 // local solve has returned, so the tangent parks the LU factors of its Newton matrix in the 1/g rows + the extra rows.

@@ -46,6 +46,11 @@ def norm_step():
     dist.all_reduce(s, op=dist.ReduceOp.SUM)
 
 t_ex = timed(lambda: ex.exchange(res, csr))
+ex.attach_peer(with_csr=True)
+t_peer = timed(lambda: ex.exchange_peer(res, csr))
+t_peer_res = timed(lambda: ex.exchange_peer(res, None))
+n_to = ex.peer_timeouts()
+ex.detach_peer()
 t_res = timed(lambda: ex.exchange(res, None))
 t_nrm = timed(norm_step)
 t_memset = timed(lambda: csr.zero_())
@@ -55,6 +60,8 @@ if rank == 0:
     print('n = %d, %d ranks, NCCL env: %s' % (N, world, {k: v for k, v in os.environ.items() if k.startswith('NCCL_')}))
     print('exchange (residual + CSR rows): %.3f ms for up to %.1f MB sent / %.1f MB received per rank = %.0f GB/s per direction'
           % (t_ex, mx[0].item() / 1e6, mx[1].item() / 1e6, mx[0].item() / t_ex / 1e6))
+    print('peer-memory exchange (cpfem_peer_put into the owner\'s mailbox over NVLink + flag, unpack-add): %.3f ms = %.0f GB/s per direction; '
+          'residual alone %.3f ms; wait timeouts %d' % (t_peer, mx[0].item() / t_peer / 1e6, t_peer_res, n_to))
     print('exchange of the residual alone: %.3f ms; owned-row norm + all-reduce: %.3f ms; CSR zero-fill (%.2f GB): %.3f ms'
           % (t_res, t_nrm, csr.numel() * 8 / 1e9, t_memset))
 dist.barrier()

@@ -4,7 +4,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tests/multigpu_check.py
 
 Every rank assembles its slab of a 304-steel polycrystal with the CUDA path, exchanges the interface rows over NCCL
-(partition.ExchangePlan), applies the Dirichlet rows and solves the row-partitioned system with
+(partition.ExchangePlan.exchange) and through the peer-memory mailboxes (exchange_peer: CUDA IPC + cpfem_peer_* kernels), applies the Dirichlet rows and solves the row-partitioned system with
 partition.DistributedBicgstab (node-block SpMV kernel + halo exchange + all-reduced dot products).  Checked against the
 single-GPU assembly and cpfem_bicgstab of the whole mesh: CSR rows of the owned nodes to atomic-summation order, the
 Newton increment to solver tolerance, the global residual norm."""
@@ -75,6 +75,26 @@ def main():
         ex.exchange_overlapped(res2, csr2)
         e_ov = max(e_ov, float((res2 - res).abs().max() / csr.abs().max()), float((csr2 - csr).abs().max() / csr.abs().max()))
     ex.detach()
+    # the same exchange through the peer-memory mailboxes (CUDA IPC, cpfem_peer_put / _wait / _signal, no NCCL call):
+    # several epochs in a row (mailbox reuse + acknowledgement), residual-only and residual + CSR
+    ex.attach_peer(with_csr=True)
+    e_pm = 0.0
+    t_pm = []
+    for it in range(4):
+        res3, csr3, _ = plan.newton_update(mat, sol, state, 2e-3)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        ex.exchange_peer(res3, csr3)
+        t1.record()
+        torch.cuda.synchronize()
+        t_pm.append(t0.elapsed_time(t1))
+        e_pm = max(e_pm, float((res3 - res).abs().max() / csr.abs().max()), float((csr3 - csr).abs().max() / csr.abs().max()))
+    res4 = plan.residual(mat, sol, state, 2e-3)
+    ex.exchange_peer(res4, None)
+    torch.cuda.synchronize()
+    e_pm = max(e_pm, float((res4 - res).abs().max() / csr.abs().max()))
+    n_to = ex.peer_timeouts()
+    ex.detach_peer()
     if rows.numel():
         plan.apply_dirichlet(rows, vals, sol.reshape(-1), res=res.reshape(-1), csr_data=csr)
     nrm = float(ex.global_res_norm(res))
@@ -106,9 +126,9 @@ def main():
             assert a.numel() == b.numel()
             worst = max(worst, float((a - b).abs().max()))
     e_A = worst / float(gcsr.abs().max())
-    ok = e_x < 1e-8 and e_r < 1e-12 and e_A < 1e-12 and e_ov < 1e-12 and abs(nrm - gnrm) < 1e-10 * gnrm and k > 0
+    ok = e_x < 1e-8 and e_r < 1e-12 and e_A < 1e-12 and e_ov < 1e-12 and e_pm < 1e-12 and n_to == 0 and abs(nrm - gnrm) < 1e-10 * gnrm and k > 0
     print(f'rank {rank}/{world}: distributed BiCGStab {k} its (single GPU {gk}), err {err:.2e} | x {e_x:.2e}  res {e_r:.2e}  '
-          f'CSR rows {e_A:.2e}  overlapped exchange {e_ov:.2e}  ||res|| {nrm:.12e} vs {gnrm:.12e}  ->  {"OK" if ok else "FAIL"}', flush=True)
+          f'CSR rows {e_A:.2e}  overlapped exchange {e_ov:.2e}  peer-memory exchange {e_pm:.2e} ({min(t_pm):.3f} ms, {n_to} timeouts)  ||res|| {nrm:.12e} vs {gnrm:.12e}  ->  {"OK" if ok else "FAIL"}', flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.barrier()
