@@ -867,7 +867,11 @@ __device__ __forceinline__ void el_fill(uint32_t dst, uint32_t bar, const double
     }
 }
 
-__global__ void __launch_bounds__(ELEM_WARPS * 32, 1)
+#ifndef ELEM_MIN_BLOCKS
+#define ELEM_MIN_BLOCKS 1                // > 1 caps the registers so that element blocks can share an SM (with each other or,
+                                         // CPFEM_OVERLAP, with blocks of the next chunk's point kernel)
+#endif
+__global__ void __launch_bounds__(ELEM_WARPS * 32, ELEM_MIN_BLOCKS)
 k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, int64_t c0, int64_t ncc,
                   const double* __restrict__ scratch,
                   const int64_t* __restrict__ indptr, const uint8_t* __restrict__ rank, double* __restrict__ res,
