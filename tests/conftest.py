@@ -11,6 +11,7 @@ for p in (os.path.join(ROOT, 'jax-cpfem_b200'), os.path.join(ROOT, 'oracle'), os
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    config.addinivalue_line('markers', 'slow: minutes-long replays of whole committed series (enabled by CPFEM_RUN_SLOW=1)')
 
 
 def pytest_collection_modifyitems(config, items):
