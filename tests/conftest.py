@@ -11,7 +11,7 @@ for p in (os.path.join(ROOT, 'jax-cpfem_b200'), os.path.join(ROOT, 'oracle'), os
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
-    config.addinivalue_line('markers', 'slow: minutes-long replays of whole committed series (enabled by CPFEM_RUN_SLOW=1)')
+    config.addinivalue_line('markers', 'slow: replays of whole committed series (the longest GPU tests; deselect with -m "gpu and not slow")')
 
 
 def pytest_collection_modifyitems(config, items):

@@ -109,17 +109,20 @@ def test_304_steel_vtu_series():
 
 
 def test_case4_polycrystal_curve():
-    _case4_curve(12)
+    _case4_curve(12, {'jax_solver': {}})
 
 
 @pytest.mark.slow
-@pytest.mark.skipif(not os.environ.get('CPFEM_RUN_SLOW'), reason='all 80 committed load steps (minutes): set CPFEM_RUN_SLOW=1')
 def test_case4_polycrystal_curve_all_80_steps():
-    """The whole committed curve (80 load steps to 2.5 % strain); log of the last run: profiles/r2/k_case4_full_curve.txt."""
-    _case4_curve(80)
+    """The whole committed curve (80 load steps to 2.5 % strain); log of the last run: profiles/r2/k_case4_full_curve.txt.
+    The reference ran this case with its direct solver ('umfpack_solver', calibration_case4_...1D_GB.py:77): deep in the
+    plastic regime the rotation-deficient tangent makes BiCGStab break down (JAX's codes -10 / -11) before it has reduced
+    the residual at all, and the reference's own jax_solve would stop on its `err < 0.1` assertion.  The device solver is
+    therefore run with its restart option here (solver.py::jax_solve, `restarts`)."""
+    _case4_curve(80, {'jax_solver': {'restarts': 8}})
 
 
-def _case4_curve(nsteps):
+def _case4_curve(nsteps, lin):
     """calibration_case4 (calibration_case4_UQ_polyCrystalSteel_1D_GB.py:100-300): 304 steel, 20^3 cells / 50 grains, the
     9-array 'calibration' form of the state (per-point gss_a, h, t_sat, xm, r - the kernels' per-point-parameter path with
     a run-time rate exponent of 120), line search on, tol 1e-7.  Known answer: the committed mean-sigma_zz curve
@@ -153,7 +156,7 @@ def _case4_curve(nsteps):
         problem.dt = ts[i + 1] - ts[i]
         problem.fes[0].update_Dirichlet_boundary_conditions(mk(disps[i + 1]))
         problem.set_params(params)
-        sol = solver(problem, {'jax_solver': {}, 'initial_guess': [sol], 'tol': 1e-7, 'line_search_flag': True})[0]
+        sol = solver(problem, dict(lin, initial_guess=[sol], tol=1e-7, line_search_flag=True))[0]
         got.append(float(problem.compute_avg_stress(sol, params)[:, 2, 2].mean()))
         params = problem.update_int_vars_gp(sol, params)
     got = np.array(got)
