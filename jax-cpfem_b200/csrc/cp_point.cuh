@@ -72,7 +72,7 @@
                           // (24 registers of loop state): 57.7 -> 58.8 ms at 200^3, ptxas fills the 168 registers either way
 #endif
 #ifndef CP_BLOCK_THREADS
-#define CP_BLOCK_THREADS 128   // threads per block of the kernels that call cp_newton (checked in cpfem_kernels.cu)
+#define CP_BLOCK_THREADS 64    // threads per block of the kernels that call cp_newton (checked in cpfem_kernels.cu)
 #endif
 #ifndef CP_TRACE_PRUNE
 #define CP_TRACE_PRUNE()       // test hook (tests only): count the skipped evaluations

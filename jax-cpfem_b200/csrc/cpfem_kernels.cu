@@ -253,7 +253,7 @@ extern "C" int cpfem_plan_create(const int32_t* cells, int64_t nc, const double*
         PLAN_TRY(dev_alloc(&p->indices, p->nnz));
         PLAN_TRY(dev_alloc(&p->rank, nc * 64));
         // chunking: at most CPFEM_CHUNK_CELLS cells per assembly chunk (bounds the scratch), always a multiple of 16 cells
-        // (one 128-thread block of points).  The environment variable CPFEM_CHUNK_CELLS overrides the limit (tests use
+        // (two 64-thread blocks of points).  The environment variable CPFEM_CHUNK_CELLS overrides the limit (tests use
         // it to exercise the multi-chunk path on small meshes).
         {
             int64_t lim = CPFEM_CHUNK_CELLS;
@@ -521,7 +521,11 @@ __device__ __forceinline__ void warp_status(const CpSolveInfo& info, bool valid,
 // Per-point kernels: one thread per quadrature point, PT_BLOCK threads per block; the two per-slip-system arrays
 // (1/g, w) of every thread are columns of a [2][NS][PT_BLOCK] shared-memory tile.
 #ifndef PT_BLOCK
-#define PT_BLOCK 128
+#define PT_BLOCK 64          // threads per block.  12 warps per SM either way (168 registers); an SM slot is held until the slowest
+                             // warp of its block has converged, so smaller blocks keep more warps busy.  Measured on B200 at 200^3
+                             // (profiles/r2/m_variants_block_n200.txt), update / assembly ms: 32 threads x 12 blocks 59.2 / 107.2
+                             // (twelve 4.6 kB slip-table copies per SM), 64 x 6 56.5 / 97.4, 96 x 4 57.6 / 101.7, 128 x 3 57.3 / 99.2,
+                             // 192 x 2 58.3 / 97.0
 #endif
 // The slip-system records are read with data-dependent indices (only the active systems are processed), which the
 // constant bank serves slowly (LDC); every per-point kernel therefore starts by copying the table of its kernel
@@ -537,7 +541,7 @@ __device__ __forceinline__ CpSlipRef stage_slip(const CpSlip& param, CpSlip& sh,
     return r;
 }
 #ifndef PT_MIN_BLOCKS
-#define PT_MIN_BLOCKS 3      // 3 x 128 threads x 168 registers per SM
+#define PT_MIN_BLOCKS 6      // 6 x 64 threads x 168 registers per SM
 #endif
 static_assert(PT_BLOCK == CP_BLOCK_THREADS, "cp_newton sizes its shared-memory columns for CP_BLOCK_THREADS threads");
 typedef CpArr<PT_BLOCK> SArr;
