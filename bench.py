@@ -340,14 +340,10 @@ def main():
         elif args.exchange == 'peer':
             # peer-memory mailboxes (CUDA IPC + cpfem_peer_* kernels); if the box refuses IPC mappings every rank falls back
             # to the NCCL send/recv transport TOGETHER (attach_peer is collective) and the line says which one ran
-            ok = torch.ones(1, device=dev)
             try:
-                ex.attach_peer(with_csr=True)
-            except Exception as e:                                   # noqa: BLE001
+                ex.attach_peer(with_csr=True)        # votes after every step that can fail: all ranks raise together
+            except RuntimeError as e:
                 print(f'rank {rank}: peer-memory exchange unavailable ({e}); using NCCL send/recv', file=sys.stderr)
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if not bool(ok.item()):
                 args.exchange = 'nccl'
     if ex is not None and args.overlap_exchange:
         exchange = lambda r, c: ex.exchange_overlapped(r, c)

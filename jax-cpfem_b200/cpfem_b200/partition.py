@@ -18,6 +18,7 @@ cpfem_sumsq), on CPU tensors (tests only) they are torch index ops.
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Dict, List, Optional
 
 import numpy as onp
@@ -326,10 +327,32 @@ class ExchangePlan:
             o += self.recv_rows[q].numel() + (self.recv_slots[q].numel() if with_csr else 0)
             o = (o + 1) & ~1                                              # 16-byte aligned segments
         nbytes = max(o * 8, head)
+        def agree(ok, what):
+            # every step that can fail locally is followed by a vote, so that all ranks leave together (a rank that raised
+            # on its own would leave the others waiting in the next collective)
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+            if not bool(flag.item()):
+                raise RuntimeError(f'attach_peer: {what} failed on ' + ('this rank: ' + str(err[0]) if not ok else 'another rank'))
+
+        err = [None]
         with torch.cuda.device(dev):
             ptr = ctypes.c_void_p()
             hb = (ctypes.c_uint8 * 64)()
-            check(L.cpfem_peer_alloc(nbytes, ctypes.byref(ptr), hb), 'cpfem_peer_alloc')
+            try:
+                check(L.cpfem_peer_alloc(nbytes, ctypes.byref(ptr), hb), 'cpfem_peer_alloc')
+            except Exception as e:                                       # noqa: BLE001
+                err[0] = e
+            if os.environ.get('CPFEM_PEER_FAIL_RANK') == str(me):        # fault injection for tests/multigpu_check.py
+                if err[0] is None:
+                    L.cpfem_peer_free(ptr.value)
+                err[0] = RuntimeError('injected failure (CPFEM_PEER_FAIL_RANK)')
+            try:
+                agree(err[0] is None, 'mailbox allocation')
+            except RuntimeError:
+                if err[0] is None:
+                    L.cpfem_peer_free(ptr.value)
+                raise
             mine = torch.tensor(list(hb), dtype=torch.uint8, device=dev)
             allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
             dist.all_gather(allh, mine, group=self.pg)
@@ -342,11 +365,21 @@ class ExchangePlan:
                     w.wait()
             torch.cuda.synchronize()
             remote = {}
-            for q in sorted(set(peers_s) | set(peers_r)):
-                rp = ctypes.c_void_p()
-                hq = (ctypes.c_uint8 * 64)(*allh[q].cpu().tolist())
-                check(L.cpfem_peer_open(hq, ctypes.byref(rp)), 'cpfem_peer_open')
-                remote[q] = rp.value
+            try:
+                for q in sorted(set(peers_s) | set(peers_r)):
+                    rp = ctypes.c_void_p()
+                    hq = (ctypes.c_uint8 * 64)(*allh[q].cpu().tolist())
+                    check(L.cpfem_peer_open(hq, ctypes.byref(rp)), 'cpfem_peer_open')
+                    remote[q] = rp.value
+            except Exception as e:                                       # noqa: BLE001
+                err[0] = e
+            try:
+                agree(err[0] is None, 'mapping a neighbour\'s mailbox (CUDA IPC)')
+            except RuntimeError:
+                for rp in remote.values():
+                    L.cpfem_peer_close(rp)
+                L.cpfem_peer_free(ptr.value)
+                raise
             self._peer = dict(ptr=ptr.value, remote=remote, off=off, off_s={q: int(offs_s[q].item()) for q in peers_s},
                               with_csr=with_csr, world=world, me=me, timeout=float(timeout_s),
                               status=torch.zeros(4, dtype=torch.int64, device=dev))

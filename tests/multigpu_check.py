@@ -95,6 +95,15 @@ def main():
     e_pm = max(e_pm, float((res4 - res).abs().max() / csr.abs().max()))
     n_to = ex.peer_timeouts()
     ex.detach_peer()
+    # a rank that cannot set its mailbox up must take every rank out together (no rank left waiting in a collective)
+    os.environ['CPFEM_PEER_FAIL_RANK'] = str(world - 1)
+    try:
+        ex.attach_peer(with_csr=True)
+        raised = False
+    except RuntimeError:
+        raised = True
+    del os.environ['CPFEM_PEER_FAIL_RANK']
+    assert raised and getattr(ex, '_peer', None) is None, 'attach_peer: injected failure did not raise on every rank'
     if rows.numel():
         plan.apply_dirichlet(rows, vals, sol.reshape(-1), res=res.reshape(-1), csr_data=csr)
     nrm = float(ex.global_res_norm(res))
