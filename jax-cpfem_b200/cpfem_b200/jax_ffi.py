@@ -21,7 +21,8 @@ _CSRC = os.path.join(os.path.dirname(_HERE), 'csrc')
 _INCLUDE = os.path.join(os.path.dirname(os.path.dirname(_HERE)), 'include')
 FFI_LIB_PATH = os.path.join(_HERE, 'libcpfem_ffi.so')
 TARGETS = ('cpfem_update_state_ffi', 'cpfem_avg_stress_ffi', 'cpfem_update_avg_ffi', 'cpfem_residual_ffi',
-           'cpfem_newton_update_ffi', 'cpfem_point_eval_ffi', 'cpfem_dirichlet_ffi', 'cpfem_bicgstab_ffi')
+           'cpfem_newton_update_ffi', 'cpfem_point_eval_ffi', 'cpfem_dirichlet_ffi', 'cpfem_bicgstab_ffi',
+           'cpfem_point_jac_x_ffi', 'cpfem_vjp_params_ffi', 'cpfem_csr_transpose_ffi')
 
 _registered = False
 

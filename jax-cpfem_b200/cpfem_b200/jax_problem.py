@@ -13,6 +13,7 @@ Overridden (reference lines; jax_fem = deepmodeling/jax-fem, imported at models_
     update_int_vars_gp(sol, params)  models_copper.py:273-282
     compute_avg_stress(sol, params)  models_copper.py:297-319
     get_tensor_map() / get_maps()    models_copper.py:135-137, 263-271 (batched: the device kernel is the vmap)
+Added for the adjoint (implicit_vjp, solver.py:801-853): point_jacobians (f_jvp's jac_x / jac_y), vjp_params, csr_transpose.
 Added: `csr_data` (device) on `csr_indptr` / `csr_indices` (the pattern scipy would build at solver.py:281, bit for bit),
 `csr_scipy()` for L3's `get_A`, `last_status`, `keep_V` (materialise the reference's `problem.V` as well).
 
@@ -151,6 +152,46 @@ class B200HotPath:
         (models_copper.py:251-259)."""
         P, A, _, _ = self._point_eval(u_grad, state, 1)
         return P, A
+
+
+    # ---- adjoint row (SURVEY 8(f) F5): f_jvp's Jacobians and the pieces of implicit_vjp ----------------------------------
+    def point_jacobians(self, u_grad, *state):
+        """jac_x (n, 9, nx), jac_y (n, 9, 9) and y = S (n, 9) of f_jvp (models_copper.py:251-259) at the converged local
+        solution; x in the reference's ravel order (51 columns, 56 / 161 in the calibration / DP forms)."""
+        jax, jnp = _jax()
+        ug = jnp.asarray(u_grad, dtype=jnp.float64)
+        lead = ug.shape[:-2]                                   # one point, or any batch of points (like _point_eval)
+        n = int(onp.prod(lead)) if lead else 1
+        ug = ug.reshape(n, 3, 3)
+        flat = [jnp.asarray(s, dtype=jnp.float64).reshape((n,) + tuple(jnp.shape(s)[len(lead):])) for s in state]
+        ns = flat[1].shape[-1]
+        nextra = {4: 0, 9: 5, 10: 6}[len(state)]
+        nx = 27 + 2 * ns + (5 if nextra >= 5 else 0) + (81 if nextra >= 6 else 0)
+        out = (jax.ShapeDtypeStruct((n, 9, nx), jnp.float64), jax.ShapeDtypeStruct((n, 9, 9), jnp.float64),
+               jax.ShapeDtypeStruct((n, 9), jnp.float64), jax.ShapeDtypeStruct((4,), jnp.int64))
+        jx, jy, S, self.last_status = self._call('cpfem_point_jac_x_ffi', out, ug, *flat, nextra=onp.int64(nextra), **self._common())
+        return jx, jy, S
+
+    def vjp_params(self, sol, params, adjoint):
+        """adjoint (nnodes, 3) . d(compute_residual)/d(internal_vars): what `jax.vjp(partial_params_c_fn)(adjoint)` yields
+        inside implicit_vjp (crystal_plasticity_OR_design/solver.py:832-848), as a list shaped like `params`.  Zero the
+        adjoint on the Dirichlet dofs first; the caller applies implicit_vjp's final minus sign (:849)."""
+        jax, jnp = _jax()
+        sol = jnp.asarray(sol, dtype=jnp.float64)
+        adj = jnp.asarray(adjoint, dtype=jnp.float64).reshape(sol.shape)
+        shapes = [tuple(jnp.shape(p)) for p in params] + [(0,)] * (10 - len(params))
+        out = tuple(jax.ShapeDtypeStruct(s, jnp.float64) for s in shapes) + (jax.ShapeDtypeStruct((4,), jnp.int64),)
+        res = self._call('cpfem_vjp_params_ffi', out, sol, adj, *params, **self._common())
+        self.last_status = res[10]
+        return list(res[:len(params)])
+
+    def csr_transpose(self, csr_data=None):
+        """Values of A^T on the same pattern (`A.transpose()` of implicit_vjp, solver.py:844)."""
+        jax, jnp = _jax()
+        data = self.csr_data if csr_data is None else jnp.asarray(csr_data, dtype=jnp.float64)
+        ffi = jax_ffi.jax_ffi_module()
+        fn = ffi.ffi_call('cpfem_csr_transpose_ffi', jax.ShapeDtypeStruct(data.shape, jnp.float64), vmap_method='sequential')
+        return fn(data, plan=self._b200_plan.handle)
 
 
 def accelerate(reference_cls, preset):

@@ -21,6 +21,9 @@
 //                                                                        models_copper.py:135-137,155-169,251-271
 //   cpfem_dirichlet_ffi         apply_bc_vec + zeroRows                  solver.py:119-133,290-293
 //   cpfem_bicgstab_ffi          jax_solve                                solver.py:19-48
+//   cpfem_point_jac_x_ffi       f_jvp's jac_x / jac_y / y                models_copper.py:251-259
+//   cpfem_vjp_params_ffi        vjp_linear_fn of implicit_vjp            solver.py:832-848
+//   cpfem_csr_transpose_ffi     A.transpose() of implicit_vjp            solver.py:844
 // State arrays arrive in the reference's internal_vars order (models_copper.py:133: Fp_inv, slip resistance, slip,
 // rot_mats; models_DPsteel_inhomo.py:229 adds gss_a, h, t_sat, xm, r, C) as the trailing ("remaining") arguments: 4, 9
 // or 10 buffers.  Attributes: `plan` = the cpfem_plan* as int64 (created once per mesh through ctypes,
@@ -174,6 +177,39 @@ ffi::Error Bicgstab(cudaStream_t stream, int64_t plan, int64_t precond, double t
                                        tol, atol, maxiter, iters_to_enqueue, info->typed_data(), resid->typed_data(), stream));
 }
 
+// ---- adjoint row: f_jvp's Jacobians at the converged local solution ---------------------------------------------------
+// nextra = 0 / 5 / 6 selects x's trailing parameter columns (include/cpfem.h); jac_y may be a zero-size buffer
+ffi::Error PointJacX(cudaStream_t stream, int64_t plan, double dt, cpfem_material mat, int64_t nextra, F64 u_grads, F64Out jac_x,
+                     F64Out jac_y, F64Out S, S64Out status, ffi::RemainingArgs vars) {
+    cpfem_state in;
+    if (ffi::Error e = StateOf(vars, &in); e.failure()) return e;
+    if (ffi::Error e = ZeroStatus(stream, status); e.failure()) return e;
+    const int64_t np = static_cast<int64_t>(u_grads.element_count() / 9);
+    return Done("cpfem_point_jac_x",
+                cpfem_point_jac_x(PlanOf(plan), &mat, u_grads.typed_data(), np, &in, dt, static_cast<int32_t>(nextra),
+                                  jac_x->typed_data(), jac_y->element_count() > 0 ? jac_y->typed_data() : nullptr,
+                                  S->element_count() > 0 ? S->typed_data() : nullptr, status->typed_data(), stream));
+}
+
+// ---- adjoint row: nodal adjoint . d(residual)/d(internal_vars); ten result buffers in internal_vars order, zero-size
+// where the state has no such array (or the caller does not want it)
+ffi::Error VjpParams(cudaStream_t stream, int64_t plan, double dt, cpfem_material mat, F64 sol, F64 adjoint, F64Out g0, F64Out g1,
+                     F64Out g2, F64Out g3, F64Out g4, F64Out g5, F64Out g6, F64Out g7, F64Out g8, F64Out g9, S64Out status,
+                     ffi::RemainingArgs vars) {
+    cpfem_state in;
+    if (ffi::Error e = StateOf(vars, &in); e.failure()) return e;
+    if (ffi::Error e = ZeroStatus(stream, status); e.failure()) return e;
+    auto ptr = [](F64Out& b) -> double* { return b->element_count() > 0 ? b->typed_data() : nullptr; };
+    cpfem_state_grad out = {ptr(g0), ptr(g1), ptr(g2), ptr(g3), ptr(g4), ptr(g5), ptr(g6), ptr(g7), ptr(g8), ptr(g9)};
+    return Done("cpfem_vjp_params", cpfem_vjp_params(PlanOf(plan), &mat, sol.typed_data(), &in, dt, adjoint.typed_data(), &out,
+                                                      status->typed_data(), stream));
+}
+
+// ---- values of A^T on the plan's pattern -------------------------------------------------------------------------------
+ffi::Error CsrTranspose(cudaStream_t stream, int64_t plan, F64 csr_data, F64Out csr_data_T) {
+    return Done("cpfem_csr_transpose", cpfem_csr_transpose(PlanOf(plan), csr_data.typed_data(), csr_data_T->typed_data(), stream));
+}
+
 }  // namespace
 
 #define CPFEM_COMMON_ATTRS() \
@@ -202,3 +238,12 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(cpfem_bicgstab_ffi, Bicgstab,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<int64_t>("plan").Attr<int64_t>("precond")
                                   .Attr<double>("tol").Attr<double>("atol").Attr<int64_t>("maxiter").Attr<int64_t>("iters_to_enqueue")
                                   .Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<ffi::Buffer<ffi::S64>>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(cpfem_point_jac_x_ffi, PointJacX,
+                              ffi::Ffi::Bind().CPFEM_COMMON_ATTRS().Attr<int64_t>("nextra").Arg<F64>().Ret<F64>().Ret<F64>().Ret<F64>()
+                                  .Ret<ffi::Buffer<ffi::S64>>().RemainingArgs());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(cpfem_vjp_params_ffi, VjpParams,
+                              ffi::Ffi::Bind().CPFEM_COMMON_ATTRS().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>()
+                                  .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<ffi::Buffer<ffi::S64>>()
+                                  .RemainingArgs());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(cpfem_csr_transpose_ffi, CsrTranspose,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<int64_t>("plan").Arg<F64>().Ret<F64>());
