@@ -6,6 +6,8 @@ Reference: f_jvp's jac_x, jac_y (singlecrystal_copper/models_copper.py:251-259; 
 and implicit_vjp (crystal_plasticity_OR_design/solver.py:801-853).  Tolerance: 1e-10 of each block's largest entry for the
 Jacobians (the local solution S itself is only converged to the reference's 1e-8 on both sides, but both sides stop at the
 same iterate - the iteration counts are identical); 1e-9 for the products that go through a 9x9 solve."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -218,3 +220,42 @@ def test_implicit_vjp_vs_finite_differences():
         an = float((grads[k] * dirn).sum())
         print(f'implicit_vjp block {k}: adjoint {an:.8e}  central difference {fd:.8e}')
         assert abs(fd - an) < 2e-5 * abs(an), (k, fd, an)
+
+
+def test_adjoint_kernels_vs_host_header_large():
+    """5 x 10^4 points of the 304-steel set driven into plastic flow on the GPU, then f_jvp's Jacobians and the per-point VJP
+    from the kernels (cpfem_point_jac_x / cpfem_point_vjp: the kernel's own local solve, S back to the lab frame, dual-number
+    columns) against the host build of the same header evaluated at the kernel's S (tests/hostcheck, all host cores).  Same
+    algebra, different arithmetic details: every block to 1e-10 of its largest entry.  A check of the kernels' indexing and
+    per-thread plumbing at scale; the algebra itself is pinned on the oracle by the tests above."""
+    import hostcheck_build
+    from test_adjoint_oracle import host_jac, host_vjp
+    lib = hostcheck_build.load()
+    hostcheck_build.set_threads(lib, os.cpu_count() or 1)
+    n = 50_000
+    mat = O.steel304()
+    plan, m = _dummy_plan(mat.slip), _mat(mat)
+    rng = np.random.default_rng(21)
+    R = O.get_rot_mat(cases.rand_quat(rng, n))
+    A = torch.eye(3, dtype=torch.float64, device='cuda').repeat(n, 1, 1)
+    g = torch.full((n, 12), mat.gss_initial, dtype=torch.float64, device='cuda')
+    sl = torch.zeros(n, 12, dtype=torch.float64, device='cuda')
+    Rd = torch.as_tensor(R, device='cuda')
+    dt = 2e-3
+    mkH = lambda s: (np.diag([-0.3, -0.3, 1.0])[None] * (2e-4 * s) + rng.uniform(-1, 1, size=(n, 3, 3)) * 2e-5)
+    for s in range(1, 9):
+        A, g, sl = plan.point_update_state(m, mkH(s), [A, g, sl, Rd], dt)
+    H = mkH(9)
+    st = plan.new_status()
+    jx, jy, S = plan.point_jac_x(m, H, [A, g, sl, Rd], dt, status=st)
+    W = rng.normal(size=(n, 9))
+    grad = plan.point_vjp(m, H, [A, g, sl, Rd], dt, W)
+    torch.cuda.synchronize()
+    assert int(st[0]) == 0 and int(st[1]) == 0 and int(st[3]) > 6 * n          # plastic: > 6 local iterations per point
+    Ah, gh, Sh = A.cpu().numpy(), g.cpu().numpy(), S.cpu().numpy()
+    pp = np.tile([mat.C11, mat.C12, mat.C44, mat.xm], (n, 1))
+    jx_h, jy_h, dPx, dPs = host_jac(lib, mat, dt, H, Ah, gh, R, Sh, pp, 0, 0)
+    assert_blocks(jx.cpu().numpy(), jx_h, 12, 0, what='jac_x vs host header')
+    assert np.abs(jy.cpu().numpy() - jy_h).max() < 1e-10 * np.abs(jy_h).max()
+    grad_h = host_vjp(lib, mat, dt, H, Ah, gh, R, Sh, pp, W, 0)
+    assert_blocks(grad.cpu().numpy(), grad_h, 12, 0, tol=1e-9, what='vjp vs host header')
