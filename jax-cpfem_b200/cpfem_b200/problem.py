@@ -203,12 +203,14 @@ class Problem:
     def csr_pattern(self):
         return self.plan.csr_pattern()
 
-    def csr_scipy(self):
-        """Assembled tangent as a scipy CSR (host copy) - what get_A builds at solver.py:281."""
+    def csr_scipy(self, data=None):
+        """Assembled tangent as a scipy CSR (host copy) - what get_A builds at solver.py:281.  `data`: other values on the
+        same pattern (e.g. the transposed ones of implicit_vjp)."""
         import scipy.sparse
         ip, ix = self.plan.csr_pattern()
         n = self.num_total_dofs_all_vars
-        return scipy.sparse.csr_array((self.csr_data.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(n, n))
+        data = self.csr_data if data is None else data
+        return scipy.sparse.csr_array((data.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(n, n))
 
     # ---- the two assembly entry points ---------------------------------------------------------
     def newton_update(self, sol_list):

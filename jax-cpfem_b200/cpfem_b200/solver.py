@@ -97,7 +97,7 @@ def jax_solve(problem, A, b, x0, precond, restarts=0):
 def umfpack_solve(problem, A, b):
     """solver.py:50-61 (host, scipy): kept for tests and tiny problems."""
     import scipy.sparse.linalg
-    Asp = problem.csr_scipy()
+    Asp = problem.csr_scipy(A)                   # the values handed in (get_A's, or their transpose in implicit_vjp)
     x = scipy.sparse.linalg.spsolve(Asp.tocsc(), b.cpu().numpy())
     return torch.as_tensor(x, device=problem.device)
 

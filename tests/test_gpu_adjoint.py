@@ -220,6 +220,12 @@ def test_implicit_vjp_vs_finite_differences():
         an = float((grads[k] * dirn).sum())
         print(f'implicit_vjp block {k}: adjoint {an:.8e}  central difference {fd:.8e}')
         assert abs(fd - an) < 2e-5 * abs(an), (k, fd, an)
+    # the reference's own choice for this step (calibration_case4_...1D_GB.py:90: adjoint_solver_options={'umfpack_solver': {}}):
+    # a direct solve of the TRANSPOSED system must give the same gradients as the device BiCGStab
+    problem.set_params(params)
+    grads_d = implicit_vjp(problem, [sol1], params, [v], {'umfpack_solver': {}})
+    for k in (0, 1, 3):
+        assert float((grads_d[k] - grads[k]).abs().max()) < 1e-6 * float(grads[k].abs().max()), k
 
 
 def test_adjoint_kernels_vs_host_header_large():
