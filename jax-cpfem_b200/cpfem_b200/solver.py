@@ -11,6 +11,7 @@ BiCGStab (`cpfem_bicgstab`) where it lies instead of building a scipy/PETSc matr
     apply_bc_vec / get_A                     solver.py:119-133, 279-293  (one kernel: cpfem_apply_dirichlet)
 
     implicit_vjp                             solver.py:801-853  (adjoint solve on A^T + the parameter VJP kernel, row F5)
+    ad_wrapper                               solver.py:856-874  (torch.autograd.Function instead of jax.custom_vjp)
 
 Out of scope here: arc-length, dynamic relaxation, PETSc, P_mat constraints.
 """
@@ -205,3 +206,36 @@ def implicit_vjp(problem, sol_list, params, v_list, adjoint_solver_options=None)
         lam[rows] = 0.0
     grads = problem.vjp_params(sol_list[0], params, problem.unflatten_fn_sol_list(lam)[0])
     return [-g for g in grads]
+
+
+def ad_wrapper(problem, solver_options=None, adjoint_solver_options=None):
+    """solver.py:856-874: `fwd_pred(params) -> sol_list`, differentiable with respect to `params` by the adjoint method.
+    The reference wraps the forward solve in `jax.custom_vjp`; the mirror wraps it in a `torch.autograd.Function` whose
+    backward is `implicit_vjp` (one transposed linear solve + the per-point parameter VJP kernel), so that
+    `torch.autograd.grad(objective(fwd_pred(params)[0]), params)` works on the device tensors.  Like the reference's, the
+    wrapper differentiates the SOLVE only: what a driver does with `sol` afterwards (compute_avg_stress,
+    update_int_vars_gp) runs on the kernels and is outside torch's tape."""
+    solver_options = {} if solver_options is None else solver_options
+    adjoint_solver_options = {} if adjoint_solver_options is None else adjoint_solver_options
+
+    class _FwdPred(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, *params):
+            plist = [p.detach() for p in params]
+            problem.set_params(plist)
+            sol_list = solver(problem, dict(solver_options))
+            ctx.plist, ctx.sol_list = plist, [s.detach() for s in sol_list]
+            return tuple(sol_list)
+
+        @staticmethod
+        def backward(ctx, *v_list):
+            logger.info('Running backward and solving the adjoint problem...')
+            v = [torch.zeros_like(s) if g is None else g for g, s in zip(v_list, ctx.sol_list)]
+            grads = implicit_vjp(problem, ctx.sol_list, ctx.plist, v, dict(adjoint_solver_options))
+            return tuple(grads)
+
+    def fwd_pred(params):
+        params = [api._dev_f64(p, problem.device) for p in params]
+        return list(_FwdPred.apply(*params))
+
+    return fwd_pred

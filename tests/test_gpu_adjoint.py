@@ -220,6 +220,15 @@ def test_implicit_vjp_vs_finite_differences():
         an = float((grads[k] * dirn).sum())
         print(f'implicit_vjp block {k}: adjoint {an:.8e}  central difference {fd:.8e}')
         assert abs(fd - an) < 2e-5 * abs(an), (k, fd, an)
+    # ad_wrapper (solver.py:856-874): the same gradients through torch's tape
+    from cpfem_b200.solver import ad_wrapper
+    fwd_pred = ad_wrapper(problem, opts(sol), {'jax_solver': {}})
+    leaves = [p.clone().requires_grad_(True) for p in params]
+    J = (fwd_pred(leaves)[0] * v).sum()
+    auto = torch.autograd.grad(J, leaves)
+    for k in (0, 1, 3):
+        assert float((auto[k] - grads[k]).abs().max()) < 1e-9 * float(grads[k].abs().max()), k
+    assert float(auto[2].abs().max()) == 0.0
     # the reference's own choice for this step (calibration_case4_...1D_GB.py:90: adjoint_solver_options={'umfpack_solver': {}}):
     # a direct solve of the TRANSPOSED system must give the same gradients as the device BiCGStab
     problem.set_params(params)
