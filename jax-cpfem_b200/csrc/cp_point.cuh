@@ -71,6 +71,9 @@
 #define CP_LS_SMEM 0      // experiment, off: accepted iterate and Newton increment of the local solve in shared memory
                           // (24 registers of loop state): 57.7 -> 58.8 ms at 200^3, ptxas fills the 168 registers either way
 #endif
+#ifndef CP_G_SMEM
+#define CP_G_SMEM 0       // experiment, off: G = Fc Ac of the local solve read from shared memory inside the loop (18 registers)
+#endif
 #ifndef CP_BLOCK_THREADS
 #define CP_BLOCK_THREADS 64    // threads per block of the kernels that call cp_newton (checked in cpfem_kernels.cu)
 #endif
@@ -183,6 +186,13 @@ template <int STRIDE>
 struct CpArr {
     double* p;
     CP_HD double& operator[](int a) const { return p[a * STRIDE]; }
+};
+
+// read-only view of a small per-thread vector: plain array (stride 1) or a shared-memory column
+template <int STRIDE>
+struct CpVec {
+    const double* p;
+    CP_HD double operator[](int i) const { return p[i * STRIDE]; }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -462,7 +472,7 @@ CP_HD double cp_residual(const CpSlipRef& sl, const CpPointParams& pm, double cd
     return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + 2.0 * (r[3] * r[3] + r[4] * r[4] + r[5] * r[5]));
 }
 
-#if CP_PRUNE || CP_LS_SMEM
+#if CP_PRUNE || CP_LS_SMEM || CP_G_SMEM
 // ---- experimental code shape (CP_PRUNE / CP_LS_SMEM, both off by default): pass (1) split off, skip loop ----
 // Pass (1): x_a = tau_a / g_a for every system, parked in w[a]; returns this lane's set of active systems and, in `hmax`,
 // the high word of max_a |x_a| (what the pruning of certainly rejected line-search trials looks at, cp_prune_setup).
@@ -489,8 +499,8 @@ CP_HD unsigned cp_slip_ratios(const CpSlipRef& sl, const CpPointParams& pm, cons
 }
 
 // Pass (2) and the rest of the evaluation; `act` from cp_slip_ratios (ignored when s_is_zero).
-template <int NS, int POWN, class Arr>
-CP_HD double cp_residual_x(const CpSlipRef& sl, const CpPointParams& pm, double cdt, const double* G, const Arr& ginv,
+template <int NS, int POWN, class Arr, class GT>
+CP_HD double cp_residual_x(const CpSlipRef& sl, const CpPointParams& pm, double cdt, const GT& G, const Arr& ginv,
                          const Arr& w, const double* s, bool s_is_zero, unsigned act, double* r, double* Fe, double* Lp,
                          unsigned& mask, unsigned& mact) {
     constexpr int U = 4;
@@ -559,11 +569,14 @@ CP_HD double cp_residual_x(const CpSlipRef& sl, const CpPointParams& pm, double 
 //   etilde_a = voigt(sym(d_a n_a^T))   (strain-like: shear entries carry the 1/2)
 // After the call N holds L (unit lower) and U; piv[i] = 1/U_ii.
 // ---------------------------------------------------------------------------------------------------
-template <int NS, class Arr>
-CP_HD void cp_newton_matrix(const CpSlipRef& sl, const CpPointParams& pm, const double* G, const double* Fe,
+template <int NS, class Arr, class GT>
+CP_HD void cp_newton_matrix(const CpSlipRef& sl, const CpPointParams& pm, const GT& G, const double* Fe,
                             const Arr& w, unsigned mask, double* N /*36*/, double* piv /*6*/) {
     double K[9];
-    m3_mul_tn(Fe, G, K);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) K[3 * i + j] = Fe[i] * G[j] + Fe[3 + i] * G[3 + j] + Fe[6 + i] * G[6 + j];      // K = Fe^T G
     const double S11 = pm.S11, S12 = pm.S12, S44q = 0.5 * pm.S44h;
 #pragma unroll
     for (int i = 0; i < 36; ++i) N[i] = 0.0;
@@ -780,12 +793,12 @@ CP_HD void cp_newton(const CpSlipRef& sl, const CpPointParams& pm, double cdt, d
         if (!((mask >> a) & 1u)) w[a] = 0.0;
 }
 
-#if CP_PRUNE || CP_LS_SMEM
+#if CP_PRUNE || CP_LS_SMEM || CP_G_SMEM
 // The same solve with the experimental switches: certainly rejected trials skipped (CP_PRUNE), loop state in shared memory
 // (CP_LS_SMEM).  Results are bitwise those of cp_newton (tests/test_prune_option.py).
 template <int NS, int POWN, class Arr>
 CP_HD void cp_newton_x(const CpSlipRef& sl, const CpPointParams& pm, double cdt, double tol, int max_sub, int max_iter,
-                     const double* G, const Arr& ginv, const Arr& w, double* s, double* Fe, double* Lp,
+                     double* G, const Arr& ginv, const Arr& w, double* s, double* Fe, double* Lp,
                      unsigned& mask, unsigned& mact, CpSolveInfo& info) {
     // Loop state that is touched once per evaluation - the accepted iterate y, the Newton increment, the three integers of
     // the pruning - lives in per-thread columns of shared memory on the device: the loop sits exactly at the register
@@ -808,6 +821,14 @@ CP_HD void cp_newton_x(const CpSlipRef& sl, const CpPointParams& pm, double cdt,
 #else
     int prs[3];
 #define CP_PRS(i) prs[i]
+#endif
+#if defined(__CUDA_ARCH__) && CP_G_SMEM
+    __shared__ double cp_g_s[9 * CP_BLOCK_THREADS];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cp_g_s[i * CP_BLOCK_THREADS + threadIdx.x] = G[i];
+    const CpVec<CP_BLOCK_THREADS> Gv = {cp_g_s + threadIdx.x};
+#else
+    const CpVec<1> Gv = {G};
 #endif
     double r[6], st[6];
 #pragma unroll
@@ -844,7 +865,7 @@ CP_HD void cp_newton_x(const CpSlipRef& sl, const CpPointParams& pm, double cdt,
 #endif
             }
         }
-        const double crtn = cp_residual_x<NS, POWN>(sl, pm, cdt, G, ginv, w, st, first && zero_ok, act, r, Fe, Lp, mask, mact);
+        const double crtn = cp_residual_x<NS, POWN>(sl, pm, cdt, Gv, ginv, w, st, first && zero_ok, act, r, Fe, Lp, mask, mact);
         ++info.evals;
         if (!first) {
             relax *= 0.5;
@@ -867,7 +888,7 @@ CP_HD void cp_newton_x(const CpSlipRef& sl, const CpPointParams& pm, double cdt,
             for (int i = 0; i < 6; ++i) inc[i] = -r[i];
         } else {
             double N[36], piv[6];
-            cp_newton_matrix<NS>(sl, pm, G, Fe, w, mact, N, piv);
+            cp_newton_matrix<NS>(sl, pm, Gv, Fe, w, mact, N, piv);
             cp_compliance_neg(pm, r, inc);
             cp_lu_solve(N, piv, inc);
             inc[3] *= 0.5; inc[4] *= 0.5; inc[5] *= 0.5;          // inc = D^-1 z
@@ -894,6 +915,10 @@ CP_HD void cp_newton_x(const CpSlipRef& sl, const CpPointParams& pm, double cdt,
     if (!(rn == rn)) info.status |= 2;
 #pragma unroll
     for (int i = 0; i < 6; ++i) s[i] = st[i];            // the accepted iterate is the point of the last evaluation
+#if defined(__CUDA_ARCH__) && CP_G_SMEM
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] = Gv[i];            // the caller's copy was dead during the loop (no registers held)
+#endif
     // systems outside the last processed set: w = 0 (the output stages read w of every system)
 #pragma unroll 4
     for (int a = 0; a < NS; ++a)
@@ -947,7 +972,7 @@ CP_HD void cp_point_solve(const CpSlipRef& sl, const CpMaterial& mat, const CpPo
 #pragma unroll 4
     for (int a = 0; a < NS; ++a) ps.ginv[a] = cp_rcp(g[a]);
     ps.cdt = mat.ao * dt;
-#if CP_PRUNE || CP_LS_SMEM
+#if CP_PRUNE || CP_LS_SMEM || CP_G_SMEM
     cp_newton_x<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp,
                           ps.mask, ps.mact, ps.info);
 #else

@@ -540,6 +540,12 @@ __device__ __forceinline__ CpSlipRef stage_slip(const CpSlip& param, CpSlip& sh,
     r.d = &sh;
     return r;
 }
+// PT_MAXNREG (experiments): an explicit register cap instead of the blocks-per-SM bound (ptxas picks 128 for 7 blocks of 64)
+#ifdef PT_MAXNREG
+#define PT_KERNEL_ATTR __maxnreg__(PT_MAXNREG)
+#else
+#define PT_KERNEL_ATTR __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
+#endif
 #ifndef PT_MIN_BLOCKS
 #define PT_MIN_BLOCKS 6      // 6 x 64 threads x 168 registers per SM
 #endif
@@ -589,7 +595,7 @@ __device__ __forceinline__ void solve_point(const StateView& st, const CpMateria
 // K1: state update
 // -----------------------------------------------------------------------------------------------
 template <int NS, int POWN, bool PP>
-__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
+__global__ void PT_KERNEL_ATTR
 k_update_state(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
                StateView st, cpfem_state_out out, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip, double dt,
                int64_t np, int64_t cell0, double* __restrict__ sigma_cell, long long* status) {
@@ -672,7 +678,7 @@ template <int NS>
 static constexpr size_t residual_smem() { return point_smem<NS>() + sizeof(double) * (PT_BLOCK / 32) * 4 * (GN_CELL + PJ_CELL); }
 
 template <int NS, int POWN, bool PP>
-__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
+__global__ void PT_KERNEL_ATTR
 k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
            StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip, double dt, int64_t nc,
            double* __restrict__ res, long long* status) {
@@ -742,7 +748,7 @@ k_residual(const int32_t* __restrict__ cells, const double* __restrict__ points,
 //   PJ[9][npc]  = P_ij JxW          TA[81][npc] = dP_ij/dH_kl JxW        (npc = points in the chunk)
 // -----------------------------------------------------------------------------------------------
 template <int NS, int POWN, bool PP>
-__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
+__global__ void PT_KERNEL_ATTR
 k_point_tangent(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
                 StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip, double dt, int64_t np, int64_t p0,
                 int64_t npc, double* __restrict__ scratch, long long* status,
@@ -1145,7 +1151,7 @@ k_element_tangent(const int32_t* __restrict__ cells, const double* __restrict__ 
 // K5: average Cauchy stress per cell (models_copper.py:297-319)
 // -----------------------------------------------------------------------------------------------
 template <int NS, int POWN, bool PP>
-__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
+__global__ void PT_KERNEL_ATTR
 k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ points, const double* __restrict__ sol,
              StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip, double dt, int64_t np,
              double* __restrict__ sigma_cell, long long* status) {
@@ -1198,7 +1204,7 @@ k_avg_stress(const int32_t* __restrict__ cells, const double* __restrict__ point
 // tensor_map on explicit u_grads (and its jacfwd)
 // -----------------------------------------------------------------------------------------------
 template <int NS, int POWN, bool PP>
-__global__ void __launch_bounds__(PT_BLOCK, PT_MIN_BLOCKS)
+__global__ void PT_KERNEL_ATTR
 k_point_eval(const double* __restrict__ u_grads, StateView st, const __grid_constant__ KMat km, const __grid_constant__ CpSlip slip,
              double dt, int64_t np, double* __restrict__ Pout, double* __restrict__ Aout, cpfem_state_out sout,
              int32_t* __restrict__ point_info, long long* status) {
@@ -1555,9 +1561,8 @@ static int update_state_impl(const cpfem_plan* plan, const cpfem_material* mat, 
     const KMat km = make_kmat(m);
 #define CALL(NS, PW, PPV)                                                                                                   \
     CU_TRY(allow_smem(k_update_state<NS, PW, PPV>, update_smem<NS>()));                                                     \
-    k_update_state<NS, PW, PPV><<<grid, PT_BLOCK, update_smem<NS>(), stream>>>(plan->cells, plan->points, sol, v, *out, km, \
-                                                                          plan->slip, dt, np, cell0, sigma_cell,       \
-                                                                          (long long*)status)
+    k_update_state<NS, PW, PPV><<<grid, PT_BLOCK, sigma_cell ? update_smem<NS>() : point_smem<NS>(), stream>>>(             \
+        plan->cells, plan->points, sol, v, *out, km, plan->slip, dt, np, cell0, sigma_cell, (long long*)status)
     CP_DISPATCH(plan->ns, rate_pown(m, v), per_point(v), CALL);
     LAUNCHED(1);
 #undef CALL
