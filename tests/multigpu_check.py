@@ -61,7 +61,22 @@ def main():
         return plan, sol, res, csr, rows, vals, state
 
     # ---- partitioned ----
-    rm = slab_partition_structured(N, world, rank)
+    # CHECK_GENERIC=1: the same mesh with its node ids permuted, cut by partition_cells - interface rows and CSR slots are
+    # then NOT contiguous ranges, which exercises the gather path of the exchange (cpfem_gather / the map of cpfem_peer_put)
+    generic = bool(os.environ.get('CHECK_GENERIC'))
+    if generic:
+        from cpfem_b200.partition import partition_cells
+        from cpfem_b200.generate_mesh import box_mesh
+        mm = box_mesh(N, N, N, 1., 1., 1.)
+        perm = np.random.default_rng(5).permutation(len(mm.points))          # new id of old node i = perm[i]
+        gpts = np.empty_like(mm.points)
+        gpts[perm] = mm.points
+        gcells = perm[mm.cells_dict['hexahedron']]
+        noise_all = np.ascontiguousarray(noise_all[np.argsort(perm)])         # noise follows the node, not the id
+        part = lambda w, r: partition_cells(gcells, gpts, w, r)
+    else:
+        part = lambda w, r: slab_partition_structured(N, w, r)
+    rm = part(world, rank)
     plan, sol, res, csr, rows, vals, state = build(rm)
     ip, ix = plan.csr_pattern()
     ex = ExchangePlan(rm, ip, ix)
@@ -115,7 +130,7 @@ def main():
     x, k, err = solver.solve(lambda v: plan.spmv(csr, v), -res.reshape(-1), minv=minv, tol=1e-10, atol=1e-10, maxiter=10000)
 
     # ---- whole mesh on this GPU ----
-    whole = slab_partition_structured(N, 1, 0)
+    whole = part(1, 0)
     gplan, gsol, gres, gcsr, grows, gvals, _ = build(whole)
     gplan.apply_dirichlet(grows, gvals, gsol.reshape(-1), res=gres.reshape(-1), csr_data=gcsr)
     gx, gk, gerr = gplan.bicgstab(gcsr, -gres.reshape(-1))
@@ -136,7 +151,7 @@ def main():
             worst = max(worst, float((a - b).abs().max()))
     e_A = worst / float(gcsr.abs().max())
     ok = e_x < 1e-8 and e_r < 1e-12 and e_A < 1e-12 and e_ov < 1e-12 and e_pm < 1e-12 and n_to == 0 and abs(nrm - gnrm) < 1e-10 * gnrm and k > 0
-    print(f'rank {rank}/{world}: distributed BiCGStab {k} its (single GPU {gk}), err {err:.2e} | x {e_x:.2e}  res {e_r:.2e}  '
+    print(f'rank {rank}/{world}{" (generic partition, permuted node ids)" if generic else ""}: distributed BiCGStab {k} its (single GPU {gk}), err {err:.2e} | x {e_x:.2e}  res {e_r:.2e}  '
           f'CSR rows {e_A:.2e}  overlapped exchange {e_ov:.2e}  peer-memory exchange {e_pm:.2e} ({min(t_pm):.3f} ms, {n_to} timeouts)  ||res|| {nrm:.12e} vs {gnrm:.12e}  ->  {"OK" if ok else "FAIL"}', flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
