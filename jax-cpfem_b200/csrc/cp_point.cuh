@@ -71,6 +71,10 @@
 #define CP_LS_SMEM 0      // experiment, off: accepted iterate and Newton increment of the local solve in shared memory
                           // (24 registers of loop state): 57.7 -> 58.8 ms at 200^3, ptxas fills the 168 registers either way
 #endif
+#ifndef CP_PEEL
+#define CP_PEEL 0         // experiment: the evaluation at y = 0 peeled out of the Newton loop (1), and the leading trials of the
+                          // FIRST line search that are certainly rejected skipped before the loop is entered (2); see cp_newton_p
+#endif
 #ifndef CP_G_SMEM
 #define CP_G_SMEM 0       // experiment, off: G = Fc Ac of the local solve read from shared memory inside the loop (18 registers)
 #endif
@@ -793,6 +797,138 @@ CP_HD void cp_newton(const CpSlipRef& sl, const CpPointParams& pm, double cdt, d
         if (!((mask >> a) & 1u)) w[a] = 0.0;
 }
 
+#if CP_PEEL
+// The same solve with its first evaluation peeled off.  At y = 0 (rate exponent > 1) every tau, dgamma and w vanishes, so the
+// evaluation is Fe = G, Lp = 0, r = -C : 1/2 (G^T G - I) and the first Newton step is inc = -r: done before the loop, which then
+// needs neither the `first` flag nor the zero-stress path of cp_residual.  CP_PEEL == 2 also decides the leading trials of
+// the first line search before the loop: they sit at relax inc with relax = 1, 1/2, ..., so tau_a / g_a of trial j is
+// 2^-j x that of the full step EXACTLY, and the chain of inequalities of cp_prune_setup (||r|| = ||r(0)|| and
+// ||S|| <= ||inc|| = ||r(0)|| hold by construction) tells which of them are certainly rejected: their evaluations are
+// counted and skipped.  This is per lane - a lane only enters the loop further along its own path - and bitwise neutral.
+template <int NS, int POWN, class Arr>
+CP_HD void cp_newton_p(const CpSlipRef& sl, const CpPointParams& pm, double cdt, double tol, int max_sub, int max_iter,
+                       const double* G, const Arr& ginv, const Arr& w, double* s, double* Fe, double* Lp,
+                       unsigned& mask, unsigned& mact, CpSolveInfo& info) {
+    double r[6], st[6], inc[6];
+    info.iters = 0; info.evals = 0; info.status = 0;
+    double rn, relax = 1.0;
+    int sub = 0;
+    bool go = true;
+    if (pm.n_exp > 1.0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { Lp[i] = 0.0; Fe[i] = G[i]; }
+        mask = 0u; mact = 0u;
+        const double E0 = Fe[0] * Fe[0] + Fe[3] * Fe[3] + Fe[6] * Fe[6] - 1.0;
+        const double E1 = Fe[1] * Fe[1] + Fe[4] * Fe[4] + Fe[7] * Fe[7] - 1.0;
+        const double E2 = Fe[2] * Fe[2] + Fe[5] * Fe[5] + Fe[8] * Fe[8] - 1.0;
+        const double E3 = Fe[1] * Fe[2] + Fe[4] * Fe[5] + Fe[7] * Fe[8];
+        const double E4 = Fe[0] * Fe[2] + Fe[3] * Fe[5] + Fe[6] * Fe[8];
+        const double E5 = Fe[0] * Fe[1] + Fe[3] * Fe[4] + Fe[6] * Fe[7];
+        const double C11h = 0.5 * pm.C11, C12h = 0.5 * pm.C12;
+        r[0] = 0.0 - (C11h * E0 + C12h * (E1 + E2));
+        r[1] = 0.0 - (C11h * E1 + C12h * (E0 + E2));
+        r[2] = 0.0 - (C11h * E2 + C12h * (E0 + E1));
+        r[3] = 0.0 - pm.C44 * E3;
+        r[4] = 0.0 - pm.C44 * E4;
+        r[5] = 0.0 - pm.C44 * E5;
+        rn = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + 2.0 * (r[3] * r[3] + r[4] * r[4] + r[5] * r[5]));
+        info.evals = 1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = 0.0;
+        if (!(rn > tol)) go = false;
+        else if (info.iters >= max_iter) { info.status |= 1; go = false; }
+        else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) inc[i] = -r[i];
+#if CP_PEEL >= 2
+            // which of the trials relax = 1, 1/2, ... are certainly rejected (see cp_prune_setup for the inequalities)
+            {
+                double gi = 0.0, X1 = 0.0;
+                const double i3 = inc[3] + inc[3], i4 = inc[4] + inc[4], i5 = inc[5] + inc[5];
+#pragma unroll
+                for (int a = 0; a < NS; ++a) {
+                    const CpSlipSys& y = sl.u->sys[a];
+                    const double tau = y.Et[0] * inc[0] + y.Et[1] * inc[1] + y.Et[2] * inc[2] + y.Et[3] * i3 + y.Et[4] * i4 + y.Et[5] * i5;
+                    const double ga = ginv[a];
+                    const double x = fabs(tau * ga);
+                    X1 = x > X1 ? x : X1;
+                    gi = ga > gi ? ga : gi;
+                }
+                const double d0 = G[0] - 1.0, d4 = G[4] - 1.0, d8 = G[8] - 1.0;
+                const double gam = 1.0 - sqrt(d0 * d0 + d4 * d4 + d8 * d8 + G[1] * G[1] + G[2] * G[2] + G[3] * G[3] + G[5] * G[5] + G[6] * G[6] + G[7] * G[7]);
+                double cmin = pm.C11 + 2.0 * pm.C12;
+                cmin = (pm.C11 - pm.C12) < cmin ? (pm.C11 - pm.C12) : cmin;
+                cmin = (2.0 * pm.C44) < cmin ? (2.0 * pm.C44) : cmin;
+                // here ||r|| of the accepted iterate = ||S|| bound = rn (the trial stresses are relax inc, ||inc|| = rn), so the
+                // requirement c_min (gam^2 L^2 - 3 (1 - gam^2)) / (2 sqrt 3) >= 2 ||r|| + ||S|| reads, with 1.5 to spare,
+                const double g2 = gam * gam;
+                const double Lreq2 = (15.588457268119896 * rn / cmin + 3.0 * (1.0 - g2)) / g2;       // 2 sqrt(3) . 1.5 . 3
+                // L >= cdt X^(n+1) g_min / ||S||, ||S|| <= relax rn  =>  certain if X^(n+1) >= L_req relax rn / (cdt g_min); the
+                // left side of trial j is X1^(n+1) 2^(-j (n+1)), the right side T 2^-j
+                double T = sqrt(Lreq2) * rn * gi / cdt * (1.0 + 1e-6);
+                double ax[1] = {X1}, pw[1];
+                cp_rate_pow<POWN, 1>(ax, pm.n_exp - 1.0, pw);
+                double pX = pw[0] * X1 * X1;                                                    // X1^(n+1)
+                const double hn = exp2(-(pm.n_exp + 1.0));
+                const bool usable = (gam >= 0.5) && (cmin > 0.0) && (gi > 0.0) && (T < 1e300) && (sl.u->sys[0].pad[0] < 1e-12);
+                // a trial whose slip increments could overflow the literal evaluation (inf - inf = NaN, which the reference's
+                // comparison ACCEPTS) is evaluated: cdt X^n < 1e60 <= X^(n+1) < 1e60 X / cdt, and X >= 1 wherever pX >= T > 1
+                while (usable && sub + 1 < max_sub && pX >= T && T > 1.0 && pX * cdt < 1e60) {
+                    CP_TRACE_PRUNE();
+                    relax *= 0.5;
+                    ++sub;
+                    ++info.evals;
+                    pX *= hn;
+                    T *= 0.5;
+                }
+            }
+#endif
+#pragma unroll
+            for (int i = 0; i < 6; ++i) st[i] = 0.0 + relax * inc[i];      // s + relax inc with s = +0.0, like the loop forms it
+        }
+    } else {
+        // rate exponent <= 1: the evaluation at y = 0 is an ordinary one; a NaN norm makes the loop accept it whatever it gives
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { s[i] = 0.0; st[i] = 0.0; inc[i] = 0.0; }
+        rn = nan("");
+        info.iters = -1;
+    }
+    while (go) {
+        const double crtn = cp_residual<NS, POWN>(sl, pm, cdt, G, ginv, w, st, false, r, Fe, Lp, mask, mact);
+        ++info.evals;
+        relax *= 0.5;
+        ++sub;
+        if (crtn >= rn && sub < max_sub) {               // line search: next trial y + relax inc
+#pragma unroll
+            for (int i = 0; i < 6; ++i) st[i] = s[i] + relax * inc[i];
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = st[i];        // accept: y + 2 relax inc == the point just evaluated
+        ++info.iters;
+        rn = crtn;
+        if (!(rn > tol)) break;
+        if (info.iters >= max_iter) { info.status |= 1; break; }
+        {
+            double N[36], piv[6];
+            cp_newton_matrix<NS>(sl, pm, G, Fe, w, mact, N, piv);
+            cp_compliance_neg(pm, r, inc);
+            cp_lu_solve(N, piv, inc);
+            inc[3] *= 0.5; inc[4] *= 0.5; inc[5] *= 0.5;          // inc = D^-1 z
+        }
+        relax = 1.0;
+        sub = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) st[i] = s[i] + inc[i];
+    }
+    if (!(rn == rn)) info.status |= 2;
+    // systems outside the last processed set: w = 0 (the output stages read w of every system)
+#pragma unroll 4
+    for (int a = 0; a < NS; ++a)
+        if (!((mask >> a) & 1u)) w[a] = 0.0;
+}
+#endif
+
 #if CP_PRUNE || CP_LS_SMEM || CP_G_SMEM
 // The same solve with the experimental switches: certainly rejected trials skipped (CP_PRUNE), loop state in shared memory
 // (CP_LS_SMEM).  Results are bitwise those of cp_newton (tests/test_prune_option.py).
@@ -972,7 +1108,10 @@ CP_HD void cp_point_solve(const CpSlipRef& sl, const CpMaterial& mat, const CpPo
 #pragma unroll 4
     for (int a = 0; a < NS; ++a) ps.ginv[a] = cp_rcp(g[a]);
     ps.cdt = mat.ao * dt;
-#if CP_PRUNE || CP_LS_SMEM || CP_G_SMEM
+#if CP_PEEL
+    cp_newton_p<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp,
+                          ps.mask, ps.mact, ps.info);
+#elif CP_PRUNE || CP_LS_SMEM || CP_G_SMEM
     cp_newton_x<NS, POWN>(sl, pm, ps.cdt, mat.tol, mat.max_sub_step, mat.max_iter, ps.G, ps.ginv, ps.w, ps.s, ps.Fe, ps.Lp,
                           ps.mask, ps.mact, ps.info);
 #else
